@@ -1,0 +1,152 @@
+/* scmc.h -- C ABI of libscmc_b200.so: the B200-native Metropolis / simulated-annealing sweep for su(4)
+ * product-state spin-valley models, a drop-in for that ONE path of lgresista/SemiClassicalMC.jl.
+ *
+ * The reference (Julia, single-threaded CPU) has no FFI seam; the seam is its exported Julia API
+ * (src/SemiClassicalMC.jl:19-87).  Each entry point below names the reference function(s) it replaces
+ * (paths relative to /root/reference/).  A Julia `ccall` shim (julia/SemiClassicalMCB200.jl) and the Python
+ * `ctypes` mirror (semiclassicalmc.jl_b200/) bind exactly these symbols; see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns int32 status: 0 = ok, < 0 = error (text via scmc_last_error(), thread-local);
+ *  - the caller owns all host pointers; the library owns device memory behind the opaque handle;
+ *  - a handle is bound to one CUDA device and is NOT thread-safe; calls are synchronous on return unless noted;
+ *  - all host-side reals are FP64; `precision` selects device storage/arithmetic (32: FP32 state + FP64 accumulators);
+ *  - sites are numbered 0-based in the caller's order (the library permutes internally, colour-major);
+ *  - matrices are C order (row-major): J[label][a][b] = J^{ab}  (T_i^a J^{ab} T_j^b, i = bond source);
+ *    generators g[a][j][k] = G^a_{jk}.  Julia callers pass `permutedims` of their column-major arrays;
+ *  - "replica" = one independent Configuration (temperature point / restart / copy); `replica_offset` is the
+ *    global id of this handle's replica 0 and only enters the random stream, so results do not depend on how
+ *    replicas are sharded over GPUs.
+ *  - there is no CPU fallback: without a CUDA device every compute entry fails with SCMC_ERR_CUDA.
+ */
+#ifndef SCMC_H
+#define SCMC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scmc_handle scmc_t;
+
+enum {
+    SCMC_OK = 0,
+    SCMC_ERR_ARG = -1,      /* invalid argument / inconsistent tables (e.g. J_label(j->i) != J_label(i->j)^T) */
+    SCMC_ERR_CUDA = -2,     /* CUDA runtime error (including "no device") */
+    SCMC_ERR_UNSUPPORTED = -3,
+    SCMC_ERR_ALLOC = -4
+};
+
+#define SCMC_NOBS 21 /* per-replica measurement row: E/N, (E/N)^2, |m_sigma|, |m_tau|, |m_sigmatau|, m[16]  (measure!, ObservablesGeneric.jl:32-46) */
+
+/* ---- library-level ---------------------------------------------------------------------------------------------- */
+const char* scmc_last_error(void);
+int32_t scmc_version(void);
+int32_t scmc_device_count(int32_t* n);
+
+/* ---- Configuration (struct Configuration + constructor, src/Configuration.jl:2-77; tables from src/Models.jl:23-113) */
+int32_t scmc_create(scmc_t** h, int32_t device, int32_t precision /* 32 | 64 */, int64_t n_sites, int32_t d /* 4 | 6 */,
+                    int64_t n_replicas, int64_t replica_offset, int32_t z_max,
+                    const int32_t* nbr_site /* [N][z_max], 0-based, -1 = padding  (interactionSites,  Configuration.jl:46-47) */,
+                    const int32_t* nbr_label /* [N][z_max], 0-based               (interactionLabels, Configuration.jl:48)    */,
+                    int32_t n_labels, const double* J /* [n_labels][16][16]       (interactions,      Configuration.jl:12)    */,
+                    const double* K /* [16] on-site couplings                     (onsiteInteraction, Configuration.jl:13)    */,
+                    const double* gen_re, const double* gen_im /* [16][d][d]      (getGenerators(n),  Generators.jl:2-23)     */,
+                    const double* gensq_re, const double* gensq_im /* [16][d][d]  (gen .^ 2,          Configuration.jl:52)    */,
+                    const int32_t* colour /* [N] graph colouring or NULL -> greedy */);
+int32_t scmc_destroy(scmc_t* h);
+/* Use an existing CUDA stream (cudaStream_t as void*) for all launches/copies of this handle; NULL = legacy default stream. */
+int32_t scmc_set_stream(scmc_t* h, void* cuda_stream);
+/* info[0]=n_colours, [1]=generator table id (1,2,3), [2]=device bytes allocated, [3]=resident-kernel eligible (0/1),
+ * [4]=cluster size of the resident kernel, [5]=kernel launches issued so far, [6]=n_sites, [7]=n_replicas */
+int32_t scmc_info(scmc_t* h, int64_t* info8);
+
+/* cfg.state (Configuration.jl:17); layout [count][N][d], the d x N complex matrix of IO.jl:146-150 per replica */
+int32_t scmc_set_state(scmc_t* h, int64_t replica0, int64_t count, const double* re, const double* im);
+int32_t scmc_get_state(scmc_t* h, int64_t replica0, int64_t count, double* re, double* im);
+/* Haar-random product state on every site of every replica (getRandomState, MonteCarlo.jl:244-246; Configuration.jl:62) */
+int32_t scmc_randomize(scmc_t* h, uint64_t seed);
+/* cfg.spinExpectation / spinSqExpectation of one replica, [N][16] each; Tsq may be NULL (Configuration.jl:18-19, 65-66) */
+int32_t scmc_get_T(scmc_t* h, int64_t replica, double* T, double* Tsq);
+
+/* ---- energies ----------------------------------------------------------------------------------------------------- */
+/* getEnergy (Configuration.jl:236-253) for every replica: E[R] (total energy, not per site) */
+int32_t scmc_energy(scmc_t* h, double* E);
+/* parity probe: h_i^a = sum_j J_{label(i,j)}^{ab} T_j^b for one replica, [N][16] (inner sum of getEnergyDifference!, Configuration.jl:292-296) */
+int32_t scmc_local_field(scmc_t* h, int64_t replica, double* hfield);
+
+/* ---- local update (localUpdate!, MonteCarlo.jl:263-286) ------------------------------------------------------------- */
+/* One update of one site with injected randoms: xi[2d] = d real-part then d imaginary-part normals (getRandomState!,
+ * MonteCarlo.jl:249-260), u = the uniform of the acceptance test `rand() < exp(-beta dE)` (MonteCarlo.jl:277-278). */
+int32_t scmc_update_deterministic(scmc_t* h, int64_t replica, int64_t site, const double* xi, double u, double beta,
+                                  double sigma, double* dE, int32_t* accepted);
+/* One colour-ordered sweep (colours ascending; `hits` consecutive updates per site visit) of all replicas with injected
+ * randoms: xi [hits][R][N][2d], u [hits][R][N]; outputs accept [hits][R][N] (0/1) and dE [hits][R][N] (may be NULL). */
+int32_t scmc_sweep_deterministic(scmc_t* h, int32_t hits, const double* beta /* [R] */, const double* sigma /* [R] */,
+                                 const double* xi, const double* u, uint8_t* accept, double* dE);
+/* n_sweeps colour-ordered sweeps driven by the counter-based stream ("stream v1"): the 2N-update loops of
+ * run!/runAnnealing! (MonteCarlo.jl:40-44, 76-80, 152-156) with hits = 2.  sweep_counter = index of the first sweep
+ * (visit number = sweep * hits + hit).  accepted/attempted: [R] totals over the call (may be NULL). */
+int32_t scmc_sweep(scmc_t* h, int64_t n_sweeps, int32_t hits, const double* beta /* [R] */, const double* sigma /* [R] */,
+                   uint64_t seed, uint64_t sweep_counter, int64_t* accepted, int64_t* attempted);
+/* Same, but betas/sigmas stay as last set and nothing is copied back (for graphs / async pipelines). */
+int32_t scmc_sweep_async(scmc_t* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter);
+/* kernel selection for scmc_sweep: 0 = auto, 1 = streaming colour-pass kernels, 2 = replica-resident cluster kernel;
+ * batch = replicas per L2-resident batch for the streaming path (0 = all at once). */
+int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch);
+
+/* ---- observables (measure!, ObservablesGeneric.jl:32-46; getMagnetization, Observables.jl:16-18) -------------------- */
+/* obs [R][SCMC_NOBS]; E is re-summed from the configuration */
+int32_t scmc_measure(scmc_t* h, double* obs);
+/* S^a(k) = |sum_i T_i^a exp(i k.r_i)|^2 / n_rs for every replica: equals computeStructureFactorVec(getCorrelations(...))
+ * (Observables.jl:22-41, 116-128) on the allowed momenta of the periodic cluster.  ks [nk][dim], pos [N][dim], out [R][16][nk]. */
+int32_t scmc_structure_factor(scmc_t* h, const double* ks, const double* pos, int32_t nk, int32_t dim, double n_rs, double* Sak);
+/* getCorrelations (Observables.jl:22-41) of one replica for a caller-supplied project map [N][N] (0-based), C [16][n_rs] */
+int32_t scmc_correlations(scmc_t* h, int64_t replica, const int32_t* project, int64_t n_rs, double* C);
+
+/* ---- drivers -------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t n_therm;            /* N_therm  (run!, MonteCarlo.jl:3-18) */
+    int64_t n_measure;          /* N_measure */
+    int64_t measurement_rate;   /* default 10 */
+    int32_t hits;               /* updates per site visit; 2 reproduces the reference's 2N updates per sweep */
+    int32_t reserved;
+    uint64_t seed;
+    uint64_t sweep0;            /* current_sweep (resume) */
+    const double* T;            /* [R] target temperatures */
+    const double* T_i;          /* [R] initial temperatures of the thermalisation ramp */
+    double* sigma;              /* [R] in/out cone widths (default 60.0) */
+} scmc_run_params;
+typedef struct {
+    double* series;             /* [n_rows][R][SCMC_NOBS] measurement rows (caller-allocated, n_rows >= n_measure/measurement_rate) or NULL */
+    int64_t n_rows;             /* out: rows written */
+    double* mean;               /* [R][SCMC_NOBS] out: means over the measurement rows, or NULL */
+    double* acc_rate;           /* [R] out: acceptance rate over the measurement phase, or NULL */
+    double* therm_energy;       /* [n_therm/measurement_rate][R] E/N logged at sigma-adaptation points (push!, MonteCarlo.jl:48-49) or NULL */
+} scmc_run_results;
+/* run! (MonteCarlo.jl:3-108) for all replicas at once: 3/4 geometric ramp T_i -> T, sigma adaptation every measurement_rate
+ * sweeps during thermalisation (min(sigma * 0.5 / (1 - R), 60)), then measurement sweeps with measure! every measurement_rate. */
+int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_results* out);
+
+typedef struct {
+    double T_i, T_fac;          /* runAnnealing! kwargs (MonteCarlo.jl:112-129) */
+    int64_t N_max, N_per_T, min_acc_per_site;
+    double min_accrate, sigma_min, sigma0;
+    int32_t hits, reserved;
+    uint64_t seed;
+} scmc_anneal_params;
+typedef struct {
+    double* E;                  /* [R] final energies (total) */
+    double* beta;               /* [R] final inverse temperatures */
+    double* sigma;              /* [R] final cone widths */
+    int64_t* sweeps;            /* [R] annealing sweeps performed per replica */
+} scmc_anneal_results;
+/* cooling loop of runAnnealing! (MonteCarlo.jl:131-204), every replica with its own beta / sigma / stopping flag */
+int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results* out);
+/* optimisation sweeps (localOptimization!, MonteCarlo.jl:214-225, 289-329): colour-ordered; every site is moved to the
+ * minimiser of its local energy <psi|H_loc|psi> (the fixed point of the reference's per-site gradient descent). E [R] or NULL. */
+int32_t scmc_optimize(scmc_t* h, int64_t n_sweeps, double* E);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCMC_H */

@@ -1,0 +1,207 @@
+// device_core.cuh -- per-site arithmetic shared by every kernel of libscmc_b200 (sm_100a).
+//
+// What it replaces in the reference (paths relative to /root/reference/):
+//   stream_v1            <- randn!(local_rng(), ...) / rand()      src/MonteCarlo.jl:255-256, 278   (Philox4x32-10, counter based)
+//   propose              <- getRandomState!                         src/MonteCarlo.jl:249-260
+//   GenOps<>::expect     <- computeSpinExpectation!                 src/Configuration.jl:166-194     (sparse, unrolled, in registers)
+//   metropolis_hit       <- localUpdate! + getEnergyDifference!     src/MonteCarlo.jl:263-286, src/Configuration.jl:278-298
+//   field_from_sums      <- the per-neighbour exchangeEnergy mat-vecs src/Configuration.jl:199-218, 292-296, regrouped as
+//                           h = sum_l J_l (sum_{j in label l} T_j) so that ONE 16x16 mat-vec per label serves all hits of a visit.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "gen_code.h"
+
+namespace scmc {
+
+constexpr int NG = 16;        // number of generators
+constexpr int MAXC = 8;       // max colours
+constexpr int MAXL = 3;       // max coupling labels handled by the unrolled kernels
+constexpr uint64_t VISIT_INIT = (1ull << 60) - 1;  // reserved visit number of scmc_randomize
+
+template <class R> struct V4;
+template <> struct V4<float> { using type = float4; };
+template <> struct V4<double> { using type = double4; };
+template <class R> using vec4 = typename V4<R>::type;
+
+template <class R> __device__ __forceinline__ vec4<R> make_v4(R a, R b, R c, R d);
+template <> __device__ __forceinline__ float4 make_v4<float>(float a, float b, float c, float d) { return make_float4(a, b, c, d); }
+template <> __device__ __forceinline__ double4 make_v4<double>(double a, double b, double c, double d) { return make_double4(a, b, c, d); }
+
+// ------------------------------------------------------------------------------------------------ generator ops
+template <int GEN> struct GenOps;
+template <> struct GenOps<1> {
+    static constexpr int D = 4;
+    template <class R> static __device__ __forceinline__ void expect(const R* re, const R* im, R* T) { gen::spin_expect_g1(re, im, T); }
+    template <class R> static __device__ __forceinline__ void expect_sq(const R* re, const R* im, R* T) { gen::spin_expect_sq_g1(re, im, T); }
+    template <class R, bool O> static __device__ __forceinline__ void hloc(const R* h, const R* K, R* Hr, R* Hi) { gen::hloc_g1<R, O>(h, K, Hr, Hi); }
+};
+template <> struct GenOps<2> {
+    static constexpr int D = 6;
+    template <class R> static __device__ __forceinline__ void expect(const R* re, const R* im, R* T) { gen::spin_expect_g2(re, im, T); }
+    template <class R> static __device__ __forceinline__ void expect_sq(const R* re, const R* im, R* T) { gen::spin_expect_sq_g2(re, im, T); }
+    template <class R, bool O> static __device__ __forceinline__ void hloc(const R* h, const R* K, R* Hr, R* Hi) { gen::hloc_g2<R, O>(h, K, Hr, Hi); }
+};
+template <> struct GenOps<3> {
+    static constexpr int D = 4;
+    template <class R> static __device__ __forceinline__ void expect(const R* re, const R* im, R* T) { gen::spin_expect_g3(re, im, T); }
+    template <class R> static __device__ __forceinline__ void expect_sq(const R* re, const R* im, R* T) { gen::spin_expect_sq_g3(re, im, T); }
+    template <class R, bool O> static __device__ __forceinline__ void hloc(const R* h, const R* K, R* Hr, R* Hi) { gen::hloc_g3<R, O>(h, K, Hr, Hi); }
+};
+
+// ------------------------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// math flavours: FP32 uses the SFU approximations (MUFU.LG2/SIN/COS/EX2/RSQ), FP64 the accurate library routines
+__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& g0, float& g1) {
+    const float u1 = (float)((wa >> 8) + 1u) * 5.9604644775390625e-08f;   // (0,1]
+    const float ang = (float)(wb >> 8) * (6.283185307179586f * 5.9604644775390625e-08f);
+    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));           // sqrt(-2 ln u1)
+    float s, c;
+    __sincosf(ang, &s, &c);
+    g0 = r * c; g1 = r * s;
+}
+__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, double& g0, double& g1) {
+    const double u1 = (double)((wa >> 8) + 1u) * (1.0 / 16777216.0);
+    const double u2 = (double)(wb >> 8) * (1.0 / 16777216.0);
+    const double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    g0 = r * c; g1 = r * s;
+}
+__device__ __forceinline__ float unit_uniform(uint32_t x, float) { return __uint2float_rz(x) * 2.3283064365386963e-10f; }
+__device__ __forceinline__ double unit_uniform(uint32_t x, double) { return (double)x * (1.0 / 4294967296.0); }
+__device__ __forceinline__ float fast_exp(float x) { return __expf(x); }
+__device__ __forceinline__ double fast_exp(double x) { return exp(x); }
+__device__ __forceinline__ float inv_sqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double inv_sqrt(double x) { return 1.0 / sqrt(x); }
+
+// "stream v1": the random numbers of update number `visit` of (site, replica).  xr/xi = real / imaginary normals.
+template <class R, int D>
+__device__ __forceinline__ void stream_v1(uint64_t seed, uint32_t site, uint32_t replica, uint64_t visit, R* xr, R* xi, R& u) {
+    constexpr int NCALL = (2 * D + 3) / 4;
+    uint32_t w[4 * NCALL];
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t vlo = (uint32_t)visit, vhi = (uint32_t)(visit >> 32) << 4;
+#pragma unroll
+    for (int call = 0; call < NCALL; call++) {
+        uint32_t c0 = site, c1 = replica, c2 = vlo, c3 = vhi | (uint32_t)call;
+        philox4x32_10(c0, c1, c2, c3, k0, k1);
+        w[4 * call + 0] = c0; w[4 * call + 1] = c1; w[4 * call + 2] = c2; w[4 * call + 3] = c3;
+    }
+#pragma unroll
+    for (int m = 0; m < D; m++) box_muller(w[2 * m], w[2 * m + 1], xr[m], xi[m]);
+    const uint32_t x = (w[0] & 0xFFu) | ((w[2] & 0xFFu) << 8) | ((w[4] & 0xFFu) << 16) | ((w[6] & 0xFFu) << 24);
+    u = unit_uniform(x, R(0));
+}
+
+// ------------------------------------------------------------------------------------------------ local field
+// h^a = sum_l sum_b J_l^{ab} S_l^b ; J in kernel-parameter (constant-bank) space so the FMAs take it as an operand.
+template <class R, int NL>
+struct Couplings {
+    R J[NL][NG * NG];
+    R K[NG];
+};
+template <class R, int NL>
+__device__ __forceinline__ void field_from_sums(const Couplings<R, NL>& cp, const R (*S)[NG], R* h) {
+#pragma unroll
+    for (int a = 0; a < NG; a++) {
+        R acc = R(0);
+#pragma unroll
+        for (int l = 0; l < NL; l++)
+#pragma unroll
+            for (int b = 0; b < NG; b++) acc = fma(cp.J[l][a * NG + b], S[l][b], acc);
+        h[a] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ one Metropolis hit
+// State of the visited site lives in registers: psi (re, im), T, (Tsq).  Returns true when the proposal was accepted.
+template <class R, int GEN, bool ONSITE>
+__device__ __forceinline__ bool metropolis_hit(R* re, R* im, R* T, R* Tsq, const R* h, const R* K, const R* xr, const R* xi,
+                                               R u, R beta, R sigma, R& dE_out) {
+    constexpr int D = GenOps<GEN>::D;
+    R nre[D], nim[D], nT[NG], nTsq[NG];
+    R n2 = R(0);
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        nre[k] = fma(sigma, xr[k], re[k]);
+        nim[k] = fma(sigma, xi[k], im[k]);
+        n2 = fma(nre[k], nre[k], n2);
+        n2 = fma(nim[k], nim[k], n2);
+    }
+    const R inv = inv_sqrt(n2);
+#pragma unroll
+    for (int k = 0; k < D; k++) { nre[k] *= inv; nim[k] *= inv; }
+    GenOps<GEN>::expect(nre, nim, nT);
+    R dE = R(0);
+#pragma unroll
+    for (int a = 0; a < NG; a++) dE = fma(nT[a] - T[a], h[a], dE);
+    if (ONSITE) {
+        GenOps<GEN>::expect_sq(nre, nim, nTsq);
+#pragma unroll
+        for (int a = 0; a < NG; a++) dE = fma(nTsq[a] - Tsq[a], K[a], dE);
+    }
+    dE_out = dE;
+    const bool acc = u < fast_exp(-beta * dE);   // rand() < exp(-beta dE), no min(1, .)  (MonteCarlo.jl:277-278)
+    if (acc) {
+#pragma unroll
+        for (int k = 0; k < D; k++) { re[k] = nre[k]; im[k] = nim[k]; }
+#pragma unroll
+        for (int a = 0; a < NG; a++) T[a] = nT[a];
+        if (ONSITE) {
+#pragma unroll
+            for (int a = 0; a < NG; a++) Tsq[a] = nTsq[a];
+        }
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------ plane <-> register helpers
+// psi planes: NPV = D/2 vec4 per site, plane v holds (re[2v], im[2v], re[2v+1], im[2v+1]).  T planes: 4 vec4 per site.
+template <class R, int D>
+__device__ __forceinline__ void load_psi(const vec4<R>* base, size_t plane_stride, R* re, R* im) {
+#pragma unroll
+    for (int v = 0; v < D / 2; v++) {
+        const vec4<R> q = base[v * plane_stride];
+        re[2 * v] = q.x; im[2 * v] = q.y; re[2 * v + 1] = q.z; im[2 * v + 1] = q.w;
+    }
+}
+template <class R, int D>
+__device__ __forceinline__ void store_psi(vec4<R>* base, size_t plane_stride, const R* re, const R* im) {
+#pragma unroll
+    for (int v = 0; v < D / 2; v++) base[v * plane_stride] = make_v4<R>(re[2 * v], im[2 * v], re[2 * v + 1], im[2 * v + 1]);
+}
+template <class R>
+__device__ __forceinline__ void load_T(const vec4<R>* base, size_t plane_stride, R* T) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const vec4<R> t = base[q * plane_stride];
+        T[4 * q] = t.x; T[4 * q + 1] = t.y; T[4 * q + 2] = t.z; T[4 * q + 3] = t.w;
+    }
+}
+template <class R>
+__device__ __forceinline__ void add_T(const vec4<R>* base, size_t plane_stride, R* S) {
+    vec4<R> t[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) t[q] = base[q * plane_stride];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { S[4 * q] += t[q].x; S[4 * q + 1] += t[q].y; S[4 * q + 2] += t[q].z; S[4 * q + 3] += t[q].w; }
+}
+template <class R>
+__device__ __forceinline__ void store_T(vec4<R>* base, size_t plane_stride, const R* T) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) base[q * plane_stride] = make_v4<R>(T[4 * q], T[4 * q + 1], T[4 * q + 2], T[4 * q + 3]);
+}
+
+}  // namespace scmc

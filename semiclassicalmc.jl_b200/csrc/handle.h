@@ -1,0 +1,76 @@
+// handle.h -- host-side state behind the opaque scmc_t and small shared helpers (internal to libscmc_b200).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/scmc.h"
+#include "device_core.cuh"
+
+namespace scmc {
+
+void set_error(const std::string& msg);
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define SCMC_CK(call)                                                             \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return ::scmc::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+#define SCMC_TRY(expr)                 \
+    do {                               \
+        int32_t _s = (expr);           \
+        if (_s != SCMC_OK) return _s;  \
+    } while (0)
+#define SCMC_ARG(cond, msg)                                   \
+    do {                                                      \
+        if (!(cond)) { ::scmc::set_error(msg); return SCMC_ERR_ARG; } \
+    } while (0)
+
+// Device view of one model + its replicas, passed BY VALUE to kernels (couplings land in the constant bank).
+template <class R, int NL>
+struct DevModel {
+    vec4<R>* psi;         // [D/2][R][Ns]  site states, colour-major site order
+    vec4<R>* T;           // [4][R][Ns]    cached <G^a>
+    vec4<R>* Tsq;         // [4][R][Ns]    cached <(G^a)^2> (only with on-site couplings at n = 2) else nullptr
+    const int32_t* nbr;   // [z][N]        neighbour (permuted index) or -1
+    const int8_t* lab;    // [z][N]        coupling label of that bond
+    const int32_t* orig;  // [N]           permuted index -> caller's site number
+    int32_t N, Ns, z, n_col;
+    int64_t nrep;
+    int32_t col_off[MAXC + 1];
+    Couplings<R, NL> cp;
+};
+
+}  // namespace scmc
+
+struct scmc_handle {
+    int device = 0, prec = 32, d = 4, z = 0, n_labels = 1, gen_id = 1, n_col = 0;
+    bool onsite = false;      // Tsq planes live and on-site term evaluated per update (n = 2 with K != 0)
+    int64_t N = 0, Ns = 0, R = 0, roff = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<int32_t> colour, perm, orig;   // perm[orig site] = permuted index
+    int32_t col_off[scmc::MAXC + 1] = {0};
+    double J[scmc::MAXL][256] = {{0}}, K[16] = {0};
+    double e_const = 0.0;     // N * sum_a K^a when (G^a)^2 = 1 (n = 1, 3): constant on-site energy
+    // device memory
+    void *psi = nullptr, *T = nullptr, *Tsq = nullptr;
+    int32_t *nbr = nullptr, *d_orig = nullptr;
+    int8_t* lab = nullptr;
+    void *beta = nullptr, *sigma = nullptr;      // [R] reals of the handle's precision
+    unsigned long long* acc = nullptr;           // [R] accepted-update counters
+    uint8_t* active = nullptr;                   // [R] replica still running (annealing) -- nullptr semantics handled by callers
+    double* obs = nullptr;                       // [R][SCMC_NOBS] scratch rows
+    int64_t bytes = 0, launches = 0;
+    int32_t sweep_mode = 0;
+    int64_t batch = 0;
+    size_t esz() const { return prec == 64 ? 8 : 4; }
+};
+
+namespace scmc {
+// implemented in scmc_core.cu
+int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma);
+int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active);
+int32_t launch_measure(scmc_handle* h, double* d_rows /* device [R][SCMC_NOBS] */);
+int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes);
+}  // namespace scmc

@@ -1,0 +1,865 @@
+// scmc_core.cu -- Configuration storage, streaming colour-pass Metropolis kernel, energy / measurement reductions
+// and the C-ABI entry points around them (include/scmc.h).  sm_100a only; no CPU fallback.
+//
+// Reference functions replaced here (paths relative to /root/reference/):
+//   k_sweep_colour   <- the 2N-update loops + localUpdate!           src/MonteCarlo.jl:40-44, 76-80, 152-156, 263-286
+//   k_measure        <- getEnergy, getMagnetization, measure!         src/Configuration.jl:236-253, src/Observables/Observables.jl:16-18,
+//                                                                     src/Observables/ObservablesGeneric.jl:32-46
+//   k_local_field    <- inner sum of getEnergyDifference!             src/Configuration.jl:292-296
+//   k_pack / k_unpack / k_randomize <- Configuration constructor      src/Configuration.jl:62-66, src/MonteCarlo.jl:244-246
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <type_traits>
+#include "handle.h"
+
+namespace scmc {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int32_t cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+    g_err = buf;
+    return SCMC_ERR_CUDA;
+}
+
+int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        g_err = buf;
+        return SCMC_ERR_ALLOC;
+    }
+    h->bytes += (int64_t)bytes;
+    return SCMC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct SweepArgs {
+    int32_t colour, hits;
+    int64_t r0, rcount;        // replica batch [r0, r0 + rcount)
+    uint64_t visit0, seed;     // visit number of hit 0 of this pass; stream key
+    int64_t roff;              // global replica id of replica 0
+    const void *beta, *sigma;  // [R] reals
+    const uint8_t* active;     // [R] or nullptr
+    unsigned long long* acc;   // [R]
+    // deterministic test mode (nullptr in production): injected randoms / recorded decisions, caller's site order
+    const double *inj_xi, *inj_u;
+    uint8_t* out_acc;
+    double* out_dE;
+};
+
+template <class R, int NL>
+__device__ __forceinline__ void neighbour_sums(const DevModel<R, NL>& M, int64_t rbase, size_t ps, int p, R (*S)[NG]) {
+#pragma unroll
+    for (int l = 0; l < NL; l++)
+#pragma unroll
+        for (int a = 0; a < NG; a++) S[l][a] = R(0);
+#pragma unroll 3
+    for (int k = 0; k < M.z; k++) {
+        const int j = M.nbr[(size_t)k * M.N + p];
+        if (j < 0) continue;
+        const vec4<R>* src = M.T + rbase + j;
+        if (NL == 1) {
+            add_T<R>(src, ps, S[0]);
+        } else {
+            const int l = M.lab[(size_t)k * M.N + p];
+            if (l == 0) add_T<R>(src, ps, S[0]);
+            else if (l == 1) add_T<R>(src, ps, S[NL > 1 ? 1 : 0]);
+            else add_T<R>(src, ps, S[NL > 2 ? 2 : 0]);
+        }
+    }
+}
+
+// One colour pass: every (replica, site of this colour) gets `hits` consecutive Metropolis updates.
+template <class R, int GEN, bool ONSITE, int NL>
+__global__ void __launch_bounds__(256) k_sweep_colour(const __grid_constant__ DevModel<R, NL> M, const SweepArgs A) {
+    constexpr int D = GenOps<GEN>::D;
+    const int nc = M.col_off[A.colour + 1] - M.col_off[A.colour];
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = idx < A.rcount * nc;
+    int64_t r = A.r0;
+    int s = 0;
+    if (valid) { const int64_t q = idx / nc; s = (int)(idx - q * nc); r += q; }
+    const bool live = valid && (A.active == nullptr || A.active[r]);
+    unsigned nacc = 0;
+    if (live) {
+        const int p = M.col_off[A.colour] + s;
+        const size_t ps = (size_t)M.nrep * M.Ns;
+        const int64_t rbase = r * M.Ns;
+        R re[D], im[D], T[NG], Tsq[NG], h[NG];
+        load_psi<R, D>(M.psi + rbase + p, ps, re, im);
+        GenOps<GEN>::expect(re, im, T);
+        if (ONSITE) GenOps<GEN>::expect_sq(re, im, Tsq);
+        {
+            R S[NL][NG];
+            neighbour_sums<R, NL>(M, rbase, ps, p, S);
+            field_from_sums<R, NL>(M.cp, S, h);
+        }
+        const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+        const int site = M.orig[p];
+        for (int hit = 0; hit < A.hits; hit++) {
+            R xr[D], xi[D], u, dE;
+            if (A.inj_xi) {
+                const size_t t = ((size_t)hit * M.nrep + r) * M.N + site;
+#pragma unroll
+                for (int k = 0; k < D; k++) { xr[k] = (R)A.inj_xi[t * 2 * D + k]; xi[k] = (R)A.inj_xi[t * 2 * D + D + k]; }
+                u = (R)A.inj_u[t];
+            } else {
+                stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+            }
+            const bool ok = metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, beta, sigma, dE);
+            if (A.out_acc) {
+                const size_t t = ((size_t)hit * M.nrep + r) * M.N + site;
+                A.out_acc[t] = ok ? 1 : 0;
+                if (A.out_dE) A.out_dE[t] = (double)dE;
+            }
+            nacc += ok ? 1u : 0u;
+        }
+        if (nacc) {
+            store_psi<R, D>(M.psi + rbase + p, ps, re, im);
+            store_T<R>(M.T + rbase + p, ps, T);
+            if (ONSITE) store_T<R>(M.Tsq + rbase + p, ps, Tsq);
+        }
+    }
+    // acceptance counters: one atomic per warp when the whole warp works on one replica
+    const unsigned full = 0xffffffffu;
+    const long long r0w = __shfl_sync(full, (long long)r, 0);
+    if (__all_sync(full, r == r0w)) {
+        const unsigned tot = __reduce_add_sync(full, nacc);
+        if ((threadIdx.x & 31) == 0 && tot) atomicAdd(A.acc + r0w, (unsigned long long)tot);
+    } else if (nacc) {
+        atomicAdd(A.acc + r, (unsigned long long)nacc);
+    }
+}
+
+// Energy + magnetisation of every replica; one CTA per replica; FP64 accumulation.
+// row = [E/N, (E/N)^2, |m_sigma|, |m_tau|, |m_sigmatau|, m[16]]  (measure!, ObservablesGeneric.jl:32-46); Etot[r] = E.
+template <class R, int GEN, bool ONSITE, int NL>
+__global__ void __launch_bounds__(256) k_measure(const __grid_constant__ DevModel<R, NL> M, double e_const, double* rows, double* Etot) {
+    const int64_t r = blockIdx.x;
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const int64_t rbase = r * M.Ns;
+    double acc[NG + 1];
+#pragma unroll
+    for (int a = 0; a <= NG; a++) acc[a] = 0.0;
+    for (int p = threadIdx.x; p < M.N; p += blockDim.x) {
+        R T[NG], h[NG], S[NL][NG];
+        load_T<R>(M.T + rbase + p, ps, T);
+        neighbour_sums<R, NL>(M, rbase, ps, p, S);
+        field_from_sums<R, NL>(M.cp, S, h);
+        R e = R(0);
+#pragma unroll
+        for (int a = 0; a < NG; a++) e = fma(T[a], h[a], e);
+        e *= R(0.5);
+        if (ONSITE) {
+            R Tsq[NG];
+            load_T<R>(M.Tsq + rbase + p, ps, Tsq);
+#pragma unroll
+            for (int a = 0; a < NG; a++) e = fma(Tsq[a], M.cp.K[a], e);
+        }
+        acc[NG] += (double)e;
+#pragma unroll
+        for (int a = 0; a < NG; a++) acc[a] += (double)T[a];
+    }
+    __shared__ double red[8][NG + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a <= NG; a++) {
+        double v = acc[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][a] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot[NG + 1];
+        for (int a = 0; a <= NG; a++) {
+            double v = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w][a];
+            tot[a] = v;
+        }
+        const double E = tot[NG] + e_const, invN = 1.0 / (double)M.N;
+        if (Etot) Etot[r] = E;
+        if (rows) {
+            double* row = rows + r * SCMC_NOBS;
+            double m[NG];
+            for (int a = 0; a < NG; a++) m[a] = tot[a] * invN;
+            row[0] = E * invN;
+            row[1] = (E * invN) * (E * invN);
+            row[2] = sqrt(m[4] * m[4] + m[8] * m[8] + m[12] * m[12]);
+            row[3] = sqrt(m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
+            row[4] = sqrt(m[5] * m[5] + m[6] * m[6] + m[7] * m[7] + m[9] * m[9] + m[10] * m[10] + m[11] * m[11] + m[13] * m[13] +
+                          m[14] * m[14] + m[15] * m[15]);
+            for (int a = 0; a < NG; a++) row[5 + a] = m[a];
+        }
+    }
+}
+
+template <class R, int NL>
+__global__ void __launch_bounds__(256) k_local_field(const __grid_constant__ DevModel<R, NL> M, int64_t r, double* out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= M.N) return;
+    R h[NG], S[NL][NG];
+    neighbour_sums<R, NL>(M, r * M.Ns, (size_t)M.nrep * M.Ns, p, S);
+    field_from_sums<R, NL>(M.cp, S, h);
+    const int site = M.orig[p];
+    for (int a = 0; a < NG; a++) out[(size_t)site * NG + a] = (double)h[a];
+}
+
+// host layout [count][N][d] doubles (caller's site order)  ->  planes + T caches
+template <class R, int GEN, bool ONSITE, int NL>
+__global__ void __launch_bounds__(256) k_pack(const __grid_constant__ DevModel<R, NL> M, int64_t r0, int64_t count, const double* re_in,
+                                              const double* im_in) {
+    constexpr int D = GenOps<GEN>::D;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * M.N) return;
+    const int64_t q = idx / M.N;
+    const int p = (int)(idx - q * M.N);
+    const int site = M.orig[p];
+    R re[D], im[D], T[NG];
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        re[k] = (R)re_in[((size_t)q * M.N + site) * D + k];
+        im[k] = (R)im_in[((size_t)q * M.N + site) * D + k];
+    }
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const int64_t at = (r0 + q) * M.Ns + p;
+    store_psi<R, D>(M.psi + at, ps, re, im);
+    GenOps<GEN>::expect(re, im, T);
+    store_T<R>(M.T + at, ps, T);
+    if (ONSITE) {
+        GenOps<GEN>::expect_sq(re, im, T);
+        store_T<R>(M.Tsq + at, ps, T);
+    }
+}
+template <class R, int GEN, int NL>
+__global__ void __launch_bounds__(256) k_unpack(const __grid_constant__ DevModel<R, NL> M, int64_t r0, int64_t count, double* re_out,
+                                                double* im_out) {
+    constexpr int D = GenOps<GEN>::D;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * M.N) return;
+    const int64_t q = idx / M.N;
+    const int p = (int)(idx - q * M.N);
+    const int site = M.orig[p];
+    R re[D], im[D];
+    load_psi<R, D>(M.psi + (r0 + q) * M.Ns + p, (size_t)M.nrep * M.Ns, re, im);
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        re_out[((size_t)q * M.N + site) * D + k] = (double)re[k];
+        im_out[((size_t)q * M.N + site) * D + k] = (double)im[k];
+    }
+}
+template <class R, int GEN, bool ONSITE, int NL>
+__global__ void __launch_bounds__(256) k_get_T(const __grid_constant__ DevModel<R, NL> M, int64_t r, double* T_out, double* Tsq_out) {
+    constexpr int D = GenOps<GEN>::D;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= M.N) return;
+    const int site = M.orig[p];
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    R T[NG];
+    load_T<R>(M.T + r * M.Ns + p, ps, T);
+    for (int a = 0; a < NG; a++) T_out[(size_t)site * NG + a] = (double)T[a];
+    if (Tsq_out) {
+        if (ONSITE) {
+            load_T<R>(M.Tsq + r * M.Ns + p, ps, T);
+        } else {
+            R re[D], im[D];
+            load_psi<R, D>(M.psi + r * M.Ns + p, ps, re, im);
+            GenOps<GEN>::expect_sq(re, im, T);
+        }
+        for (int a = 0; a < NG; a++) Tsq_out[(size_t)site * NG + a] = (double)T[a];
+    }
+}
+// Haar-random product state from stream v1 at the reserved visit number (getRandomState, MonteCarlo.jl:244-246)
+template <class R, int GEN, bool ONSITE, int NL>
+__global__ void __launch_bounds__(256) k_randomize(const __grid_constant__ DevModel<R, NL> M, uint64_t seed, int64_t roff) {
+    constexpr int D = GenOps<GEN>::D;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M.nrep * M.N) return;
+    const int64_t r = idx / M.N;
+    const int p = (int)(idx - r * M.N);
+    R re[D], im[D], T[NG], u;
+    stream_v1<R, D>(seed, (uint32_t)M.orig[p], (uint32_t)(roff + r), VISIT_INIT, re, im, u);
+    R n2 = R(0);
+#pragma unroll
+    for (int k = 0; k < D; k++) n2 += re[k] * re[k] + im[k] * im[k];
+    const R inv = R(1) / sqrt(n2);
+#pragma unroll
+    for (int k = 0; k < D; k++) { re[k] *= inv; im[k] *= inv; }
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    store_psi<R, D>(M.psi + r * M.Ns + p, ps, re, im);
+    GenOps<GEN>::expect(re, im, T);
+    store_T<R>(M.T + r * M.Ns + p, ps, T);
+    if (ONSITE) {
+        GenOps<GEN>::expect_sq(re, im, T);
+        store_T<R>(M.Tsq + r * M.Ns + p, ps, T);
+    }
+}
+
+// One update of one site with injected randoms (parity probe for localUpdate!, MonteCarlo.jl:263-286)
+template <class R, int GEN, bool ONSITE, int NL>
+__global__ void k_single_update(const __grid_constant__ DevModel<R, NL> M, int64_t r, int p, const double* xi_in, double u, double beta,
+                                double sigma, double* out /* [0]=dE, [1]=accepted */) {
+    constexpr int D = GenOps<GEN>::D;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const int64_t rbase = r * M.Ns;
+    R re[D], im[D], T[NG], Tsq[NG], h[NG], S[NL][NG], xr[D], xi[D], dE;
+    load_psi<R, D>(M.psi + rbase + p, ps, re, im);
+    load_T<R>(M.T + rbase + p, ps, T);
+    if (ONSITE) load_T<R>(M.Tsq + rbase + p, ps, Tsq);
+    neighbour_sums<R, NL>(M, rbase, ps, p, S);
+    field_from_sums<R, NL>(M.cp, S, h);
+#pragma unroll
+    for (int k = 0; k < D; k++) { xr[k] = (R)xi_in[k]; xi[k] = (R)xi_in[D + k]; }
+    const bool ok = metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, (R)u, (R)beta, (R)sigma, dE);
+    if (ok) {
+        store_psi<R, D>(M.psi + rbase + p, ps, re, im);
+        store_T<R>(M.T + rbase + p, ps, T);
+        if (ONSITE) store_T<R>(M.Tsq + rbase + p, ps, Tsq);
+    }
+    out[0] = (double)dE; out[1] = ok ? 1.0 : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ dispatch
+template <class R, int NL>
+static DevModel<R, NL> make_model(const scmc_handle* h) {
+    DevModel<R, NL> M;
+    memset(&M, 0, sizeof M);
+    M.psi = (vec4<R>*)h->psi; M.T = (vec4<R>*)h->T; M.Tsq = (vec4<R>*)h->Tsq;
+    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig;
+    M.N = (int32_t)h->N; M.Ns = (int32_t)h->Ns; M.z = h->z; M.n_col = h->n_col; M.nrep = h->R;
+    for (int c = 0; c <= MAXC; c++) M.col_off[c] = h->col_off[c];
+    for (int l = 0; l < NL; l++)
+        for (int t = 0; t < 256; t++) M.cp.J[l][t] = l < h->n_labels ? (R)h->J[l][t] : R(0);
+    for (int a = 0; a < NG; a++) M.cp.K[a] = (R)h->K[a];
+    return M;
+}
+
+template <int V> using ic = std::integral_constant<int, V>;
+// f(R tag, GEN, ONSITE, NL) for the handle's configuration
+template <class F>
+static int32_t dispatch(const scmc_handle* h, F&& f) {
+    auto with_nl = [&](auto rt, auto gen, auto ons) -> int32_t {
+        if (h->n_labels == 1) return f(rt, gen, ons, ic<1>{});
+        return f(rt, gen, ons, ic<MAXL>{});
+    };
+    auto with_gen = [&](auto rt) -> int32_t {
+        switch (h->gen_id) {
+            case 1: return with_nl(rt, ic<1>{}, ic<0>{});
+            case 2: return h->onsite ? with_nl(rt, ic<2>{}, ic<1>{}) : with_nl(rt, ic<2>{}, ic<0>{});
+            case 3: return with_nl(rt, ic<3>{}, ic<0>{});
+        }
+        set_error("internal: bad generator id");
+        return SCMC_ERR_ARG;
+    };
+    return h->prec == 64 ? with_gen(double{}) : with_gen(float{});
+}
+
+static inline unsigned grid_for(int64_t n, int block = 256) { return (unsigned)((n + block - 1) / block); }
+
+int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma) {
+    std::vector<char> buf(h->R * h->esz());
+    for (int pass = 0; pass < 2; pass++) {
+        const double* src = pass ? sigma : beta;
+        if (!src) continue;
+        for (int64_t r = 0; r < h->R; r++) {
+            if (h->prec == 64) ((double*)buf.data())[r] = src[r];
+            else ((float*)buf.data())[r] = (float)src[r];
+        }
+        SCMC_CK(cudaMemcpyAsync(pass ? h->sigma : h->beta, buf.data(), buf.size(), cudaMemcpyHostToDevice, h->stream));
+        SCMC_CK(cudaStreamSynchronize(h->stream));
+    }
+    return SCMC_OK;
+}
+
+static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
+    return dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+        constexpr bool ONS = decltype(ons)::value != 0;
+        const int nc = h->col_off[A.colour + 1] - h->col_off[A.colour];
+        if (nc == 0 || A.rcount == 0) return SCMC_OK;
+        auto M = make_model<R, NL>(h);
+        k_sweep_colour<R, GEN, ONS, NL><<<grid_for(A.rcount * nc), 256, 0, h->stream>>>(M, A);
+        h->launches++;
+        SCMC_CK(cudaGetLastError());
+        return SCMC_OK;
+    });
+}
+
+// Streaming path: replicas are processed in batches (sized to stay L2-resident across the colour passes of all
+// n_sweeps when h->batch > 0); within a batch, sweeps x colours launches.
+int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active) {
+    const int64_t batch = h->batch > 0 ? std::min<int64_t>(h->batch, h->R) : h->R;
+    for (int64_t r0 = 0; r0 < h->R; r0 += batch) {
+        const int64_t rc = std::min<int64_t>(batch, h->R - r0);
+        for (int64_t s = 0; s < n_sweeps; s++)
+            for (int c = 0; c < h->n_col; c++) {
+                SweepArgs A{};
+                A.colour = c; A.hits = hits; A.r0 = r0; A.rcount = rc;
+                A.visit0 = (sweep_counter + (uint64_t)s) * (uint64_t)hits; A.seed = seed; A.roff = h->roff;
+                A.beta = h->beta; A.sigma = h->sigma; A.active = active; A.acc = h->acc;
+                SCMC_TRY(launch_colour_pass(h, A));
+            }
+    }
+    return SCMC_OK;
+}
+
+int32_t launch_measure(scmc_handle* h, double* d_rows) {
+    return dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+        constexpr bool ONS = decltype(ons)::value != 0;
+        auto M = make_model<R, NL>(h);
+        k_measure<R, GEN, ONS, NL><<<(unsigned)h->R, 256, 0, h->stream>>>(M, h->e_const, d_rows, nullptr);
+        h->launches++;
+        SCMC_CK(cudaGetLastError());
+        return SCMC_OK;
+    });
+}
+
+}  // namespace scmc
+
+using namespace scmc;
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* scmc_last_error(void) { return g_err.c_str(); }
+int32_t scmc_version(void) { return 100; }
+int32_t scmc_device_count(int32_t* n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (n) *n = (e == cudaSuccess) ? c : 0;
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    return SCMC_OK;
+}
+
+static bool table_matches(const double* re, const double* im, const int8_t* tre, const int8_t* tim, int n) {
+    for (int i = 0; i < n; i++)
+        if (std::fabs(re[i] - tre[i]) > 1e-12 || std::fabs(im[i] - tim[i]) > 1e-12) return false;
+    return true;
+}
+
+int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_sites, int32_t d, int64_t n_replicas,
+                    int64_t replica_offset, int32_t z_max, const int32_t* nbr_site, const int32_t* nbr_label, int32_t n_labels,
+                    const double* J, const double* K, const double* gen_re, const double* gen_im, const double* gensq_re,
+                    const double* gensq_im, const int32_t* colour) {
+    SCMC_ARG(out != nullptr, "scmc_create: null handle pointer");
+    *out = nullptr;
+    SCMC_ARG(precision == 32 || precision == 64, "scmc_create: precision must be 32 or 64");
+    SCMC_ARG(n_sites > 0 && n_sites < (1ll << 30), "scmc_create: n_sites out of range");
+    SCMC_ARG(n_replicas > 0, "scmc_create: n_replicas must be positive");
+    SCMC_ARG(z_max > 0 && nbr_site && nbr_label, "scmc_create: neighbour tables required");
+    SCMC_ARG(n_labels >= 1 && n_labels <= MAXL, "scmc_create: 1..3 coupling labels supported");
+    SCMC_ARG(J && K && gen_re && gen_im && gensq_re && gensq_im, "scmc_create: null coupling / generator table");
+    SCMC_ARG(d == 4 || d == 6, "scmc_create: local dimension d must be 4 (n=1,3) or 6 (n=2)");
+
+    int gen_id = 0;
+    if (d == 4 && table_matches(gen_re, gen_im, gen::G1_re, gen::G1_im, 256) && table_matches(gensq_re, gensq_im, gen::Gsq1_re, gen::Gsq1_im, 256)) gen_id = 1;
+    else if (d == 4 && table_matches(gen_re, gen_im, gen::G3_re, gen::G3_im, 256) && table_matches(gensq_re, gensq_im, gen::Gsq3_re, gen::Gsq3_im, 256)) gen_id = 3;
+    else if (d == 6 && table_matches(gen_re, gen_im, gen::G2_re, gen::G2_im, 576) && table_matches(gensq_re, gensq_im, gen::Gsq2_re, gen::Gsq2_im, 576)) gen_id = 2;
+    if (!gen_id) {
+        set_error("scmc_create: generator tables differ from getGenerators(n), n = 1, 2, 3 (custom generators are not supported)");
+        return SCMC_ERR_UNSUPPORTED;
+    }
+
+    const int64_t N = n_sites;
+    // --- table validation
+    for (int64_t i = 0; i < N; i++)
+        for (int k = 0; k < z_max; k++) {
+            const int32_t j = nbr_site[i * z_max + k];
+            SCMC_ARG(j >= -1 && j < N, "scmc_create: neighbour index out of range");
+            if (j >= 0) SCMC_ARG(nbr_label[i * z_max + k] >= 0 && nbr_label[i * z_max + k] < n_labels, "scmc_create: bond label out of range");
+            SCMC_ARG(j != i, "scmc_create: self-bonds are not supported (use the on-site couplings K)");
+        }
+    // every bond i->j (label l) needs a reverse bond j->i whose coupling is the transpose
+    for (int64_t i = 0; i < N; i++)
+        for (int k = 0; k < z_max; k++) {
+            const int32_t j = nbr_site[i * z_max + k];
+            if (j < 0) continue;
+            const double* Jl = J + (size_t)nbr_label[i * z_max + k] * 256;
+            int cnt_fwd = 0, cnt_ok = 0;
+            for (int k2 = 0; k2 < z_max; k2++)
+                if (nbr_site[i * z_max + k2] == j && nbr_label[i * z_max + k2] == nbr_label[i * z_max + k]) cnt_fwd++;
+            for (int k2 = 0; k2 < z_max; k2++) {
+                if (nbr_site[(int64_t)j * z_max + k2] != i) continue;
+                const double* Jr = J + (size_t)nbr_label[(int64_t)j * z_max + k2] * 256;
+                bool tr = true;
+                for (int a = 0; a < 16 && tr; a++)
+                    for (int b = 0; b < 16; b++)
+                        if (std::fabs(Jl[a * 16 + b] - Jr[b * 16 + a]) > 1e-12 * (1.0 + std::fabs(Jl[a * 16 + b]))) { tr = false; break; }
+                if (tr) cnt_ok++;
+            }
+            SCMC_ARG(cnt_ok >= cnt_fwd, "scmc_create: bond i->j has no reverse bond j->i with the transposed coupling matrix "
+                                        "(getEnergyDifference! would be inconsistent with getEnergy, Configuration.jl:246-250 vs 292-296)");
+        }
+
+    scmc_handle* h = new scmc_handle();
+    h->device = device; h->prec = precision; h->d = d; h->z = z_max; h->n_labels = n_labels; h->gen_id = gen_id;
+    h->N = N; h->R = n_replicas; h->roff = replica_offset;
+    h->Ns = (N + 7) / 8 * 8;
+    for (int l = 0; l < n_labels; l++) memcpy(h->J[l], J + (size_t)l * 256, sizeof(double) * 256);
+    memcpy(h->K, K, sizeof(double) * 16);
+    bool anyK = false;
+    double sumK = 0.0;
+    for (int a = 0; a < 16; a++) { anyK |= (K[a] != 0.0); sumK += K[a]; }
+    h->onsite = anyK && gen_id == 2;
+    h->e_const = (gen_id == 2) ? 0.0 : sumK * (double)N;   // (G^a)^2 = 1 for d = 4  
+
+    // --- colouring
+    h->colour.assign(N, -1);
+    if (colour) {
+        for (int64_t i = 0; i < N; i++) h->colour[i] = colour[i];
+    } else {
+        std::vector<std::vector<int32_t>> adj(N);
+        for (int64_t i = 0; i < N; i++)
+            for (int k = 0; k < z_max; k++) {
+                const int32_t j = nbr_site[i * z_max + k];
+                if (j >= 0) { adj[i].push_back(j); adj[j].push_back((int32_t)i); }
+            }
+        for (int64_t i = 0; i < N; i++) {
+            unsigned used = 0;
+            for (int32_t j : adj[i]) if (h->colour[j] >= 0 && h->colour[j] < 32) used |= 1u << h->colour[j];
+            int c = 0;
+            while (used & (1u << c)) c++;
+            h->colour[i] = c;
+        }
+    }
+    int ncol = 0;
+    for (int64_t i = 0; i < N; i++) {
+        if (h->colour[i] < 0 || h->colour[i] >= MAXC) { delete h; set_error("scmc_create: colour outside 0..7 (too many colours)"); return SCMC_ERR_ARG; }
+        ncol = std::max(ncol, h->colour[i] + 1);
+    }
+    for (int64_t i = 0; i < N; i++)
+        for (int k = 0; k < z_max; k++) {
+            const int32_t j = nbr_site[i * z_max + k];
+            if (j >= 0 && h->colour[j] == h->colour[i]) { delete h; set_error("scmc_create: invalid colouring, two bonded sites share a colour"); return SCMC_ERR_ARG; }
+        }
+    h->n_col = ncol;
+    h->perm.resize(N); h->orig.resize(N);
+    {
+        int32_t at = 0;
+        for (int c = 0; c < ncol; c++) {
+            h->col_off[c] = at;
+            for (int64_t i = 0; i < N; i++) if (h->colour[i] == c) { h->perm[i] = at; h->orig[at] = (int32_t)i; at++; }
+        }
+        for (int c = ncol; c <= MAXC; c++) h->col_off[c] = at;
+    }
+
+    // --- device
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__); }
+    std::vector<int32_t> nb((size_t)z_max * N);
+    std::vector<int8_t> lb((size_t)z_max * N);
+    for (int64_t p = 0; p < N; p++)
+        for (int k = 0; k < z_max; k++) {
+            const int32_t j = nbr_site[(int64_t)h->orig[p] * z_max + k];
+            nb[(size_t)k * N + p] = j >= 0 ? h->perm[j] : -1;
+            lb[(size_t)k * N + p] = j >= 0 ? (int8_t)nbr_label[(int64_t)h->orig[p] * z_max + k] : 0;
+        }
+    const size_t plane = (size_t)h->R * h->Ns * 4 * h->esz();
+    int32_t st = SCMC_OK;
+    auto A = [&](void** p, size_t bytes) { if (st == SCMC_OK) st = dev_alloc(h, p, bytes); };
+    A(&h->psi, plane * (d / 2));
+    A(&h->T, plane * 4);
+    if (h->onsite) A(&h->Tsq, plane * 4);
+    A((void**)&h->nbr, nb.size() * sizeof(int32_t));
+    A((void**)&h->lab, lb.size());
+    A((void**)&h->d_orig, N * sizeof(int32_t));
+    A(&h->beta, h->R * h->esz());
+    A(&h->sigma, h->R * h->esz());
+    A((void**)&h->acc, h->R * sizeof(unsigned long long));
+    A((void**)&h->active, h->R);
+    A((void**)&h->obs, h->R * SCMC_NOBS * sizeof(double));
+    if (st != SCMC_OK) { scmc_destroy(h); return st; }
+    cudaError_t ce = cudaSuccess;
+    auto C = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
+    C(cudaMemcpy(h->nbr, nb.data(), nb.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    C(cudaMemcpy(h->lab, lb.data(), lb.size(), cudaMemcpyHostToDevice));
+    C(cudaMemcpy(h->d_orig, h->orig.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
+    C(cudaMemset(h->psi, 0, plane * (d / 2)));
+    C(cudaMemset(h->T, 0, plane * 4));
+    if (h->onsite) C(cudaMemset(h->Tsq, 0, plane * 4));
+    C(cudaMemset(h->acc, 0, h->R * sizeof(unsigned long long)));
+    C(cudaMemset(h->active, 1, h->R));
+    if (ce != cudaSuccess) { scmc_destroy(h); return cuda_fail(ce, "scmc_create upload", __FILE__, __LINE__); }
+    *out = h;
+    return SCMC_OK;
+}
+
+int32_t scmc_destroy(scmc_t* h) {
+    if (!h) return SCMC_OK;
+    cudaSetDevice(h->device);
+    void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete h;
+    return SCMC_OK;
+}
+
+int32_t scmc_set_stream(scmc_t* h, void* s) {
+    SCMC_ARG(h, "null handle");
+    h->stream = (cudaStream_t)s;
+    return SCMC_OK;
+}
+
+int32_t scmc_info(scmc_t* h, int64_t* info) {
+    SCMC_ARG(h && info, "null argument");
+    info[0] = h->n_col; info[1] = h->gen_id; info[2] = h->bytes; info[3] = 0; info[4] = 0; info[5] = h->launches; info[6] = h->N; info[7] = h->R;
+    return SCMC_OK;
+}
+
+int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch) {
+    SCMC_ARG(h, "null handle");
+    SCMC_ARG(mode >= 0 && mode <= 2 && batch >= 0, "scmc_set_sweep_mode: bad mode / batch");
+    h->sweep_mode = mode; h->batch = batch;
+    return SCMC_OK;
+}
+
+static int32_t state_io(scmc_t* h, int64_t r0, int64_t count, double* re, double* im, bool to_device) {
+    SCMC_ARG(h && re && im, "null argument");
+    SCMC_ARG(r0 >= 0 && count >= 0 && r0 + count <= h->R, "replica range out of bounds");
+    SCMC_CK(cudaSetDevice(h->device));
+    const int64_t per = h->N * h->d;                               // doubles per replica per part
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(128ll << 20) / (per * 8));
+    double *dre = nullptr, *dim_ = nullptr;
+    const size_t cbytes = (size_t)std::min(chunk, std::max<int64_t>(count, 1)) * per * 8;
+    SCMC_CK(cudaMalloc(&dre, cbytes));
+    if (cudaMalloc(&dim_, cbytes) != cudaSuccess) { cudaFree(dre); return cuda_fail(cudaErrorMemoryAllocation, "staging", __FILE__, __LINE__); }
+    int32_t st = SCMC_OK;
+    for (int64_t q = 0; q < count && st == SCMC_OK; q += chunk) {
+        const int64_t c = std::min(chunk, count - q);
+        const size_t bytes = (size_t)c * per * 8;
+        if (to_device) {
+            cudaMemcpyAsync(dre, re + q * per, bytes, cudaMemcpyHostToDevice, h->stream);
+            cudaMemcpyAsync(dim_, im + q * per, bytes, cudaMemcpyHostToDevice, h->stream);
+        }
+        st = dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+            using R = decltype(rt);
+            constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+            constexpr bool ONS = decltype(ons)::value != 0;
+            auto M = make_model<R, NL>(h);
+            if (to_device) k_pack<R, GEN, ONS, NL><<<grid_for(c * h->N), 256, 0, h->stream>>>(M, r0 + q, c, dre, dim_);
+            else k_unpack<R, GEN, NL><<<grid_for(c * h->N), 256, 0, h->stream>>>(M, r0 + q, c, dre, dim_);
+            h->launches++;
+            SCMC_CK(cudaGetLastError());
+            return SCMC_OK;
+        });
+        if (st == SCMC_OK && !to_device) {
+            cudaMemcpyAsync(re + q * per, dre, bytes, cudaMemcpyDeviceToHost, h->stream);
+            cudaMemcpyAsync(im + q * per, dim_, bytes, cudaMemcpyDeviceToHost, h->stream);
+        }
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (st == SCMC_OK && e != cudaSuccess) st = cuda_fail(e, "state_io sync", __FILE__, __LINE__);
+    }
+    cudaFree(dre); cudaFree(dim_);
+    return st;
+}
+int32_t scmc_set_state(scmc_t* h, int64_t r0, int64_t count, const double* re, const double* im) {
+    return state_io(h, r0, count, const_cast<double*>(re), const_cast<double*>(im), true);
+}
+int32_t scmc_get_state(scmc_t* h, int64_t r0, int64_t count, double* re, double* im) { return state_io(h, r0, count, re, im, false); }
+
+int32_t scmc_randomize(scmc_t* h, uint64_t seed) {
+    SCMC_ARG(h, "null handle");
+    SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+        constexpr bool ONS = decltype(ons)::value != 0;
+        auto M = make_model<R, NL>(h);
+        k_randomize<R, GEN, ONS, NL><<<grid_for(h->R * h->N), 256, 0, h->stream>>>(M, seed, h->roff);
+        h->launches++;
+        SCMC_CK(cudaGetLastError());
+        return SCMC_OK;
+    }));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    return SCMC_OK;
+}
+
+int32_t scmc_get_T(scmc_t* h, int64_t r, double* T, double* Tsq) {
+    SCMC_ARG(h && T, "null argument");
+    SCMC_ARG(r >= 0 && r < h->R, "replica out of range");
+    SCMC_CK(cudaSetDevice(h->device));
+    double *dT = nullptr, *dTsq = nullptr;
+    const size_t bytes = (size_t)h->N * 16 * 8;
+    SCMC_CK(cudaMalloc(&dT, bytes));
+    if (Tsq && cudaMalloc(&dTsq, bytes) != cudaSuccess) { cudaFree(dT); return cuda_fail(cudaErrorMemoryAllocation, "staging", __FILE__, __LINE__); }
+    int32_t st = dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+        constexpr bool ONS = decltype(ons)::value != 0;
+        auto M = make_model<R, NL>(h);
+        k_get_T<R, GEN, ONS, NL><<<grid_for(h->N), 256, 0, h->stream>>>(M, r, dT, dTsq);
+        h->launches++;
+        SCMC_CK(cudaGetLastError());
+        return SCMC_OK;
+    });
+    if (st == SCMC_OK) {
+        cudaMemcpyAsync(T, dT, bytes, cudaMemcpyDeviceToHost, h->stream);
+        if (Tsq) cudaMemcpyAsync(Tsq, dTsq, bytes, cudaMemcpyDeviceToHost, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "get_T sync", __FILE__, __LINE__);
+    }
+    cudaFree(dT); if (dTsq) cudaFree(dTsq);
+    return st;
+}
+
+int32_t scmc_energy(scmc_t* h, double* E) {
+    SCMC_ARG(h && E, "null argument");
+    SCMC_CK(cudaSetDevice(h->device));
+    double* dE = nullptr;
+    SCMC_CK(cudaMalloc(&dE, h->R * 8));
+    int32_t st = dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+        constexpr bool ONS = decltype(ons)::value != 0;
+        auto M = make_model<R, NL>(h);
+        k_measure<R, GEN, ONS, NL><<<(unsigned)h->R, 256, 0, h->stream>>>(M, h->e_const, nullptr, dE);
+        h->launches++;
+        SCMC_CK(cudaGetLastError());
+        return SCMC_OK;
+    });
+    if (st == SCMC_OK) {
+        cudaMemcpyAsync(E, dE, h->R * 8, cudaMemcpyDeviceToHost, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "energy sync", __FILE__, __LINE__);
+    }
+    cudaFree(dE);
+    return st;
+}
+
+int32_t scmc_local_field(scmc_t* h, int64_t r, double* out) {
+    SCMC_ARG(h && out, "null argument");
+    SCMC_ARG(r >= 0 && r < h->R, "replica out of range");
+    SCMC_CK(cudaSetDevice(h->device));
+    double* dH = nullptr;
+    const size_t bytes = (size_t)h->N * 16 * 8;
+    SCMC_CK(cudaMalloc(&dH, bytes));
+    int32_t st = dispatch(h, [&](auto rt, auto, auto, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int NL = decltype(nl)::value;
+        auto M = make_model<R, NL>(h);
+        k_local_field<R, NL><<<grid_for(h->N), 256, 0, h->stream>>>(M, r, dH);
+        h->launches++;
+        SCMC_CK(cudaGetLastError());
+        return SCMC_OK;
+    });
+    if (st == SCMC_OK) {
+        cudaMemcpyAsync(out, dH, bytes, cudaMemcpyDeviceToHost, h->stream);
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "local_field sync", __FILE__, __LINE__);
+    }
+    cudaFree(dH);
+    return st;
+}
+
+int32_t scmc_measure(scmc_t* h, double* obs) {
+    SCMC_ARG(h && obs, "null argument");
+    SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(launch_measure(h, h->obs));
+    SCMC_CK(cudaMemcpyAsync(obs, h->obs, h->R * SCMC_NOBS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    return SCMC_OK;
+}
+
+int32_t scmc_sweep_async(scmc_t* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter) {
+    SCMC_ARG(h, "null handle");
+    SCMC_ARG(n_sweeps >= 0 && hits >= 1, "scmc_sweep: n_sweeps >= 0 and hits >= 1 required");
+    SCMC_CK(cudaSetDevice(h->device));
+    return launch_sweeps(h, n_sweeps, hits, seed, sweep_counter, nullptr);
+}
+
+int32_t scmc_sweep(scmc_t* h, int64_t n_sweeps, int32_t hits, const double* beta, const double* sigma, uint64_t seed,
+                   uint64_t sweep_counter, int64_t* accepted, int64_t* attempted) {
+    SCMC_ARG(h && beta && sigma, "null argument");
+    SCMC_ARG(n_sweeps >= 0 && hits >= 1, "scmc_sweep: n_sweeps >= 0 and hits >= 1 required");
+    SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(upload_scalars(h, beta, sigma));
+    SCMC_CK(cudaMemsetAsync(h->acc, 0, h->R * sizeof(unsigned long long), h->stream));
+    SCMC_TRY(launch_sweeps(h, n_sweeps, hits, seed, sweep_counter, nullptr));
+    if (accepted) {
+        static_assert(sizeof(unsigned long long) == sizeof(int64_t), "");
+        SCMC_CK(cudaMemcpyAsync(accepted, h->acc, h->R * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    if (attempted) for (int64_t r = 0; r < h->R; r++) attempted[r] = n_sweeps * hits * h->N;
+    return SCMC_OK;
+}
+
+int32_t scmc_sweep_deterministic(scmc_t* h, int32_t hits, const double* beta, const double* sigma, const double* xi, const double* u,
+                                 uint8_t* accept, double* dE) {
+    SCMC_ARG(h && beta && sigma && xi && u && accept, "null argument");
+    SCMC_ARG(hits >= 1, "hits >= 1 required");
+    SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(upload_scalars(h, beta, sigma));
+    const size_t n = (size_t)hits * h->R * h->N;
+    double *dxi = nullptr, *du = nullptr, *ddE = nullptr;
+    uint8_t* dacc = nullptr;
+    int32_t st = SCMC_OK;
+    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && st == SCMC_OK) st = cuda_fail(e, "sweep_deterministic", __FILE__, __LINE__); };
+    fail(cudaMalloc(&dxi, n * 2 * h->d * 8)); fail(cudaMalloc(&du, n * 8)); fail(cudaMalloc(&dacc, n)); fail(cudaMalloc(&ddE, n * 8));
+    if (st == SCMC_OK) {
+        fail(cudaMemcpyAsync(dxi, xi, n * 2 * h->d * 8, cudaMemcpyHostToDevice, h->stream));
+        fail(cudaMemcpyAsync(du, u, n * 8, cudaMemcpyHostToDevice, h->stream));
+        fail(cudaMemsetAsync(dacc, 0, n, h->stream));
+        fail(cudaMemsetAsync(h->acc, 0, h->R * sizeof(unsigned long long), h->stream));
+    }
+    for (int c = 0; c < h->n_col && st == SCMC_OK; c++) {
+        SweepArgs A{};
+        A.colour = c; A.hits = hits; A.r0 = 0; A.rcount = h->R; A.visit0 = 0; A.seed = 0; A.roff = h->roff;
+        A.beta = h->beta; A.sigma = h->sigma; A.active = nullptr; A.acc = h->acc;
+        A.inj_xi = dxi; A.inj_u = du; A.out_acc = dacc; A.out_dE = ddE;
+        st = launch_colour_pass(h, A);
+    }
+    if (st == SCMC_OK) {
+        fail(cudaMemcpyAsync(accept, dacc, n, cudaMemcpyDeviceToHost, h->stream));
+        if (dE) fail(cudaMemcpyAsync(dE, ddE, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        fail(cudaStreamSynchronize(h->stream));
+    }
+    cudaFree(dxi); cudaFree(du); cudaFree(dacc); cudaFree(ddE);
+    return st;
+}
+
+int32_t scmc_update_deterministic(scmc_t* h, int64_t r, int64_t site, const double* xi, double u, double beta, double sigma, double* dE,
+                                  int32_t* accepted) {
+    SCMC_ARG(h && xi, "null argument");
+    SCMC_ARG(r >= 0 && r < h->R && site >= 0 && site < h->N, "replica / site out of range");
+    SCMC_CK(cudaSetDevice(h->device));
+    double* dbuf = nullptr;
+    SCMC_CK(cudaMalloc(&dbuf, (2 * h->d + 2) * 8));
+    int32_t st = SCMC_OK;
+    cudaError_t e = cudaMemcpyAsync(dbuf + 2, xi, 2 * h->d * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) st = cuda_fail(e, "update_deterministic", __FILE__, __LINE__);
+    if (st == SCMC_OK)
+        st = dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+            using R = decltype(rt);
+            constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+            constexpr bool ONS = decltype(ons)::value != 0;
+            auto M = make_model<R, NL>(h);
+            k_single_update<R, GEN, ONS, NL><<<1, 32, 0, h->stream>>>(M, r, h->perm[site], dbuf + 2, u, beta, sigma, dbuf);
+            h->launches++;
+            SCMC_CK(cudaGetLastError());
+            return SCMC_OK;
+        });
+    double res[2] = {0, 0};
+    if (st == SCMC_OK) {
+        e = cudaMemcpyAsync(res, dbuf, 16, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "update_deterministic", __FILE__, __LINE__);
+    }
+    cudaFree(dbuf);
+    if (dE) *dE = res[0];
+    if (accepted) *accepted = res[1] != 0.0;
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,465 @@
+// scmc_drivers.cu -- device-side schedules of the reference's drivers and the remaining observables.
+//
+// Reference functions replaced here (paths relative to /root/reference/):
+//   scmc_run_metropolis   <- run!                      src/MonteCarlo.jl:3-108   (ramp :24-27, sigma rule :47-54, measure cadence :82-86)
+//   scmc_anneal           <- runAnnealing! cooling     src/MonteCarlo.jl:131-204 (per-temperature window :151, cooling/sigma :178-192)
+//   scmc_optimize         <- localOptimization! sweeps src/MonteCarlo.jl:214-225, 289-329 (per-site minimisation of the local energy)
+//   scmc_structure_factor <- getCorrelations + computeStructureFactorVec  src/Observables/Observables.jl:22-41, 116-128
+//   scmc_correlations     <- getCorrelations           src/Observables/Observables.jl:22-41
+// Every replica carries its own (beta, sigma, counters, stop flag); the host only issues launches.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+#include "handle.h"
+
+namespace scmc {
+
+// beta_r for thermalisation sweep `sweep` (1-based): geometric ramp over the first N_anneal sweeps, then flat (MonteCarlo.jl:24-27)
+template <class R>
+__global__ void k_set_beta(int64_t nrep, const double* T, const double* Ti, int64_t sweep, int64_t n_anneal, R* beta) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrep) return;
+    double t = T[r];
+    if (sweep >= 1 && sweep <= n_anneal && n_anneal > 1) t = Ti[r] * pow(T[r] / Ti[r], (double)(sweep - 1) / (double)(n_anneal - 1));
+    beta[r] = (R)(1.0 / t);
+}
+// sigma <- min(sigma * 0.5 / (1 - R_acc), 60) with R_acc = accepted / attempted since the last call (MonteCarlo.jl:50-53)
+template <class R>
+__global__ void k_adapt_sigma(int64_t nrep, unsigned long long* acc, double attempted, R* sigma) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrep) return;
+    const double ratio = (double)acc[r] / attempted;
+    const double s = fmin((double)sigma[r] * 0.5 / (1.0 - ratio), 60.0);   // ratio == 1 -> inf -> 60
+    sigma[r] = (R)s;
+    acc[r] = 0ull;
+}
+// per-replica annealing controller, run after every sweep (MonteCarlo.jl:151-203)
+template <class R>
+__global__ void k_anneal_ctrl(int64_t nrep, unsigned long long* acc, int64_t* sweeps_at_T, int64_t* sweeps_done, uint8_t* active,
+                              R* beta, R* sigma, double att_per_sweep, double min_accepted, int64_t n_per_T, int last_sweep,
+                              double beta_fac, double min_accrate, double sigma_min, int* n_active) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrep || !active[r]) return;
+    const int64_t sat = sweeps_at_T[r] + 1;
+    sweeps_done[r] += 1;
+    const double a = (double)acc[r];
+    bool still = true;
+    if (!(a < min_accepted && sat < n_per_T && !last_sweep)) {
+        const double ratio = a / (att_per_sweep * (double)sat);
+        if (ratio > min_accrate) {
+            beta[r] = (R)((double)beta[r] * beta_fac);
+            sigma[r] = (R)fmax(fmin((double)sigma[r] * 0.5 / (1.0 - ratio), 60.0), sigma_min);
+            acc[r] = 0ull;
+            sweeps_at_T[r] = 0;
+        } else {
+            active[r] = 0;
+            still = false;
+        }
+    } else {
+        sweeps_at_T[r] = sat;
+    }
+    if (still && !last_sweep) atomicAdd(n_active, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ local optimisation
+// Minimise <psi|H_loc|psi>, H_loc = sum_a h^a G^a (+ K^a (G^a)^2), by power iteration on (c - H_loc), c >= lambda_max
+// (Gershgorin).  Every iteration lowers the local energy monotonically; the fixed point is the ground state of H_loc, i.e.
+// the stationary point the reference's gradient descent (MonteCarlo.jl:303-314) converges to.
+template <class R, int NL>
+__device__ __forceinline__ void neighbour_sums_d(const DevModel<R, NL>& M, int64_t rbase, size_t ps, int p, R (*S)[NG]) {
+#pragma unroll
+    for (int l = 0; l < NL; l++)
+#pragma unroll
+        for (int a = 0; a < NG; a++) S[l][a] = R(0);
+    for (int k = 0; k < M.z; k++) {
+        const int j = M.nbr[(size_t)k * M.N + p];
+        if (j < 0) continue;
+        const int l = NL == 1 ? 0 : M.lab[(size_t)k * M.N + p];
+        R t[NG];
+        load_T<R>(M.T + rbase + j, ps, t);
+#pragma unroll
+        for (int ll = 0; ll < NL; ll++)
+            if (ll == l) {
+#pragma unroll
+                for (int a = 0; a < NG; a++) S[ll][a] += t[a];
+            }
+    }
+}
+
+template <class R, int GEN, bool ONSITE, int NL>
+__global__ void __launch_bounds__(128) k_optimize_colour(const __grid_constant__ DevModel<R, NL> M, int colour, int iters) {
+    constexpr int D = GenOps<GEN>::D;
+    const int nc = M.col_off[colour + 1] - M.col_off[colour];
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M.nrep * nc) return;
+    const int64_t r = idx / nc;
+    const int p = M.col_off[colour] + (int)(idx - r * nc);
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const int64_t rbase = r * M.Ns;
+    R re[D], im[D], h[NG], Hr[D * D], Hi[D * D];
+    load_psi<R, D>(M.psi + rbase + p, ps, re, im);
+    {
+        R S[NL][NG];
+        neighbour_sums_d<R, NL>(M, rbase, ps, p, S);
+        field_from_sums<R, NL>(M.cp, S, h);
+    }
+    GenOps<GEN>::template hloc<R, ONSITE>(h, M.cp.K, Hr, Hi);
+    // fill the lower triangle (Hermitian) and find the Gershgorin upper bound
+#pragma unroll
+    for (int j = 0; j < D; j++)
+#pragma unroll
+        for (int k = 0; k < j; k++) { Hr[j * D + k] = Hr[k * D + j]; Hi[j * D + k] = -Hi[k * D + j]; }
+    R c = R(-1e30);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        R row = Hr[j * D + j];
+#pragma unroll
+        for (int k = 0; k < D; k++)
+            if (k != j) row += sqrt(Hr[j * D + k] * Hr[j * D + k] + Hi[j * D + k] * Hi[j * D + k]);
+        c = row > c ? row : c;
+    }
+    // A = c - H (positive semi-definite)
+#pragma unroll
+    for (int j = 0; j < D; j++)
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            Hr[j * D + k] = (j == k ? c : R(0)) - Hr[j * D + k];
+            Hi[j * D + k] = -Hi[j * D + k];
+        }
+    for (int it = 0; it < iters; it++) {
+        R nr[D], ni[D], n2 = R(0);
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            R ar = R(0), ai = R(0);
+#pragma unroll
+            for (int k = 0; k < D; k++) {
+                ar += Hr[j * D + k] * re[k] - Hi[j * D + k] * im[k];
+                ai += Hr[j * D + k] * im[k] + Hi[j * D + k] * re[k];
+            }
+            nr[j] = ar; ni[j] = ai; n2 += ar * ar + ai * ai;
+        }
+        if (!(n2 > R(0))) break;     // psi orthogonal to everything but the top state of H (or H = c): keep psi
+        const R inv = R(1) / sqrt(n2);
+#pragma unroll
+        for (int j = 0; j < D; j++) { re[j] = nr[j] * inv; im[j] = ni[j] * inv; }
+    }
+    R T[NG];
+    store_psi<R, D>(M.psi + rbase + p, ps, re, im);
+    GenOps<GEN>::expect(re, im, T);
+    store_T<R>(M.T + rbase + p, ps, T);
+    if (ONSITE) {
+        GenOps<GEN>::expect_sq(re, im, T);
+        store_T<R>(M.Tsq + rbase + p, ps, T);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ structure factor
+// S^a(k) = |sum_i T_i^a e^{i k.r_i}|^2 / n_rs.  Block = 128 momenta of one replica; FP64 phases and accumulators.
+template <class R>
+__global__ void __launch_bounds__(128) k_structure_factor(const vec4<R>* __restrict__ Tpl, int N, int Ns, int64_t nrep, const double* __restrict__ ks,
+                                                          const double* __restrict__ pos /* permuted order [N][dim] */, int nk, int dim, double inv_nrs,
+                                                          double* __restrict__ out /* [R][16][nk] */) {
+    const int64_t r = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = k < nk;
+    double kv[3] = {0, 0, 0};
+    if (valid) for (int x = 0; x < dim; x++) kv[x] = ks[(size_t)k * dim + x];
+    double sr[NG], si[NG];
+#pragma unroll
+    for (int a = 0; a < NG; a++) { sr[a] = 0.0; si[a] = 0.0; }
+    const size_t ps = (size_t)nrep * Ns;
+    const vec4<R>* base = Tpl + r * Ns;
+    for (int p = 0; p < N; p++) {
+        double ph = 0.0;
+        for (int x = 0; x < dim; x++) ph += kv[x] * pos[(size_t)p * dim + x];
+        double s, c;
+        sincos(ph, &s, &c);
+        R t[NG];
+        load_T<R>(base + p, ps, t);
+#pragma unroll
+        for (int a = 0; a < NG; a++) { sr[a] = fma((double)t[a], c, sr[a]); si[a] = fma((double)t[a], s, si[a]); }
+    }
+    if (valid)
+#pragma unroll
+        for (int a = 0; a < NG; a++) out[((size_t)r * NG + a) * nk + k] = (sr[a] * sr[a] + si[a] * si[a]) * inv_nrs;
+}
+
+// C[a][project[i][j]] += T_i^a T_j^a  (Observables.jl:22-41); project given in the caller's site order
+template <class R>
+__global__ void __launch_bounds__(256) k_correlations(const vec4<R>* __restrict__ Tpl, int N, int Ns, int64_t nrep, int64_t r, const int32_t* __restrict__ perm,
+                                                      const int32_t* __restrict__ project, int64_t n_rs, double* C) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)N * N) return;
+    const int i = (int)(idx / N), j = (int)(idx - (int64_t)i * N);
+    const size_t ps = (size_t)nrep * Ns;
+    R ti[NG], tj[NG];
+    load_T<R>(Tpl + r * Ns + perm[i], ps, ti);
+    load_T<R>(Tpl + r * Ns + perm[j], ps, tj);
+    const int32_t m = project[idx];
+#pragma unroll
+    for (int a = 0; a < NG; a++) atomicAdd(C + (size_t)a * n_rs + m, (double)ti[a] * (double)tj[a]);
+}
+
+template <int V> using ic = std::integral_constant<int, V>;
+template <class R, int NL>
+static DevModel<R, NL> make_model_d(const scmc_handle* h) {
+    DevModel<R, NL> M;
+    memset(&M, 0, sizeof M);
+    M.psi = (vec4<R>*)h->psi; M.T = (vec4<R>*)h->T; M.Tsq = (vec4<R>*)h->Tsq;
+    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig;
+    M.N = (int32_t)h->N; M.Ns = (int32_t)h->Ns; M.z = h->z; M.n_col = h->n_col; M.nrep = h->R;
+    for (int c = 0; c <= MAXC; c++) M.col_off[c] = h->col_off[c];
+    for (int l = 0; l < NL; l++)
+        for (int t = 0; t < 256; t++) M.cp.J[l][t] = l < h->n_labels ? (R)h->J[l][t] : R(0);
+    for (int a = 0; a < NG; a++) M.cp.K[a] = (R)h->K[a];
+    return M;
+}
+template <class F>
+static int32_t dispatch_d(const scmc_handle* h, F&& f) {
+    auto with_nl = [&](auto rt, auto gen, auto ons) -> int32_t {
+        if (h->n_labels == 1) return f(rt, gen, ons, ic<1>{});
+        return f(rt, gen, ons, ic<MAXL>{});
+    };
+    auto with_gen = [&](auto rt) -> int32_t {
+        switch (h->gen_id) {
+            case 1: return with_nl(rt, ic<1>{}, ic<0>{});
+            case 2: return h->onsite ? with_nl(rt, ic<2>{}, ic<1>{}) : with_nl(rt, ic<2>{}, ic<0>{});
+            case 3: return with_nl(rt, ic<3>{}, ic<0>{});
+        }
+        return SCMC_ERR_ARG;
+    };
+    return h->prec == 64 ? with_gen(double{}) : with_gen(float{});
+}
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+struct DevBuf {   // RAII device scratch
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T* as() { return (T*)p; }
+};
+
+}  // namespace scmc
+
+using namespace scmc;
+
+extern "C" {
+
+int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_results* out) {
+    SCMC_ARG(h && p && out, "null argument");
+    SCMC_ARG(p->T && p->T_i && p->sigma, "scmc_run_metropolis: T, T_i and sigma arrays required");
+    SCMC_ARG(p->n_therm >= 0 && p->n_measure >= 0 && p->measurement_rate >= 1 && p->hits >= 1, "scmc_run_metropolis: bad counts");
+    SCMC_CK(cudaSetDevice(h->device));
+    const int64_t R = h->R, rate = p->measurement_rate;
+    const int64_t n_anneal = (int64_t)std::ceil(0.75 * (double)p->n_therm);
+    const int64_t total = p->n_therm + p->n_measure;
+    const int64_t meas_start = std::max<int64_t>(p->n_therm + 1, (int64_t)p->sweep0 + 1);
+    const int64_t rows_total = total >= meas_start ? total / rate - (meas_start - 1) / rate : 0;
+    DevBuf dT, dTi, dser;
+    SCMC_CK(dT.alloc(R * 8)); SCMC_CK(dTi.alloc(R * 8));
+    SCMC_CK(cudaMemcpyAsync(dT.p, p->T, R * 8, cudaMemcpyHostToDevice, h->stream));
+    SCMC_CK(cudaMemcpyAsync(dTi.p, p->T_i, R * 8, cudaMemcpyHostToDevice, h->stream));
+    SCMC_TRY(upload_scalars(h, nullptr, p->sigma));
+    SCMC_CK(cudaMemsetAsync(h->acc, 0, R * sizeof(unsigned long long), h->stream));
+    const size_t row_bytes = (size_t)R * SCMC_NOBS * 8;
+    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(rows_total, 1), (int64_t)((512ull << 20) / row_bytes)));
+    SCMC_CK(dser.alloc(chunk_rows * row_bytes));
+    std::vector<double> host_chunk, mean_acc;
+    if (out->mean) mean_acc.assign((size_t)R * SCMC_NOBS, 0.0);
+    if (!out->series && out->mean) host_chunk.resize((size_t)chunk_rows * R * SCMC_NOBS);
+    const double att_per_sweep = (double)p->hits * (double)h->N;
+    const unsigned gR = grid_for(R, 128);
+    auto set_beta = [&](int64_t sweep) -> int32_t {
+        if (h->prec == 64) k_set_beta<double><<<gR, 128, 0, h->stream>>>(R, dT.as<double>(), dTi.as<double>(), sweep, n_anneal, (double*)h->beta);
+        else k_set_beta<float><<<gR, 128, 0, h->stream>>>(R, dT.as<double>(), dTi.as<double>(), sweep, n_anneal, (float*)h->beta);
+        h->launches++;
+        SCMC_CK(cudaGetLastError());
+        return SCMC_OK;
+    };
+    // ---- thermalisation (MonteCarlo.jl:38-66)
+    int64_t n_log = 0;
+    for (int64_t sweep = (int64_t)p->sweep0 + 1; sweep <= p->n_therm; sweep++) {
+        SCMC_TRY(set_beta(sweep));
+        SCMC_TRY(launch_sweeps(h, 1, p->hits, p->seed, (uint64_t)(sweep - 1), nullptr));
+        if (sweep % rate == 0) {
+            if (out->therm_energy) {
+                SCMC_TRY(launch_measure(h, h->obs));
+                SCMC_CK(cudaMemcpy2DAsync(out->therm_energy + n_log * R, 8, h->obs, SCMC_NOBS * 8, 8, R, cudaMemcpyDeviceToHost, h->stream));
+                n_log++;
+            }
+            if (h->prec == 64) k_adapt_sigma<double><<<gR, 128, 0, h->stream>>>(R, h->acc, att_per_sweep * (double)rate, (double*)h->sigma);
+            else k_adapt_sigma<float><<<gR, 128, 0, h->stream>>>(R, h->acc, att_per_sweep * (double)rate, (float*)h->sigma);
+            h->launches++;
+            SCMC_CK(cudaGetLastError());
+        }
+    }
+    // ---- measurement (MonteCarlo.jl:69-99); sigma frozen
+    SCMC_TRY(set_beta(0));
+    SCMC_CK(cudaMemsetAsync(h->acc, 0, R * sizeof(unsigned long long), h->stream));
+    int64_t rows = 0, in_chunk = 0, n_meas_sweeps = 0;
+    auto flush = [&]() -> int32_t {
+        if (in_chunk == 0) return SCMC_OK;
+        double* dst = out->series ? out->series + (size_t)(rows - in_chunk) * R * SCMC_NOBS : (host_chunk.empty() ? nullptr : host_chunk.data());
+        if (dst) {
+            SCMC_CK(cudaMemcpyAsync(dst, dser.p, (size_t)in_chunk * row_bytes, cudaMemcpyDeviceToHost, h->stream));
+            SCMC_CK(cudaStreamSynchronize(h->stream));
+            if (out->mean)
+                for (int64_t q = 0; q < in_chunk; q++)
+                    for (size_t t = 0; t < (size_t)R * SCMC_NOBS; t++) mean_acc[t] += dst[(size_t)q * R * SCMC_NOBS + t];
+        }
+        in_chunk = 0;
+        return SCMC_OK;
+    };
+    for (int64_t sweep = meas_start; sweep <= total; sweep++) {
+        SCMC_TRY(launch_sweeps(h, 1, p->hits, p->seed, (uint64_t)(sweep - 1), nullptr));
+        n_meas_sweeps++;
+        if (sweep % rate == 0) {
+            SCMC_TRY(launch_measure(h, dser.as<double>() + (size_t)in_chunk * R * SCMC_NOBS));
+            in_chunk++; rows++;
+            if (in_chunk == chunk_rows) SCMC_TRY(flush());
+        }
+    }
+    SCMC_TRY(flush());
+    out->n_rows = rows;
+    if (out->mean) for (size_t t = 0; t < (size_t)R * SCMC_NOBS; t++) out->mean[t] = rows ? mean_acc[t] / (double)rows : 0.0;
+    // results: sigma, acceptance
+    std::vector<unsigned long long> acc(R);
+    SCMC_CK(cudaMemcpyAsync(acc.data(), h->acc, R * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<char> sg(R * h->esz());
+    SCMC_CK(cudaMemcpyAsync(sg.data(), h->sigma, sg.size(), cudaMemcpyDeviceToHost, h->stream));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    for (int64_t r = 0; r < R; r++) {
+        p->sigma[r] = h->prec == 64 ? ((double*)sg.data())[r] : (double)((float*)sg.data())[r];
+        if (out->acc_rate) out->acc_rate[r] = n_meas_sweeps ? (double)acc[r] / (att_per_sweep * (double)n_meas_sweeps) : 0.0;
+    }
+    return SCMC_OK;
+}
+
+int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results* out) {
+    SCMC_ARG(h && p && out, "null argument");
+    SCMC_ARG(p->T_i > 0 && p->T_fac > 0 && p->N_max >= 1 && p->N_per_T >= 1 && p->hits >= 1, "scmc_anneal: bad parameters");
+    SCMC_CK(cudaSetDevice(h->device));
+    const int64_t R = h->R;
+    std::vector<double> b0(R, 1.0 / p->T_i), s0(R, p->sigma0);
+    SCMC_TRY(upload_scalars(h, b0.data(), s0.data()));
+    DevBuf dsat, ddone, dnact;
+    SCMC_CK(dsat.alloc(R * 8)); SCMC_CK(ddone.alloc(R * 8)); SCMC_CK(dnact.alloc(sizeof(int)));
+    SCMC_CK(cudaMemsetAsync(dsat.p, 0, R * 8, h->stream));
+    SCMC_CK(cudaMemsetAsync(ddone.p, 0, R * 8, h->stream));
+    SCMC_CK(cudaMemsetAsync(h->acc, 0, R * sizeof(unsigned long long), h->stream));
+    SCMC_CK(cudaMemsetAsync(h->active, 1, R, h->stream));
+    const double att_per_sweep = (double)p->hits * (double)h->N, min_accepted = (double)p->min_acc_per_site * (double)h->N;
+    const unsigned gR = grid_for(R, 128);
+    int n_active = (int)std::min<int64_t>(R, 1 << 30);
+    const int check_every = 16;
+    for (int64_t sweep = 1; sweep < p->N_max && n_active > 0; sweep++) {
+        SCMC_TRY(launch_sweeps(h, 1, p->hits, p->seed, (uint64_t)(sweep - 1), h->active));
+        const bool check = (sweep % check_every == 0) || (sweep + 1 >= p->N_max);
+        SCMC_CK(cudaMemsetAsync(dnact.p, 0, sizeof(int), h->stream));
+        const int last = (sweep + 1 >= p->N_max) ? 1 : 0;
+        if (h->prec == 64)
+            k_anneal_ctrl<double><<<gR, 128, 0, h->stream>>>(R, h->acc, dsat.as<int64_t>(), ddone.as<int64_t>(), h->active, (double*)h->beta, (double*)h->sigma,
+                                                            att_per_sweep, min_accepted, p->N_per_T, last, 1.0 / p->T_fac, p->min_accrate, p->sigma_min,
+                                                            dnact.as<int>());
+        else
+            k_anneal_ctrl<float><<<gR, 128, 0, h->stream>>>(R, h->acc, dsat.as<int64_t>(), ddone.as<int64_t>(), h->active, (float*)h->beta, (float*)h->sigma,
+                                                           att_per_sweep, min_accepted, p->N_per_T, last, 1.0 / p->T_fac, p->min_accrate, p->sigma_min,
+                                                           dnact.as<int>());
+        h->launches++;
+        SCMC_CK(cudaGetLastError());
+        if (check) {
+            SCMC_CK(cudaMemcpyAsync(&n_active, dnact.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            SCMC_CK(cudaStreamSynchronize(h->stream));
+        }
+    }
+    SCMC_CK(cudaMemsetAsync(h->active, 1, R, h->stream));
+    if (out->E) SCMC_TRY(scmc_energy(h, out->E));
+    std::vector<char> buf(R * h->esz());
+    for (int pass = 0; pass < 2; pass++) {
+        double* dst = pass ? out->sigma : out->beta;
+        if (!dst) continue;
+        SCMC_CK(cudaMemcpyAsync(buf.data(), pass ? h->sigma : h->beta, buf.size(), cudaMemcpyDeviceToHost, h->stream));
+        SCMC_CK(cudaStreamSynchronize(h->stream));
+        for (int64_t r = 0; r < R; r++) dst[r] = h->prec == 64 ? ((double*)buf.data())[r] : (double)((float*)buf.data())[r];
+    }
+    if (out->sweeps) {
+        SCMC_CK(cudaMemcpyAsync(out->sweeps, ddone.p, R * 8, cudaMemcpyDeviceToHost, h->stream));
+        SCMC_CK(cudaStreamSynchronize(h->stream));
+    }
+    return SCMC_OK;
+}
+
+int32_t scmc_optimize(scmc_t* h, int64_t n_sweeps, double* E) {
+    SCMC_ARG(h && n_sweeps >= 0, "bad argument");
+    SCMC_CK(cudaSetDevice(h->device));
+    for (int64_t s = 0; s < n_sweeps; s++)
+        for (int c = 0; c < h->n_col; c++) {
+            SCMC_TRY(dispatch_d(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+                using R = decltype(rt);
+                constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+                constexpr bool ONS = decltype(ons)::value != 0;
+                const int nc = h->col_off[c + 1] - h->col_off[c];
+                if (nc == 0) return SCMC_OK;
+                auto M = make_model_d<R, NL>(h);
+                k_optimize_colour<R, GEN, ONS, NL><<<grid_for(h->R * nc, 128), 128, 0, h->stream>>>(M, c, 48);
+                h->launches++;
+                SCMC_CK(cudaGetLastError());
+                return SCMC_OK;
+            }));
+        }
+    if (E) return scmc_energy(h, E);
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    return SCMC_OK;
+}
+
+int32_t scmc_structure_factor(scmc_t* h, const double* ks, const double* pos, int32_t nk, int32_t dim, double n_rs, double* Sak) {
+    SCMC_ARG(h && ks && pos && Sak, "null argument");
+    SCMC_ARG(nk >= 1 && dim >= 1 && dim <= 3 && n_rs > 0, "scmc_structure_factor: bad nk / dim / n_rs");
+    SCMC_CK(cudaSetDevice(h->device));
+    std::vector<double> ppos((size_t)h->N * dim);
+    for (int64_t q = 0; q < h->N; q++)
+        for (int x = 0; x < dim; x++) ppos[(size_t)q * dim + x] = pos[(size_t)h->orig[q] * dim + x];
+    DevBuf dk, dp, dout;
+    SCMC_CK(dk.alloc((size_t)nk * dim * 8)); SCMC_CK(dp.alloc(ppos.size() * 8));
+    const size_t out_bytes = (size_t)h->R * 16 * nk * 8;
+    SCMC_CK(dout.alloc(out_bytes));
+    SCMC_CK(cudaMemcpyAsync(dk.p, ks, (size_t)nk * dim * 8, cudaMemcpyHostToDevice, h->stream));
+    SCMC_CK(cudaMemcpyAsync(dp.p, ppos.data(), ppos.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    const dim3 grid(grid_for(nk, 128), (unsigned)std::min<int64_t>(h->R, 65535));
+    SCMC_ARG(h->R <= 65535, "scmc_structure_factor: more than 65535 replicas per call not supported");
+    if (h->prec == 64)
+        k_structure_factor<double><<<grid, 128, 0, h->stream>>>((const double4*)h->T, (int)h->N, (int)h->Ns, h->R, dk.as<double>(), dp.as<double>(), nk, dim, 1.0 / n_rs, dout.as<double>());
+    else
+        k_structure_factor<float><<<grid, 128, 0, h->stream>>>((const float4*)h->T, (int)h->N, (int)h->Ns, h->R, dk.as<double>(), dp.as<double>(), nk, dim, 1.0 / n_rs, dout.as<double>());
+    h->launches++;
+    SCMC_CK(cudaGetLastError());
+    SCMC_CK(cudaMemcpyAsync(Sak, dout.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    return SCMC_OK;
+}
+
+int32_t scmc_correlations(scmc_t* h, int64_t r, const int32_t* project, int64_t n_rs, double* C) {
+    SCMC_ARG(h && project && C, "null argument");
+    SCMC_ARG(r >= 0 && r < h->R && n_rs >= 1, "replica out of range / bad n_rs");
+    SCMC_ARG(h->N <= 46340, "scmc_correlations: N too large for the all-pairs reference algorithm");
+    for (int64_t t = 0; t < h->N * h->N; t++) SCMC_ARG(project[t] >= 0 && project[t] < n_rs, "scmc_correlations: project index out of range");
+    SCMC_CK(cudaSetDevice(h->device));
+    DevBuf dproj, dperm, dC;
+    SCMC_CK(dproj.alloc((size_t)h->N * h->N * 4)); SCMC_CK(dperm.alloc(h->N * 4)); SCMC_CK(dC.alloc((size_t)16 * n_rs * 8));
+    SCMC_CK(cudaMemcpyAsync(dproj.p, project, (size_t)h->N * h->N * 4, cudaMemcpyHostToDevice, h->stream));
+    SCMC_CK(cudaMemcpyAsync(dperm.p, h->perm.data(), h->N * 4, cudaMemcpyHostToDevice, h->stream));
+    SCMC_CK(cudaMemsetAsync(dC.p, 0, (size_t)16 * n_rs * 8, h->stream));
+    if (h->prec == 64)
+        k_correlations<double><<<grid_for(h->N * h->N, 256), 256, 0, h->stream>>>((const double4*)h->T, (int)h->N, (int)h->Ns, h->R, r, dperm.as<int32_t>(), dproj.as<int32_t>(), n_rs, dC.as<double>());
+    else
+        k_correlations<float><<<grid_for(h->N * h->N, 256), 256, 0, h->stream>>>((const float4*)h->T, (int)h->N, (int)h->Ns, h->R, r, dperm.as<int32_t>(), dproj.as<int32_t>(), n_rs, dC.as<double>());
+    h->launches++;
+    SCMC_CK(cudaGetLastError());
+    SCMC_CK(cudaMemcpyAsync(C, dC.p, (size_t)16 * n_rs * 8, cudaMemcpyDeviceToHost, h->stream));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    return SCMC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+"""su(4) spin-valley generators T^a = sigma^mu (x) tau^nu at parton filling n.
+
+Host-side mirror of `getGenerators`, `get_su4index`, `expval`
+(/root/reference/src/Generators.jl:2-28, 82-84).  Built directly on Fock-state
+bit patterns: a one-body operator  O = sum_{pq} M_pq c_p^dagger c_q  with
+M = kron(sigma^mu, sigma^nu) moves one parton from mode q to mode p.  Like the
+reference (Generators.jl:39-51) the hop carries NO fermionic sign, so
+that n=2 tables equal the reference's.  Basis order = ascending Fock integer with
+mode 0 = (up,+) the least significant bit, i.e. n=1: (up+, up-, dn+, dn-),
+n=2: integers [3, 5, 6, 9, 10, 12].
+
+`emit_cuda_tables()` writes the same tables as `constexpr` integer arrays
+(`csrc/gen_tables.h`) so the CUDA kernels unroll the sparse contraction at
+compile time; `scmc_create` compares caller-supplied generators against them
+and falls back to the data-driven path when they differ.
+"""
+import numpy as np
+
+_PAULI = np.array(
+    [[[1, 0], [0, 1]], [[0, 1], [1, 0]], [[0, -1j], [1j, 0]], [[1, 0], [0, -1]]],
+    dtype=np.complex128,
+)
+
+
+def get_su4index(mu, nu):
+    """1-based generator index as in the reference (Generators.jl:26-28)."""
+    return 4 * mu + nu + 1
+
+
+def fock_states(n):
+    return [m for m in range(16) if bin(m).count("1") == n]
+
+
+def _one_body(M, states):
+    idx = {m: i for i, m in enumerate(states)}
+    d = len(states)
+    out = np.zeros((d, d), dtype=np.complex128)
+    for col, m in enumerate(states):
+        for q in range(4):
+            if not (m >> q) & 1:
+                continue
+            emptied = m & ~(1 << q)
+            for p in range(4):
+                if M[p, q] == 0 or (emptied >> p) & 1:
+                    continue
+                out[idx[emptied | (1 << p)], col] += M[p, q]
+    return out
+
+
+def getGenerators(n):
+    """[16, d, d] complex; G[a] = sigma^mu (x) tau^nu, a = 4 mu + nu (0-based)."""
+    if n not in (1, 2, 3):
+        raise ValueError("filling n must be 1, 2 or 3")
+    states = fock_states(n)
+    return np.stack([_one_body(np.kron(_PAULI[mu], _PAULI[nu]), states) for mu in range(4) for nu in range(4)])
+
+
+def getGeneratorsSq(n):
+    g = getGenerators(n)
+    return np.einsum("aij,ajk->aik", g, g)
+
+
+def expval(M, state):
+    """<state| M |state> (Generators.jl:82-84)."""
+    state = np.asarray(state)
+    return np.vdot(state, np.asarray(M) @ state)
+
+
+def _quantise(g):
+    re_ = np.rint(g.real).astype(int)
+    im_ = np.rint(g.imag).astype(int)
+    assert np.allclose(re_, g.real) and np.allclose(im_, g.imag), "generator entries must be integers"
+    return re_, im_
+
+
+def _term(coef, name):
+    if coef == 0:
+        return ""
+    sign = "+" if coef > 0 else "-"
+    mag = abs(coef)
+    return f" {sign} {name}" if mag == 1 else f" {sign} R({mag}) * {name}"
+
+
+def _emit_expect(fname, g):
+    """Straight-line T^a = sum_jk conj(psi_j) G^a_jk psi_k using P_jk = conj(psi_j) psi_k (j <= k) and hermiticity."""
+    gre, gim = _quantise(g)
+    d = g.shape[1]
+    used = set()
+    rows = []
+    for a in range(16):
+        expr = ""
+        for j in range(d):
+            expr += _term(gre[a, j, j], f"p{j}{j}r")
+            if gre[a, j, j]:
+                used.add((j, j, "r"))
+            for k in range(j + 1, d):
+                # G_jk P_jk + G_kj P_kj = 2 (Re G_jk Re P_jk - Im G_jk Im P_jk)
+                if gre[a, j, k]:
+                    expr += _term(2 * gre[a, j, k], f"p{j}{k}r"); used.add((j, k, "r"))
+                if gim[a, j, k]:
+                    expr += _term(-2 * gim[a, j, k], f"p{j}{k}i"); used.add((j, k, "i"))
+        rows.append(f"    T[{a}] = R(0){expr};" if expr else f"    T[{a}] = R(0);")
+    out = [f"template <class R> __device__ __forceinline__ void {fname}(const R* re, const R* im, R* T) {{"]
+    for (j, k, part) in sorted(used):
+        if part == "r":
+            out.append(f"    const R p{j}{k}r = re[{j}] * re[{k}] + im[{j}] * im[{k}];")
+        else:
+            out.append(f"    const R p{j}{k}i = re[{j}] * im[{k}] - im[{j}] * re[{k}];")
+    out += rows + ["}"]
+    return out
+
+
+def _emit_hloc(fname, g, gsq):
+    """H_loc = sum_a h[a] G^a + K[a] (G^a)^2 ; upper triangle j <= k into Hr[j*D+k], Hi[j*D+k]."""
+    gre, gim = _quantise(g)
+    qre, qim = _quantise(gsq)
+    d = g.shape[1]
+    out = [f"template <class R, bool ONSITE> __device__ __forceinline__ void {fname}(const R* h, const R* K, R* Hr, R* Hi) {{"]
+    for j in range(d):
+        for k in range(j, d):
+            er = "".join(_term(gre[a, j, k], f"h[{a}]") for a in range(16))
+            ei = "".join(_term(gim[a, j, k], f"h[{a}]") for a in range(16))
+            qr = "".join(_term(qre[a, j, k], f"K[{a}]") for a in range(16))
+            qi = "".join(_term(qim[a, j, k], f"K[{a}]") for a in range(16))
+            out.append(f"    Hr[{j * d + k}] = R(0){er}; Hi[{j * d + k}] = R(0){ei};")
+            if qr or qi:
+                out.append(f"    if (ONSITE) {{ Hr[{j * d + k}] += R(0){qr}; Hi[{j * d + k}] += R(0){qi}; }}")
+    out.append("}")
+    return out
+
+
+def emit_cuda_tables(path):
+    """Write csrc/gen_code.h: unrolled expectation-value / local-Hamiltonian code and integer tables for n = 1, 2, 3."""
+    lines = [
+        "// GENERATED by semiclassicalmc.jl_b200/generators.py:emit_cuda_tables -- do not edit by hand.",
+        "// su(4) generators G^a = sigma^mu (x) tau^nu at filling n, reference convention",
+        "// (/root/reference/src/Generators.jl:2-65, signless parton operator); `gK` = filling n = K.",
+        "// spin_expect_*   : T^a   = <psi|G^a|psi>      (replaces the dense loop of src/Configuration.jl:166-194)",
+        "// spin_expect_sq_*: Tsq^a = <psi|(G^a)^2|psi>  (generatorsSq, src/Configuration.jl:52,59)",
+        "// hloc_*          : H_loc = sum_a h^a G^a + K^a (G^a)^2, upper triangle (for the on-device local optimiser)",
+        "#pragma once",
+        "#include <cstdint>",
+        "namespace scmc { namespace gen {",
+    ]
+    for n in (1, 2, 3):
+        g, q = getGenerators(n), getGeneratorsSq(n)
+        lines += _emit_expect(f"spin_expect_g{n}", g)
+        lines += _emit_expect(f"spin_expect_sq_g{n}", q)
+        lines += _emit_hloc(f"hloc_g{n}", g, q)
+        for name, arr in (("G", g), ("Gsq", q)):
+            re_, im_ = _quantise(arr)
+            for part, tab in (("re", re_), ("im", im_)):
+                flat = ",".join(str(int(v)) for v in tab.reshape(-1))
+                lines.append(f"static const int8_t {name}{n}_{part}[16 * {g.shape[1]} * {g.shape[1]}] = {{{flat}}};")
+    lines.append("}}  // namespace scmc::gen")
+    with open(path, "w") as fh:
+        fh.write("\n".join(lines) + "\n")

@@ -1,0 +1,131 @@
+"""Observables -- host mirror of /root/reference/src/Observables/Observables.jl and ObservablesGeneric.jl.
+Reductions over the lattice (energy, magnetisation, correlations, structure factor) run on the device through the C ABI."""
+import numpy as np
+
+from . import _lib
+from .binning import LogBinner, ErrorPropagator
+from .lattice import getKsInBox  # noqa: F401  (re-export, Observables.jl:91-98)
+
+
+class Observables:
+    pass
+
+
+def getMagnetization(cfg, replica=0):
+    """sum_i T_i / N (Observables.jl:16-18) from the device reduction."""
+    return cfg.measure()[replica, 5:21]
+
+
+def getRs(cfg):
+    """All r_i - r_j representatives: positions - (positions[0] + b) for every basis vector b (Observables.jl:44-46)."""
+    return np.concatenate([cfg.positions - (cfg.positions[0] + b) for b in cfg.basis], axis=0)
+
+
+def getProject(cfg):
+    """m[i, j] with r_i - r_j = rs[m[i, j]] under periodic boundaries (Observables.jl:49-80), 0-based.
+    Uses integer cell coordinates instead of the reference's O(N^3) search; identical map."""
+    L, nb = cfg.L, len(cfg.basis)
+    cells, bl = cfg.lattice.cells, cfg.basisLabels - 1
+    rs = getRs(cfg)
+    vecs = np.stack(cfg.unitVectors)
+    # candidate slot for (cell difference dn, basis pair): the site with cell dn and basis bi, in block bj  ->  verify numerically
+    N = cfg.nSites
+    dim = cells.shape[1]
+    strides = np.array([L ** (dim - 1 - k) for k in range(dim)])
+    proj = np.zeros((N, N), dtype=np.int32)
+    basis = np.stack(cfg.basis)
+    for i in range(N):
+        dn = (cells[i][None, :] - cells) % L                      # [N, dim]
+        db = basis[bl[i]][None, :] - basis[bl]                    # [N, dim_space]
+        r = dn @ vecs + db
+        # rs block b holds positions - positions[0] - basis[b]; look for site (cell dn, basis s) with basis[s] - basis[0] - basis[b] = db
+        best = np.full(N, np.iinfo(np.int64).max, dtype=np.int64)
+        for b in range(nb):
+            for s_ in range(nb):
+                ok = np.all(np.abs((basis[s_] - basis[0] - basis[b])[None, :] - db) < 1e-10, axis=1)
+                idx = b * N + s_ + nb * (dn @ strides)
+                best = np.where(ok & (idx < best), idx, best)     # first match in rs order (the reference uses findfirst)
+        assert np.all(best < nb * N) and np.allclose(rs[best], r, atol=1e-9)
+        proj[i] = best
+    return proj
+
+
+def getCorrelations(cfg, project, replica=0):
+    """C[a, m] = sum_{i,j: project[i,j] = m} T_i^a T_j^a (Observables.jl:22-41), on the device."""
+    project = np.ascontiguousarray(project, dtype=np.int32)
+    n_rs = len(cfg.basis) * cfg.nSites
+    Cm = np.zeros((16, n_rs))
+    _lib.check(cfg._lib.scmc_correlations(cfg._h, replica, _lib.iptr(project), n_rs, _lib.dptr(Cm)))
+    return Cm
+
+
+def computeStructureFactorVec(correlation, rs, ks):
+    """sf[a, k] = (1/|rs|) sum_n cos(k.r_n) C[a, n] (Observables.jl:116-128) for host-side correlation matrices."""
+    rs, ks = np.asarray(rs), np.asarray(ks)
+    return (np.asarray(correlation) @ np.cos(rs @ ks.T)) / rs.shape[0]
+
+
+def computeStructureFactor(correlation, rs, ks, components=None):
+    """Observables.jl:101-113; default components = rows 1..15 of the reference (0..14 here)."""
+    comps = list(range(np.shape(correlation)[0] - 1)) if components is None else list(components)
+    return computeStructureFactorVec(correlation, rs, ks)[comps].sum(axis=0)
+
+
+def structureFactor(cfg, ks):
+    """Device path: S^a(k) = |sum_i T_i^a e^{ik.r_i}|^2 / |rs| for every replica, [R, 16, nk]; equals
+    computeStructureFactorVec(getCorrelations(cfg, getProject(cfg)), getRs(cfg), ks) on allowed momenta."""
+    ks = _lib.f64(ks)
+    pos = _lib.f64(cfg.positions)
+    out = np.zeros((cfg.n_replicas, 16, ks.shape[0]))
+    _lib.check(cfg._lib.scmc_structure_factor(cfg._h, _lib.dptr(ks), _lib.dptr(pos), ks.shape[0], ks.shape[1],
+                                              float(len(cfg.basis) * cfg.nSites), _lib.dptr(out)))
+    return out
+
+
+class ObservablesGeneric(Observables):
+    """Accumulators of ObservablesGeneric.jl:3-29, one set per replica."""
+
+    def __init__(self, cfg, correlations=False):
+        R = cfg.n_replicas
+        self.energy = [ErrorPropagator(2) for _ in range(R)]
+        self.sigma = [LogBinner() for _ in range(R)]
+        self.tau = [LogBinner() for _ in range(R)]
+        self.sigmatau = [LogBinner() for _ in range(R)]
+        self.magnetizationVec = [LogBinner(np.zeros(16)) for _ in range(R)]
+        self.rs = getRs(cfg)
+        self.with_correlations = correlations
+        self.project = getProject(cfg) if correlations else None
+        self.correlations = [LogBinner(np.zeros((16, len(cfg.basis) * cfg.nSites))) for _ in range(R)] if correlations else None
+
+    def push_rows(self, rows):
+        """rows: [n, R, 21] measurement rows from the device."""
+        for row in rows:
+            for r, x in enumerate(row):
+                self.energy[r].push(x[0], x[1]); self.sigma[r].push(x[2]); self.tau[r].push(x[3]); self.sigmatau[r].push(x[4])
+                self.magnetizationVec[r].push(x[5:21])
+
+
+def initializeObservables(obstype, cfg, **kw):
+    return obstype(cfg, **kw)
+
+
+def measure_(obs, cfg, E=None):
+    """measure! (ObservablesGeneric.jl:32-46): one measurement of every replica; E is re-summed on the device."""
+    obs.push_rows(cfg.measure()[None])
+    if obs.with_correlations:
+        for r in range(cfg.n_replicas):
+            obs.correlations[r].push(getCorrelations(cfg, obs.project, r))
+
+
+def means(obs, cfg, beta, replica=0):
+    """The `means/*` group written by saveMeans! (ObservablesGeneric.jl:49-72) as a dict (mean, error)."""
+    N = cfg.nSites
+    e = obs.energy[replica]
+    c = lambda m: beta * beta * (m[1] - m[0] * m[0]) * N
+    dc = lambda m: np.array([-2.0 * beta * beta * m[0] * N, beta * beta * N])
+    out = {"energy": (e.means()[0], e.std_errors()[0]), "heat": (e.mean(c), e.std_error(dc))}
+    for name, b in (("σ", obs.sigma), ("τ", obs.tau), ("στ", obs.sigmatau), ("magnetizationVec", obs.magnetizationVec)):
+        out[name] = (b[replica].mean(), b[replica].std_error())
+    if obs.with_correlations:
+        out["correlations"] = (obs.correlations[replica].mean(), obs.correlations[replica].std_error())
+    return out

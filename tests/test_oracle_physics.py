@@ -1,0 +1,155 @@
+"""Pins the C oracle (oracle/scmc_oracle.c) with analytic identities and the notebook's recorded
+outputs (doc/examples.ipynb cells 13 and 25), and checks the product's host-side geometry against the oracle's."""
+import numpy as np
+import pytest
+
+from conftest import NOTEBOOK_J, random_symmetric_J, random_states
+from oracle import lattice as ol
+from oracle import oracle as orc
+
+
+def tri_oracle(L, J=NOTEBOOK_J, n=1, K=None):
+    pos, nbr, lab, bl = ol.triangular(L)
+    return orc.Oracle(nbr, lab, J, np.zeros(16) if K is None else K, n), pos, nbr
+
+
+def test_expectation_identities_n1():
+    o, _, _ = tri_oracle(3)
+    o.seed(11); o.randomize()
+    T, Tsq = o.get_T()
+    assert np.allclose(T[:, 0], 1.0, atol=1e-14)
+    assert np.allclose((T[:, 1:] ** 2).sum(axis=1), 3.0, atol=1e-13)
+    assert np.allclose(Tsq, 1.0, atol=1e-14)
+    psi = o.get_state()
+    for i, j in ((0, 1), (2, 5), (3, 3)):
+        assert np.isclose(T[i] @ T[j], 4 * abs(np.vdot(psi[i], psi[j])) ** 2, atol=1e-13)     # Fierz identity
+
+
+def test_expectation_matches_numpy_n2():
+    pos, nbr, lab, bl = ol.honeycomb(2)
+    o = orc.Oracle(nbr, lab, np.eye(16), np.arange(16) * 0.1, 2)
+    o.seed(5); o.randomize()
+    T, Tsq = o.get_T()
+    psi = o.get_state()
+    assert np.allclose(T, np.einsum("ij,ajk,ik->ia", psi.conj(), o.gen, psi).real, atol=1e-13)
+    assert np.allclose(Tsq, np.einsum("ij,ajk,ik->ia", psi.conj(), o.gensq, psi).real, atol=1e-13)
+    assert np.allclose(T[:, 0], 2.0)
+
+
+def test_energy_and_difference_consistent():
+    J = random_symmetric_J(3)
+    o, _, nbr = tri_oracle(4, J)
+    o.seed(2); o.randomize()
+    T, _ = o.get_T()
+    E = o.energy()
+    assert np.isclose(E, 0.5 * sum(T[i] @ J @ T[nbr[i, k]] for i in range(16) for k in range(6)), rtol=1e-13)
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        i = int(rng.integers(16))
+        ok, dE = o.local_update(i, rng.standard_normal(8), 0.0, 1.0, 0.5)     # u = 0 -> always accepted
+        assert ok
+        E2 = o.energy()
+        assert np.isclose(E2 - E, dE, atol=1e-12)
+        assert np.isclose(dE, 0, atol=100) and np.allclose(o.local_field(i) @ (o.get_T()[0][i] - T[i]), dE, atol=1e-12)
+        E, T = E2, o.get_T()[0]
+
+
+def test_heisenberg_bond_energy_and_ground_states():
+    pos, nbr, lab, bl = ol.honeycomb(3)
+    for Jv, expected in ((-1.0, 4 * -1.0 * 3 / 2), (1.0, 0.0)):
+        o = orc.Oracle(nbr, lab, Jv * np.eye(16), np.zeros(16), 1)
+        psi = np.zeros((18, 4), dtype=complex)
+        if Jv < 0:
+            psi[:, 0] = 1            # ferromagnet
+        else:
+            psi[bl == 1, 0] = 1; psi[bl == 2, 1] = 1      # orthogonal neighbours on the bipartite lattice
+        o.set_state(psi)
+        assert np.isclose(o.energy() / 18, expected + (0 if Jv < 0 else 0), atol=1e-13) or np.isclose(o.energy() / 18, expected + Jv * 3 / 2 * 0, atol=1e-13)
+    # bond energy 4 J |<psi_i|psi_j>|^2
+    rng = np.random.default_rng(1)
+    o = orc.Oracle(nbr, lab, 0.7 * np.eye(16), np.zeros(16), 1)
+    psi = random_states(rng, 18, 4); o.set_state(psi)
+    Eb = 0.5 * sum(4 * 0.7 * abs(np.vdot(psi[i], psi[nbr[i, k]])) ** 2 for i in range(18) for k in range(3))
+    assert np.isclose(o.energy(), Eb, rtol=1e-13)
+
+
+def test_notebook_ground_state_energy_exact():
+    """FM spin (x) 120-degree valley order gives E/N = -3.6 exactly on triangular L % 3 == 0."""
+    L = 6
+    o, pos, nbr = tri_oracle(L)
+    psi = np.zeros((L * L, 4), dtype=complex)
+    for i in range(L):
+        for j in range(L):
+            ang = 2 * np.pi / 3 * ((i - j) % 3)
+            valley = np.array([np.cos(ang / 2), np.sin(ang / 2)])      # tau in the x-z plane at angle `ang`
+            psi[j + L * i] = np.kron([1, 0], valley)
+    o.set_state(psi)
+    assert np.isclose(o.energy() / (L * L), -3.6, atol=1e-13)
+
+
+@pytest.mark.timeout(300)
+def test_notebook_thermal_observables():
+    """examples.ipynb cell 13: e = -3.540997(91), c = 2.933(58), |m_sigma| = 0.993221(8), |m_tau| = 0.02001(13), |m_sigmatau| = 0.02885(11)
+    at T = 0.02 on triangular L = 6 (1e5 + 1e5 sweeps there; 2e4 + 3e4 here, so wider windows)."""
+    o, _, _ = tri_oracle(6)
+    o.seed(20230301); o.randomize()
+    res = o.run_metropolis(0.02, 1.0, 20000, 30000, 10)
+    s = res["series"]
+    e_err = orc.log_binning_error(s[:, 0])
+    assert abs(s[:, 0].mean() - (-3.540997)) < 5 * e_err + 3e-4
+    assert abs(orc.specific_heat(s[:, 0], s[:, 1], 50.0, 36) - 2.933) < 0.25
+    assert abs(s[:, 2].mean() - 0.993221) < 2e-4
+    assert abs(s[:, 3].mean() - 0.02001) < 2e-3
+    assert abs(s[:, 4].mean() - 0.02885) < 2e-3
+    assert 0.4 < res["acc_rate"] < 0.6          # cells 11/15/17/19: 0.497 - 0.5125
+
+
+@pytest.mark.timeout(300)
+def test_notebook_annealing_energy():
+    """examples.ipynb cell 25 (L = 12): E/N -> -3.597 after SA, -3.599993 after 10 optimisation sweeps; exact -3.6.  L = 6 here for speed."""
+    o, _, _ = tri_oracle(6)
+    o.seed(7); o.randomize()
+    res = o.run_annealing(3.0, T_fac=0.98, N_max=20000, N_o=10, N_per_T=100, min_acc_per_site=10, min_accrate=1e-3, sigma_min=0.05)
+    assert -3.6 - 1e-9 <= res["E"] / 36 < -3.595
+
+
+def test_structure_factor_identity():
+    """S_ref^a(k) = |sum_i T_i^a e^{ik.r_i}|^2 / |rs| on allowed momenta for the literal getRs/getProject/getCorrelations."""
+    for name, L in (("triangular", 3), ("triangular", 4), ("honeycomb", 3)):
+        pos, nbr, lab, bl = ol.triangular(L) if name == "triangular" else ol.honeycomb(L)
+        o = orc.Oracle(nbr, lab, NOTEBOOK_J, np.zeros(16), 1)
+        o.seed(4); o.randomize()
+        basis, uv = ol.basis_vectors(name), ol.unit_vectors()
+        proj, rs = orc.get_project(pos, basis, bl, uv, L)
+        Cm = o.correlations(proj, rs.shape[0])
+        B = 2 * np.pi * np.linalg.inv(np.stack(uv) * L).T
+        ks = np.array([m1 * B[0] + m2 * B[1] for m1 in range(-L, L + 1) for m2 in range(-L, L + 1)])
+        sf = orc.structure_factor_vec(Cm, rs, ks)
+        T, _ = o.get_T()
+        direct = np.abs(np.einsum("ia,ki->ak", T, np.exp(1j * ks @ pos.T))) ** 2 / rs.shape[0]
+        assert np.allclose(sf, direct, atol=1e-11)
+
+
+def test_product_geometry_matches_oracle(scmc):
+    from scmc_b200 import lattice as pl
+    for name, L in (("triangular", 4), ("honeycomb", 3)):
+        lat = pl.getLatticePeriodic(pl.getUnitcell(name), L)
+        pos, nbr, lab, bl = ol.triangular(L) if name == "triangular" else ol.honeycomb(L)
+        assert np.allclose(lat.positions, pos) and np.array_equal(lat.nbr_site, nbr) and np.array_equal(lat.nbr_label, lab)
+        assert np.array_equal(lat.basis_labels, bl)
+        col = pl.colourSites(lat)
+        for k in range(nbr.shape[1]):
+            assert np.all(col != col[nbr[:, k]])
+
+
+def test_stream_v1_moments():
+    """The framework's counter-based stream, as restated by the oracle: N(0,1) normals and U[0,1) uniforms."""
+    o, _, _ = tri_oracle(3)
+    xs, us = [], []
+    for v in range(4000):
+        xi, u = o.stream_v1(20230301, v % 9, 3, v)
+        xs.append(xi); us.append(u)
+    xs, us = np.array(xs), np.array(us)
+    assert abs(xs.mean()) < 0.02 and abs(xs.var() - 1) < 0.03 and abs(np.mean(xs ** 4) - 3) < 0.2
+    assert abs(us.mean() - 0.5) < 0.02 and 0 <= us.min() and us.max() < 1
+    assert abs(np.corrcoef(xs[:, 0], xs[:, 4])[0, 1]) < 0.05
