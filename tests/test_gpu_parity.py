@@ -1,0 +1,248 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): energies / local fields 1e-12 relative in FP64 and 1e-5 in FP32; accept/reject decisions
+bit-exact under injected randoms; thermal observables within statistical error bars; annealed ground-state energy within 1e-8.
+"""
+import numpy as np
+import pytest
+
+from conftest import NOTEBOOK_J, make_oracle, random_states, random_symmetric_J
+
+pytestmark = pytest.mark.gpu
+
+TOL = {64: 1e-12, 32: 1e-5}
+
+
+def build(scmc, kind, precision, R=3, seed=1234, **kw):
+    if kind == "tri_notebook":       # n = 1, triangular L = 6, 3 colours
+        return scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 6, 1, n_replicas=R, precision=precision, seed=seed, **kw)
+    if kind == "tri_dense_odd":      # n = 1, dense random symmetric J, L = 5 (greedy colouring)
+        return scmc.initializeCfg("nearest-neighbor", "triangular", [random_symmetric_J(7)], 5, 1, n_replicas=R, precision=precision, seed=seed, **kw)
+    if kind == "honey_n2_onsite":    # n = 2 (d = 6) with on-site couplings: Tsq path
+        Jon = np.diag(np.linspace(-0.3, 0.4, 16))
+        return scmc.initializeCfg("nearest-neighbor", "honeycomb", [Jon, random_symmetric_J(9)], 4, 2, n_replicas=R, precision=precision, seed=seed, **kw)
+    if kind == "tghbn":              # 3 labels, 12 neighbours, on-site K, n = 2, 4 colours
+        return scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.15, 0.8], 4, 2, n_replicas=R, precision=precision, seed=seed, **kw)
+    if kind == "honey_heis":         # BASELINE config C1: su(4) Heisenberg on honeycomb 6x6
+        return scmc.initializeCfg("nearest-neighbor", "honeycomb", [np.eye(16)], 6, 1, n_replicas=R, precision=precision, seed=seed, **kw)
+    if kind == "tri_n3":
+        return scmc.initializeCfg("nearest-neighbor", "triangular", [random_symmetric_J(3)], 4, 3, n_replicas=R, precision=precision, seed=seed, **kw)
+    raise KeyError(kind)
+
+
+KINDS = ["tri_notebook", "tri_dense_odd", "honey_n2_onsite", "tghbn", "honey_heis", "tri_n3"]
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+@pytest.mark.parametrize("kind", KINDS)
+def test_expectations_energy_field(scmc, oracle_mod, kind, precision):
+    cfg = build(scmc, kind, precision)
+    rng = np.random.default_rng(5)
+    psi = random_states(rng, cfg.n_replicas, cfg.nSites, cfg.d)
+    cfg.set_state(psi)
+    tol = TOL[precision]
+    back = cfg.get_state()
+    assert np.allclose(back, psi, atol=1e-15 if precision == 64 else 1e-7)
+    E = cfg.energies()
+    for r in range(cfg.n_replicas):
+        o = make_oracle(cfg, oracle_mod)
+        o.set_state(psi[r])
+        T, Tsq = cfg.get_T(r, squared=True)
+        To, Tsqo = o.get_T()
+        assert np.allclose(T, To, atol=tol * 4) and np.allclose(Tsq, Tsqo, atol=tol * 4)
+        Eo = o.energy()
+        scale = max(1.0, np.abs(To).sum() * np.abs(np.stack(cfg.interactions)).max())
+        assert abs(E[r] - Eo) <= tol * scale, (E[r], Eo)
+        h = cfg.local_field(r)
+        ho = np.stack([o.local_field(i) for i in range(cfg.nSites)])
+        assert np.allclose(h, ho, atol=tol * max(1.0, np.abs(ho).max()) * 4)
+    obs = cfg.measure()
+    assert np.allclose(obs[:, 0] * cfg.nSites, E, rtol=1e-12, atol=1e-12)
+    o = make_oracle(cfg, oracle_mod, replica=0)
+    assert np.allclose(obs[0], o.measure(E[0]), atol=10 * tol)
+
+
+@pytest.mark.parametrize("kind", ["tri_notebook", "honey_n2_onsite", "tghbn"])
+def test_single_update_deterministic_fp64(scmc, oracle_mod, kind):
+    """localUpdate! with injected randoms: identical decisions, dE to 1e-12, same trajectory."""
+    cfg = build(scmc, kind, 64, R=2)
+    o = make_oracle(cfg, oracle_mod, replica=1)
+    rng = np.random.default_rng(17)
+    E = cfg.energies()[1]; acc = 0
+    for t in range(150):
+        i = int(rng.integers(cfg.nSites))
+        xi, u = rng.standard_normal(2 * cfg.d), rng.random()
+        beta, sigma = 3.0, 0.4
+        ok_o, dE_o = o.local_update(i, xi, u, beta, sigma)
+        E_new, acc_new = scmc.localUpdate_(cfg, E, acc, beta, i, sigma, replica=1, xi=xi, u=u)
+        assert (acc_new - acc) == int(ok_o)
+        if ok_o:
+            assert abs((E_new - E) - dE_o) <= 1e-12 * max(1.0, abs(dE_o))
+        E, acc = E_new, acc_new
+    assert np.allclose(cfg.get_state(1, 1)[0], o.get_state(), atol=1e-12)
+    assert abs(cfg.energies()[1] - o.energy()) < 1e-10
+    assert abs(E - o.energy()) < 1e-9         # incrementally tracked energy (MonteCarlo.jl:282) stays consistent
+
+
+@pytest.mark.parametrize("kind", ["tri_notebook", "tri_dense_odd", "honey_n2_onsite", "tghbn"])
+def test_sweep_deterministic_bit_exact_masks(scmc, oracle_mod, kind):
+    """Colour-ordered sweep with injected randoms: accept masks must equal the oracle's bit for bit (FP64)."""
+    R, hits = 3, 2
+    cfg = build(scmc, kind, 64, R=R)
+    N, d = cfg.nSites, cfg.d
+    rng = np.random.default_rng(23)
+    xi = rng.standard_normal((hits, R, N, 2 * d)); u = rng.random((hits, R, N))
+    beta = np.array([0.5, 2.0, 8.0]); sigma = np.array([1.0, 0.3, 0.1])
+    oracles = [make_oracle(cfg, oracle_mod, replica=r) for r in range(R)]
+    acc, dE = cfg.sweep_deterministic(beta, sigma, xi, u, hits=hits)
+    order = np.argsort(cfg.colour, kind="stable")
+    n_ties = 0
+    for r, o in enumerate(oracles):
+        sites = np.repeat(order, hits)
+        hit_idx = np.tile(np.arange(hits), N)
+        acc_o, dE_o = o.updates_injected(sites, xi[hit_idx, r, sites], u[hit_idx, r, sites], beta[r], sigma[r])
+        p = np.exp(-beta[r] * dE_o)
+        ties = np.abs(u[hit_idx, r, sites] - p) < 1e-9
+        n_ties += int(ties.sum())
+        got_acc, got_dE = acc[hit_idx, r, sites], dE[hit_idx, r, sites]
+        assert np.array_equal(got_acc[~ties], acc_o[~ties])
+        assert np.allclose(got_dE, dE_o, rtol=1e-12, atol=1e-12)
+        assert np.allclose(cfg.get_state(r, 1)[0], o.get_state(), atol=1e-12)
+    assert n_ties == 0
+
+
+@pytest.mark.parametrize("kind", ["tri_notebook", "honey_n2_onsite"])
+def test_philox_chain_follows_oracle_fp64(scmc, oracle_mod, kind):
+    """Counter-based stream v1: the FP64 device chain equals the oracle's restatement of the same colour-ordered chain."""
+    R, off, seed = 3, 40, 987654321
+    cfg = build(scmc, kind, 64, R=R, seed=seed, replica_offset=off)
+    for r in range(R):
+        o = make_oracle(cfg, oracle_mod)
+        o.randomize_v1(seed, off + r)
+        assert np.allclose(cfg.get_state(r, 1)[0], o.get_state(), atol=1e-13)
+    beta, sigma = np.array([1.0, 4.0, 20.0]), np.array([0.8, 0.3, 0.1])
+    acc1, att1 = cfg.sweep(3, beta, sigma, hits=2)
+    acc2, _ = cfg.sweep(2, beta, sigma, hits=2)          # continues the stream at sweep_counter = 3
+    assert np.all(att1 == 3 * 2 * cfg.nSites)
+    for r in range(R):
+        o = make_oracle(cfg, oracle_mod)
+        o.randomize_v1(seed, off + r)
+        a1 = o.sweeps_colour_v1(3, 2, cfg.colour, beta[r], sigma[r], seed, off + r, 0)
+        a2 = o.sweeps_colour_v1(2, 2, cfg.colour, beta[r], sigma[r], seed, off + r, 3)
+        assert (acc1[r], acc2[r]) == (a1, a2)
+        assert np.allclose(cfg.get_state(r, 1)[0], o.get_state(), atol=1e-10)
+
+
+def test_replica_sharding_is_invisible(scmc):
+    """Same global replica ids on differently sharded handles give bit-identical chains (multi-GPU contract)."""
+    seed = 4242
+    full = build(scmc, "tri_notebook", 32, R=6, seed=seed)
+    lo = build(scmc, "tri_notebook", 32, R=2, seed=seed, replica_offset=0)
+    hi = build(scmc, "tri_notebook", 32, R=4, seed=seed, replica_offset=2)
+    betas = np.linspace(0.5, 30, 6); sig = np.full(6, 0.3)
+    a = full.sweep(4, betas, sig)[0]
+    b = np.concatenate([lo.sweep(4, betas[:2], sig[:2])[0], hi.sweep(4, betas[2:], sig[2:])[0]])
+    assert np.array_equal(a, b)
+    assert np.array_equal(full.get_state(), np.concatenate([lo.get_state(), hi.get_state()]))
+    assert np.array_equal(full.energies(), np.concatenate([lo.energies(), hi.energies()]))
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_invariants_after_sweeps(scmc, precision):
+    """Size-independent properties on a large lattice (128 x 128 triangular, BASELINE C5 shape, fewer replicas)."""
+    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 128, 1, n_replicas=4, precision=precision, seed=99)
+    assert cfg.info()["n_colours"] == 4
+    E0 = cfg.energies()
+    acc, att = cfg.sweep(3, np.array([0.5, 2.0, 10.0, 1e9]), np.array([0.5, 0.3, 0.2, 0.2]))
+    assert np.all(acc > 0) and np.all(acc <= att)
+    tol = 1e-12 if precision == 64 else 2e-6
+    psi = cfg.get_state()
+    assert np.allclose(np.linalg.norm(psi, axis=-1), 1.0, atol=tol)
+    for r in (0, 3):
+        T = cfg.get_T(r)
+        assert np.allclose(T[:, 0], 1.0, atol=4 * tol) and np.allclose((T[:, 1:] ** 2).sum(axis=1), 3.0, atol=16 * tol)
+        assert np.allclose(T, np.einsum("ij,ajk,ik->ia", psi[r].conj(), cfg.generators, psi[r]).real, atol=8 * tol)
+    E1 = cfg.energies()
+    assert E1[3] < E0[3]                      # beta = 1e9: only downhill moves are accepted
+    acc_cold, _ = cfg.sweep(1, np.full(4, 1e9), np.full(4, 0.2))
+    assert acc_cold[3] > 0 and cfg.energies()[3] <= E1[3] + 1e-6 * abs(E1[3])
+
+
+def test_thermal_statistics_match_reference_chain(scmc, oracle_mod):
+    """BASELINE config C1 (su(4) Heisenberg, honeycomb 6x6, T = 0.1): FP32 colour-ordered device chains vs the oracle's
+    sequential random-site chain.  Different chains, same stationary distribution: e and c agree within error bars."""
+    R = 48
+    cfg = build(scmc, "honey_heis", 32, R=R, seed=31337)
+    res = scmc.run_(cfg, None, 0.1, 1.0, 2000, 6000, measurement_rate=10)
+    ser = res["series"]                                      # [rows, R, 21]
+    e_rep = ser[:, :, 0].mean(axis=0)
+    c_rep = 100.0 * (ser[:, :, 1].mean(axis=0) - e_rep ** 2) * cfg.nSites
+    e_gpu, e_gpu_err = e_rep.mean(), e_rep.std(ddof=1) / np.sqrt(R)
+    c_gpu, c_gpu_err = c_rep.mean(), c_rep.std(ddof=1) / np.sqrt(R)
+    es, cs = [], []
+    for k in range(6):
+        o = make_oracle(cfg, oracle_mod)
+        o.seed(1000 + k); o.randomize()
+        s = o.run_metropolis(0.1, 1.0, 2000, 6000, 10)["series"]
+        es.append(s[:, 0].mean()); cs.append(100.0 * (s[:, 1].mean() - s[:, 0].mean() ** 2) * cfg.nSites)
+    e_ref, e_ref_err = np.mean(es), np.std(es, ddof=1) / np.sqrt(len(es))
+    c_ref, c_ref_err = np.mean(cs), np.std(cs, ddof=1) / np.sqrt(len(cs))
+    assert abs(e_gpu - e_ref) < 4.5 * np.hypot(e_gpu_err, e_ref_err) + 1e-4, (e_gpu, e_gpu_err, e_ref, e_ref_err)
+    assert abs(c_gpu - c_ref) < 4.5 * np.hypot(c_gpu_err, c_ref_err) + 0.02, (c_gpu, c_gpu_err, c_ref, c_ref_err)
+    assert np.all(np.abs(res["acc_rate"] - 0.5) < 0.1)      # sigma adapted towards 50 % (MonteCarlo.jl:47-54)
+
+
+def test_notebook_observables_on_device(scmc):
+    """doc/examples.ipynb cell 13 (triangular L = 6, T = 0.02): e = -3.540997(91), |m_sigma| = 0.993221(8), |m_tau| = 0.02001(13)."""
+    R = 32
+    cfg = build(scmc, "tri_notebook", 32, R=R, seed=2023)
+    res = scmc.run_(cfg, None, 0.02, 1.0, 4000, 8000, measurement_rate=10)
+    m = res["mean"]
+    e = m[:, 0]
+    assert abs(e.mean() - (-3.540997)) < 5 * e.std(ddof=1) / np.sqrt(R) + 3e-4, (e.mean(), e.std())
+    assert abs(m[:, 2].mean() - 0.993221) < 1e-4
+    assert abs(m[:, 3].mean() - 0.02001) < 1.5e-3
+    assert abs(m[:, 4].mean() - 0.02885) < 1.5e-3
+    c = 2500.0 * (m[:, 1] - m[:, 0] ** 2) * 36
+    assert abs(c.mean() - 2.933) < 5 * c.std(ddof=1) / np.sqrt(R) + 0.1
+
+
+def test_annealing_reaches_exact_ground_state(scmc):
+    """doc/examples.ipynb cell 25 parameters (lattice L = 6 here): annealing + optimisation sweeps reach E/N = -3.6 within 1e-8 (FP64)."""
+    cfg = build(scmc, "tri_notebook", 64, R=8, seed=77)
+    res = scmc.runAnnealing_(cfg, 3.0, T_fac=0.98, N_max=20000, N_o=400, N_per_T=100, min_acc_per_site=10, min_accrate=1e-3, σ_min=0.05)
+    e_sa, e = res["E_annealed"] / 36, res["E"] / 36
+    assert np.all(e <= e_sa + 1e-12)
+    assert np.all(e >= -3.6 - 1e-9)
+    assert abs(e.min() - (-3.6)) < 1e-8, e
+    assert np.all(res["sweeps"] > 100) and np.all(res["sigma"] >= 0.05 - 1e-12)
+
+
+@pytest.mark.parametrize("kind", ["tri_notebook", "honey_heis"])
+def test_correlations_and_structure_factor(scmc, oracle_mod, kind):
+    cfg = build(scmc, kind, 64, R=2)
+    cfg.sweep(2, 1.0, 0.5)
+    proj = scmc.getProject(cfg)
+    rs = scmc.getRs(cfg)
+    proj_o, rs_o = oracle_mod.get_project(cfg.positions, cfg.basis, cfg.basisLabels, cfg.unitVectors, cfg.L)
+    assert np.array_equal(proj, proj_o) and np.allclose(rs, rs_o)
+    o = make_oracle(cfg, oracle_mod, replica=1)
+    Cg = scmc.getCorrelations(cfg, proj, replica=1)
+    Co = o.correlations(proj, rs.shape[0])
+    assert np.allclose(Cg, Co, rtol=1e-12, atol=1e-12)
+    B = 2 * np.pi * np.linalg.inv(np.stack(cfg.unitVectors) * cfg.L).T
+    ks = np.array([a * B[0] + b * B[1] for a in range(-cfg.L, cfg.L + 1) for b in range(-cfg.L, cfg.L + 1)])
+    Sg = scmc.structureFactor(cfg, ks)[1]
+    So = oracle_mod.structure_factor_vec(Co, rs, ks)
+    assert np.allclose(Sg, So, atol=1e-10)
+    assert np.allclose(scmc.computeStructureFactor(Cg, rs, ks), oracle_mod.structure_factor(Co, rs, ks), atol=1e-10)
+
+
+def test_create_rejects_bad_tables(scmc):
+    from scmc_b200 import lattice as pl
+    uc = pl.getUnitcell("triangular")
+    with pytest.raises(scmc._lib.ScmcError, match="colour"):
+        scmc.Configuration("triangular", 4, uc, [NOTEBOOK_J], np.zeros(16), 1, colour=np.zeros(16, dtype=np.int32))
+    Jasym = NOTEBOOK_J.copy(); Jasym[1, 2] = 0.5
+    with pytest.raises(scmc._lib.ScmcError, match="transposed"):
+        scmc.Configuration("triangular", 4, uc, [Jasym], np.zeros(16), 1)

@@ -1,0 +1,83 @@
+"""CPU tests of the host-side mirror: model tables (Models.jl), colouring, binning, import shim."""
+import numpy as np
+import pytest
+
+
+def test_tghbn_tables_follow_reference(scmc):
+    """Models.jl:48-113: J/8 scaling, on-site vector, label-2 matrix = transpose of label-1, zeroed [1,1], diagonal nnn."""
+    from scmc_b200 import lattice as pl
+    captured = {}
+
+    class Fake:
+        def __init__(self, latticename, L, uc, interactions, onsite, n, **kw):
+            captured.update(name=latticename, L=L, uc=uc, J=interactions, K=onsite, n=n)
+
+    import scmc_b200.models as M
+    orig = M.Configuration
+    M.Configuration = Fake
+    try:
+        M.initializeCfgTgHbn([8.0, 1.6, 0.8, 0.4, 4.0], 6, n=2)
+    finally:
+        M.Configuration = orig
+    J1, J2, J3 = captured["J"]
+    assert np.allclose(J2, J1.T) and J1[0, 0] == 0 and J2[0, 0] == 0
+    assert np.isclose(J1[1, 1], 1.0 + 0.1) and np.isclose(J1[1, 2], 0.05) and np.isclose(J1[2, 1], -0.05) and np.isclose(J1[3, 3], 1.0)
+    assert np.allclose(J3, np.diag([0] + [0.2] * 15))
+    assert np.allclose(captured["K"], [0, 0, 0, 0.25] + [-0.25, 0, 0, 0.25] * 3)
+    uc = captured["uc"]
+    assert [b.label for b in uc.bonds] == [1, 1, 1, 2, 2, 2, 3, 3, 3, 3, 3, 3]
+    lat = pl.getLatticePeriodic(uc, 6)
+    col = pl.colourSites(lat)
+    assert col.max() + 1 == 4
+    for k in range(12):
+        assert np.all(col != col[lat.nbr_site[:, k]])
+    # every bond has its reverse with the transposed coupling
+    for i in range(lat.n_sites):
+        for k in range(12):
+            j, l = lat.nbr_site[i, k], lat.nbr_label[i, k]
+            back = [lat.nbr_label[j, k2] for k2 in range(12) if lat.nbr_site[j, k2] == i]
+            assert any(np.allclose(captured["J"][l - 1], captured["J"][lb - 1].T) for lb in back)
+
+
+def test_unknown_model_returns_none(scmc, caplog):
+    assert scmc.initializeCfg("no-such-model", "triangular", [np.eye(16)], 3, 1) is None      # Models.jl:15
+
+
+def test_colourings(scmc):
+    from scmc_b200 import lattice as pl
+    for name, L, ncol in (("triangular", 6, 3), ("triangular", 128, 4), ("triangular", 48, 3), ("triangular", 36, 3), ("honeycomb", 96, 2),
+                          ("triangular", 5, None), ("square", 4, 2)):
+        lat = pl.getLatticePeriodic(pl.getUnitcell(name), L)
+        col = pl.colourSites(lat)
+        if ncol:
+            assert col.max() + 1 == ncol
+        for k in range(lat.nbr_site.shape[1]):
+            assert np.all(col != col[lat.nbr_site[:, k]])
+
+
+def test_log_binner_against_oracle_formula(scmc, oracle_mod):
+    rng = np.random.default_rng(0)
+    x = np.zeros(4096)
+    for t in range(1, 4096):
+        x[t] = 0.9 * x[t - 1] + rng.standard_normal()          # AR(1): correlated series
+    b = scmc.LogBinner()
+    b.extend(x)
+    assert np.isclose(b.mean(), x.mean())
+    assert np.isclose(b.std_error(), oracle_mod.log_binning_error(x))
+    naive = x.std(ddof=1) / np.sqrt(len(x))
+    assert b.std_error() > 2.5 * naive
+    ep = scmc.ErrorPropagator(2)
+    for v in x:
+        ep.push(v, v * v)
+    var = ep.mean(lambda m: m[1] - m[0] ** 2)
+    assert np.isclose(var, x.var())
+    assert ep.std_error(lambda m: np.array([-2 * m[0], 1.0])) > 0
+
+
+def test_ks_in_box(scmc):
+    ks = scmc.getKsInBox("triangular", 6, [8 * np.pi, 8 * np.pi], [0.0, 0.0])
+    assert np.all(np.abs(ks) <= 4 * np.pi + 1e-9)
+    from scmc_b200 import lattice as pl
+    pos = pl.getLatticePeriodic(pl.getUnitcell("triangular"), 6).positions
+    sup = 6 * np.stack(pl.getUnitcell("triangular").lattice_vectors)
+    assert np.allclose(np.exp(1j * ks @ sup.T), 1.0)           # allowed momenta of the periodic cluster
