@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libscmc_b200.so")
+LIB_PATH = os.environ.get("SCMC_LIB") or os.path.join(HERE, "libscmc_b200.so")   # SCMC_LIB: alternative build (kernel experiments)
 NOBS = 21
 
 c_dp = C.POINTER(C.c_double)

@@ -81,8 +81,6 @@ __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, double& g0,
 }
 __device__ __forceinline__ float unit_uniform(uint32_t x, float) { return __uint2float_rz(x) * 2.3283064365386963e-10f; }
 __device__ __forceinline__ double unit_uniform(uint32_t x, double) { return (double)x * (1.0 / 4294967296.0); }
-__device__ __forceinline__ float fast_exp(float x) { return __expf(x); }
-__device__ __forceinline__ double fast_exp(double x) { return exp(x); }
 __device__ __forceinline__ float inv_sqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double inv_sqrt(double x) { return 1.0 / sqrt(x); }
 
@@ -126,10 +124,29 @@ __device__ __forceinline__ void field_from_sums(const Couplings<R, NL>& cp, cons
 }
 
 // ------------------------------------------------------------------------------------------------ one Metropolis hit
-// State of the visited site lives in registers: psi (re, im), T, (Tsq).  Returns true when the proposal was accepted.
+// e_loc = T.h (+ K.Tsq) is the part of the energy that depends on the visited site; dE = e_loc(psi') - e_loc(psi)
+// (getEnergyDifference!, Configuration.jl:278-298, with the neighbour mat-vecs hoisted into h).
+template <class R, bool ONSITE>
+__device__ __forceinline__ R local_energy(const R* T, const R* Tsq, const R* h, const R* K) {
+    R e = R(0);
+#pragma unroll
+    for (int a = 0; a < NG; a++) e = fma(T[a], h[a], e);
+    if (ONSITE) {
+#pragma unroll
+        for (int a = 0; a < NG; a++) e = fma(Tsq[a], K[a], e);
+    }
+    return e;
+}
+// acceptance test rand() < exp(-beta dE) (MonteCarlo.jl:277-278): FP32 evaluates 2^(nbeta * dE) with nbeta = -beta * log2(e) on the SFU
+__device__ __forceinline__ float neg_beta_scaled(float beta) { return -beta * 1.4426950408889634f; }
+__device__ __forceinline__ double neg_beta_scaled(double beta) { return -beta; }
+__device__ __forceinline__ float accept_prob(float nbeta, float dE) { return exp2f(nbeta * dE); }
+__device__ __forceinline__ double accept_prob(double nbeta, double dE) { return exp(nbeta * dE); }
+
+// State of the visited site lives in registers: psi (re, im), T, (Tsq), e_loc.  Returns true when the proposal was accepted.
 template <class R, int GEN, bool ONSITE>
 __device__ __forceinline__ bool metropolis_hit(R* re, R* im, R* T, R* Tsq, const R* h, const R* K, const R* xr, const R* xi,
-                                               R u, R beta, R sigma, R& dE_out) {
+                                               R u, R nbeta, R sigma, R& eloc, R& dE_out) {
     constexpr int D = GenOps<GEN>::D;
     R nre[D], nim[D], nT[NG], nTsq[NG];
     R n2 = R(0);
@@ -144,17 +161,13 @@ __device__ __forceinline__ bool metropolis_hit(R* re, R* im, R* T, R* Tsq, const
 #pragma unroll
     for (int k = 0; k < D; k++) { nre[k] *= inv; nim[k] *= inv; }
     GenOps<GEN>::expect(nre, nim, nT);
-    R dE = R(0);
-#pragma unroll
-    for (int a = 0; a < NG; a++) dE = fma(nT[a] - T[a], h[a], dE);
-    if (ONSITE) {
-        GenOps<GEN>::expect_sq(nre, nim, nTsq);
-#pragma unroll
-        for (int a = 0; a < NG; a++) dE = fma(nTsq[a] - Tsq[a], K[a], dE);
-    }
+    if (ONSITE) GenOps<GEN>::expect_sq(nre, nim, nTsq);
+    const R enew = local_energy<R, ONSITE>(nT, nTsq, h, K);
+    const R dE = enew - eloc;
     dE_out = dE;
-    const bool acc = u < fast_exp(-beta * dE);   // rand() < exp(-beta dE), no min(1, .)  (MonteCarlo.jl:277-278)
+    const bool acc = u < accept_prob(nbeta, dE);   // no min(1, .): overflow to +inf accepts
     if (acc) {
+        eloc = enew;
 #pragma unroll
         for (int k = 0; k < D; k++) { re[k] = nre[k]; im[k] = nim[k]; }
 #pragma unroll

@@ -41,6 +41,10 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
+#ifndef SCMC_SWEEP_THREADS
+#define SCMC_SWEEP_THREADS 128
+#define SCMC_SWEEP_BLOCKS 5
+#endif
 struct SweepArgs {
     int32_t colour, hits;
     int64_t r0, rcount;        // replica batch [r0, r0 + rcount)
@@ -55,39 +59,53 @@ struct SweepArgs {
     double* out_dE;
 };
 
+// S_l = sum of T_j over the neighbours with label l.  The neighbour table is padded to a multiple of 3 slots; padding slots
+// (and missing bonds) point at site N, whose T planes are identically zero, so the loop is branch-free and every chunk
+// issues 3 index loads followed by 12 independent 128-bit loads (memory-level parallelism instead of 2 serial latencies per bond).
 template <class R, int NL>
 __device__ __forceinline__ void neighbour_sums(const DevModel<R, NL>& M, int64_t rbase, size_t ps, int p, R (*S)[NG]) {
 #pragma unroll
     for (int l = 0; l < NL; l++)
 #pragma unroll
         for (int a = 0; a < NG; a++) S[l][a] = R(0);
-#pragma unroll 3
-    for (int k = 0; k < M.z; k++) {
-        const int j = M.nbr[(size_t)k * M.N + p];
-        if (j < 0) continue;
-        const vec4<R>* src = M.T + rbase + j;
-        if (NL == 1) {
-            add_T<R>(src, ps, S[0]);
-        } else {
-            const int l = M.lab[(size_t)k * M.N + p];
-            if (l == 0) add_T<R>(src, ps, S[0]);
-            else if (l == 1) add_T<R>(src, ps, S[NL > 1 ? 1 : 0]);
-            else add_T<R>(src, ps, S[NL > 2 ? 2 : 0]);
+    const int32_t* nb = M.nbr + p;
+    const int8_t* lb = M.lab + p;
+#pragma unroll 2
+    for (int k = 0; k < M.z; k += 3) {
+        int j[3], l[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            j[t] = nb[(size_t)(k + t) * M.N];
+            l[t] = NL == 1 ? 0 : lb[(size_t)(k + t) * M.N];
+        }
+        vec4<R> v[3][4];
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[t][q] = M.T[rbase + j[t] + q * ps];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+#pragma unroll
+            for (int ll = 0; ll < NL; ll++)
+                if (NL == 1 || l[t] == ll) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        S[ll][4 * q] += v[t][q].x; S[ll][4 * q + 1] += v[t][q].y; S[ll][4 * q + 2] += v[t][q].z; S[ll][4 * q + 3] += v[t][q].w;
+                    }
+                }
         }
     }
 }
 
 // One colour pass: every (replica, site of this colour) gets `hits` consecutive Metropolis updates.
-template <class R, int GEN, bool ONSITE, int NL>
-__global__ void __launch_bounds__(256) k_sweep_colour(const __grid_constant__ DevModel<R, NL> M, const SweepArgs A) {
+// grid = (ceil(n_colour_sites / 256), replicas of the batch); INJECT = deterministic test mode (host-supplied randoms).
+template <class R, int GEN, bool ONSITE, int NL, bool INJECT>
+__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep_colour(const __grid_constant__ DevModel<R, NL> M, const SweepArgs A) {
     constexpr int D = GenOps<GEN>::D;
     const int nc = M.col_off[A.colour + 1] - M.col_off[A.colour];
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = idx < A.rcount * nc;
-    int64_t r = A.r0;
-    int s = 0;
-    if (valid) { const int64_t q = idx / nc; s = (int)(idx - q * nc); r += q; }
-    const bool live = valid && (A.active == nullptr || A.active[r]);
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t r = A.r0 + blockIdx.y;
+    const bool live = s < nc && (A.active == nullptr || A.active[r]);
     unsigned nacc = 0;
     if (live) {
         const int p = M.col_off[A.colour] + s;
@@ -95,18 +113,21 @@ __global__ void __launch_bounds__(256) k_sweep_colour(const __grid_constant__ De
         const int64_t rbase = r * M.Ns;
         R re[D], im[D], T[NG], Tsq[NG], h[NG];
         load_psi<R, D>(M.psi + rbase + p, ps, re, im);
-        GenOps<GEN>::expect(re, im, T);
-        if (ONSITE) GenOps<GEN>::expect_sq(re, im, Tsq);
+        const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+        const int site = M.orig[p];
         {
             R S[NL][NG];
             neighbour_sums<R, NL>(M, rbase, ps, p, S);
             field_from_sums<R, NL>(M.cp, S, h);
         }
-        const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
-        const int site = M.orig[p];
+        GenOps<GEN>::expect(re, im, T);
+        if (ONSITE) GenOps<GEN>::expect_sq(re, im, Tsq);
+        // e_loc = T.h (+ K.Tsq): dE of a proposal is e_loc' - e_loc, which needs one dot product per hit
+        R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
+        const R nbeta = neg_beta_scaled(beta);
         for (int hit = 0; hit < A.hits; hit++) {
             R xr[D], xi[D], u, dE;
-            if (A.inj_xi) {
+            if (INJECT) {
                 const size_t t = ((size_t)hit * M.nrep + r) * M.N + site;
 #pragma unroll
                 for (int k = 0; k < D; k++) { xr[k] = (R)A.inj_xi[t * 2 * D + k]; xi[k] = (R)A.inj_xi[t * 2 * D + D + k]; }
@@ -114,8 +135,8 @@ __global__ void __launch_bounds__(256) k_sweep_colour(const __grid_constant__ De
             } else {
                 stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
             }
-            const bool ok = metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, beta, sigma, dE);
-            if (A.out_acc) {
+            const bool ok = metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE);
+            if (INJECT) {
                 const size_t t = ((size_t)hit * M.nrep + r) * M.N + site;
                 A.out_acc[t] = ok ? 1 : 0;
                 if (A.out_dE) A.out_dE[t] = (double)dE;
@@ -128,15 +149,9 @@ __global__ void __launch_bounds__(256) k_sweep_colour(const __grid_constant__ De
             if (ONSITE) store_T<R>(M.Tsq + rbase + p, ps, Tsq);
         }
     }
-    // acceptance counters: one atomic per warp when the whole warp works on one replica
-    const unsigned full = 0xffffffffu;
-    const long long r0w = __shfl_sync(full, (long long)r, 0);
-    if (__all_sync(full, r == r0w)) {
-        const unsigned tot = __reduce_add_sync(full, nacc);
-        if ((threadIdx.x & 31) == 0 && tot) atomicAdd(A.acc + r0w, (unsigned long long)tot);
-    } else if (nacc) {
-        atomicAdd(A.acc + r, (unsigned long long)nacc);
-    }
+    // acceptance counters: one atomic per warp (a warp never spans two replicas)
+    const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
 }
 
 // Energy + magnetisation of every replica; one CTA per replica; FP64 accumulation.
@@ -319,7 +334,8 @@ __global__ void k_single_update(const __grid_constant__ DevModel<R, NL> M, int64
     field_from_sums<R, NL>(M.cp, S, h);
 #pragma unroll
     for (int k = 0; k < D; k++) { xr[k] = (R)xi_in[k]; xi[k] = (R)xi_in[D + k]; }
-    const bool ok = metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, (R)u, (R)beta, (R)sigma, dE);
+    R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
+    const bool ok = metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, (R)u, neg_beta_scaled((R)beta), (R)sigma, eloc, dE);
     if (ok) {
         store_psi<R, D>(M.psi + rbase + p, ps, re, im);
         store_T<R>(M.T + rbase + p, ps, T);
@@ -388,8 +404,14 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
         const int nc = h->col_off[A.colour + 1] - h->col_off[A.colour];
         if (nc == 0 || A.rcount == 0) return SCMC_OK;
         auto M = make_model<R, NL>(h);
-        k_sweep_colour<R, GEN, ONS, NL><<<grid_for(A.rcount * nc), 256, 0, h->stream>>>(M, A);
-        h->launches++;
+        for (int64_t y0 = 0; y0 < A.rcount; y0 += 65535) {      // gridDim.y limit
+            SweepArgs B = A;
+            B.r0 = A.r0 + y0; B.rcount = std::min<int64_t>(65535, A.rcount - y0);
+            const dim3 grid(grid_for(nc, SCMC_SWEEP_THREADS), (unsigned)B.rcount);
+            if (A.inj_xi) k_sweep_colour<R, GEN, ONS, NL, true><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+            else k_sweep_colour<R, GEN, ONS, NL, false><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+            h->launches++;
+        }
         SCMC_CK(cudaGetLastError());
         return SCMC_OK;
     });
@@ -506,7 +528,8 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     scmc_handle* h = new scmc_handle();
     h->device = device; h->prec = precision; h->d = d; h->z = z_max; h->n_labels = n_labels; h->gen_id = gen_id;
     h->N = N; h->R = n_replicas; h->roff = replica_offset;
-    h->Ns = (N + 7) / 8 * 8;
+    h->Ns = (N + 1 + 7) / 8 * 8;          // site N of every replica is the all-zero padding site
+    h->z = (z_max + 2) / 3 * 3;           // neighbour slots padded to a multiple of 3 (chunked loads)
     for (int l = 0; l < n_labels; l++) memcpy(h->J[l], J + (size_t)l * 256, sizeof(double) * 256);
     memcpy(h->K, K, sizeof(double) * 16);
     bool anyK = false;
@@ -558,12 +581,12 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     // --- device
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__); }
-    std::vector<int32_t> nb((size_t)z_max * N);
-    std::vector<int8_t> lb((size_t)z_max * N);
+    std::vector<int32_t> nb((size_t)h->z * N, (int32_t)N);
+    std::vector<int8_t> lb((size_t)h->z * N, 0);
     for (int64_t p = 0; p < N; p++)
         for (int k = 0; k < z_max; k++) {
             const int32_t j = nbr_site[(int64_t)h->orig[p] * z_max + k];
-            nb[(size_t)k * N + p] = j >= 0 ? h->perm[j] : -1;
+            nb[(size_t)k * N + p] = j >= 0 ? h->perm[j] : (int32_t)N;
             lb[(size_t)k * N + p] = j >= 0 ? (int8_t)nbr_label[(int64_t)h->orig[p] * z_max + k] : 0;
         }
     const size_t plane = (size_t)h->R * h->Ns * 4 * h->esz();

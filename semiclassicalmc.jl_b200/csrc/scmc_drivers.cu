@@ -73,9 +73,8 @@ __device__ __forceinline__ void neighbour_sums_d(const DevModel<R, NL>& M, int64
     for (int l = 0; l < NL; l++)
 #pragma unroll
         for (int a = 0; a < NG; a++) S[l][a] = R(0);
-    for (int k = 0; k < M.z; k++) {
+    for (int k = 0; k < M.z; k++) {      // padding slots point at the all-zero site N
         const int j = M.nbr[(size_t)k * M.N + p];
-        if (j < 0) continue;
         const int l = NL == 1 ? 0 : M.lab[(size_t)k * M.N + p];
         R t[NG];
         load_T<R>(M.T + rbase + j, ps, t);
