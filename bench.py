@@ -3,8 +3,9 @@
 
 Workload (BASELINE config C5): triangular 128 x 128, n = 1, SU(2)xSU(2) notebook couplings applied as a dense 16x16 matrix,
 8192 replicas = 64 temperatures log-spaced in [0.02, 2] x 128 copies, FP32 state + FP64 accumulators, replicas split evenly over the ranks
-(total work fixed -> "strong" scaling).  One step = `--sweeps` colour-ordered sweeps of every replica with 2 updates per site
-visit (= the reference's 2N updates per sweep, src/MonteCarlo.jl:40-44).
+(total work fixed -> "strong" scaling).  One step = one measurement interval of the reference's run! = `--sweeps` (10, measurement_rate,
+src/MonteCarlo.jl:11) colour-ordered sweeps of every replica with 2 updates per site visit (= the reference's 2N updates per sweep,
+src/MonteCarlo.jl:40-44); the e2e arm adds the measure! call that ends the interval (src/MonteCarlo.jl:82-86).
 
   value  : whole-job site-updates/s with everything resident in HBM, CUDA-event timed, max over ranks
   e2e    : the same through the public C-ABI calls with HOST buffers (scmc_sweep: beta/sigma H2D, counters D2H; scmc_measure: rows D2H)
@@ -33,12 +34,12 @@ METRIC = "site-updates/sec (n=1, 128x128 triangular Metropolis sweep)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--L", type=int, default=128)
     ap.add_argument("--replicas", type=int, default=8192, help="total replicas over all ranks")
-    ap.add_argument("--sweeps", type=int, default=1, help="sweeps per step")
+    ap.add_argument("--sweeps", type=int, default=10, help="sweeps per step (10 = the reference's measurement interval, MonteCarlo.jl:11)")
     ap.add_argument("--hits", type=int, default=2)
     ap.add_argument("--precision", type=int, default=32)
     ap.add_argument("--coupling", default="notebook", choices=["notebook", "dense"])

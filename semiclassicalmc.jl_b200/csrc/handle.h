@@ -61,6 +61,7 @@ struct scmc_handle {
     unsigned long long* acc = nullptr;           // [R] accepted-update counters
     uint8_t* active = nullptr;                   // [R] replica still running (annealing) -- nullptr semantics handled by callers
     double* obs = nullptr;                       // [R][SCMC_NOBS] scratch rows
+    void* pinned = nullptr;                      // pinned host staging for the beta / sigma tables
     int64_t bytes = 0, launches = 0;
     int32_t sweep_mode = 0;
     int64_t batch = 0;

@@ -381,17 +381,19 @@ static int32_t dispatch(const scmc_handle* h, F&& f) {
 
 static inline unsigned grid_for(int64_t n, int block = 256) { return (unsigned)((n + block - 1) / block); }
 
+// beta / sigma tables: converted on the host into the handle's pinned staging buffer, one async copy each, no sync
+// (the staging buffer is reused only after the stream has consumed it: callers synchronise before returning to the user).
 int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma) {
-    std::vector<char> buf(h->R * h->esz());
+    const size_t bytes = h->R * h->esz();
     for (int pass = 0; pass < 2; pass++) {
         const double* src = pass ? sigma : beta;
         if (!src) continue;
+        char* stage = (char*)h->pinned + pass * bytes;
         for (int64_t r = 0; r < h->R; r++) {
-            if (h->prec == 64) ((double*)buf.data())[r] = src[r];
-            else ((float*)buf.data())[r] = (float)src[r];
+            if (h->prec == 64) ((double*)stage)[r] = src[r];
+            else ((float*)stage)[r] = (float)src[r];
         }
-        SCMC_CK(cudaMemcpyAsync(pass ? h->sigma : h->beta, buf.data(), buf.size(), cudaMemcpyHostToDevice, h->stream));
-        SCMC_CK(cudaStreamSynchronize(h->stream));
+        SCMC_CK(cudaMemcpyAsync(pass ? h->sigma : h->beta, stage, bytes, cudaMemcpyHostToDevice, h->stream));
     }
     return SCMC_OK;
 }
@@ -603,6 +605,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     A((void**)&h->acc, h->R * sizeof(unsigned long long));
     A((void**)&h->active, h->R);
     A((void**)&h->obs, h->R * SCMC_NOBS * sizeof(double));
+    if (st == SCMC_OK && cudaMallocHost(&h->pinned, 2 * h->R * 8) != cudaSuccess) { set_error("cudaMallocHost failed"); st = SCMC_ERR_ALLOC; }
     if (st != SCMC_OK) { scmc_destroy(h); return st; }
     cudaError_t ce = cudaSuccess;
     auto C = [&](cudaError_t x) { if (ce == cudaSuccess) ce = x; };
@@ -624,6 +627,7 @@ int32_t scmc_destroy(scmc_t* h) {
     cudaSetDevice(h->device);
     void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (h->pinned) cudaFreeHost(h->pinned);
     delete h;
     return SCMC_OK;
 }

@@ -261,6 +261,7 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
     SCMC_CK(cudaMemcpyAsync(dT.p, p->T, R * 8, cudaMemcpyHostToDevice, h->stream));
     SCMC_CK(cudaMemcpyAsync(dTi.p, p->T_i, R * 8, cudaMemcpyHostToDevice, h->stream));
     SCMC_TRY(upload_scalars(h, nullptr, p->sigma));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
     SCMC_CK(cudaMemsetAsync(h->acc, 0, R * sizeof(unsigned long long), h->stream));
     const size_t row_bytes = (size_t)R * SCMC_NOBS * 8;
     const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(rows_total, 1), (int64_t)((512ull << 20) / row_bytes)));
@@ -343,6 +344,7 @@ int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results*
     const int64_t R = h->R;
     std::vector<double> b0(R, 1.0 / p->T_i), s0(R, p->sigma0);
     SCMC_TRY(upload_scalars(h, b0.data(), s0.data()));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
     DevBuf dsat, ddone, dnact;
     SCMC_CK(dsat.alloc(R * 8)); SCMC_CK(ddone.alloc(R * 8)); SCMC_CK(dnact.alloc(sizeof(int)));
     SCMC_CK(cudaMemsetAsync(dsat.p, 0, R * 8, h->stream));

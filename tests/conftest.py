@@ -49,3 +49,10 @@ def make_oracle(cfg, oracle_mod, replica=None):
     if replica is not None:
         o.set_state(cfg.get_state(replica, 1)[0])
     return o
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """Recorded outputs of the reference's notebook (tests/golden/make_golden.py)."""
+    import json
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "notebook_outputs.json")))

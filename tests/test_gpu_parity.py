@@ -192,19 +192,20 @@ def test_thermal_statistics_match_reference_chain(scmc, oracle_mod):
     assert np.all(np.abs(res["acc_rate"] - 0.5) < 0.1)      # sigma adapted towards 50 % (MonteCarlo.jl:47-54)
 
 
-def test_notebook_observables_on_device(scmc):
+def test_notebook_observables_on_device(scmc, golden):
     """doc/examples.ipynb cell 13 (triangular L = 6, T = 0.02): e = -3.540997(91), |m_sigma| = 0.993221(8), |m_tau| = 0.02001(13)."""
     R = 32
     cfg = build(scmc, "tri_notebook", 32, R=R, seed=2023)
     res = scmc.run_(cfg, None, 0.02, 1.0, 4000, 8000, measurement_rate=10)
     m = res["mean"]
     e = m[:, 0]
-    assert abs(e.mean() - (-3.540997)) < 5 * e.std(ddof=1) / np.sqrt(R) + 3e-4, (e.mean(), e.std())
-    assert abs(m[:, 2].mean() - 0.993221) < 1e-4
-    assert abs(m[:, 3].mean() - 0.02001) < 1.5e-3
-    assert abs(m[:, 4].mean() - 0.02885) < 1.5e-3
+    g = golden["metropolis"]["means"]
+    assert abs(e.mean() - g["energy/mean"]) < 5 * np.hypot(e.std(ddof=1) / np.sqrt(R), g["energy/error"]) + 3e-4, (e.mean(), e.std())
+    assert abs(m[:, 2].mean() - g["σ/mean"]) < 1e-4
+    assert abs(m[:, 3].mean() - g["τ/mean"]) < 1.5e-3
+    assert abs(m[:, 4].mean() - g["στ/mean"]) < 1.5e-3
     c = 2500.0 * (m[:, 1] - m[:, 0] ** 2) * 36
-    assert abs(c.mean() - 2.933) < 5 * c.std(ddof=1) / np.sqrt(R) + 0.1
+    assert abs(c.mean() - g["heat/mean"]) < 5 * np.hypot(c.std(ddof=1) / np.sqrt(R), g["heat/error"]) + 0.1
 
 
 def test_annealing_reaches_exact_ground_state(scmc):

@@ -88,29 +88,35 @@ def test_notebook_ground_state_energy_exact():
 
 
 @pytest.mark.timeout(300)
-def test_notebook_thermal_observables():
+def test_notebook_thermal_observables(golden):
     """examples.ipynb cell 13: e = -3.540997(91), c = 2.933(58), |m_sigma| = 0.993221(8), |m_tau| = 0.02001(13), |m_sigmatau| = 0.02885(11)
     at T = 0.02 on triangular L = 6 (1e5 + 1e5 sweeps there; 2e4 + 3e4 here, so wider windows)."""
     o, _, _ = tri_oracle(6)
     o.seed(20230301); o.randomize()
-    res = o.run_metropolis(0.02, 1.0, 20000, 30000, 10)
+    g, prm = golden["metropolis"]["means"], golden["metropolis"]["params"]
+    assert (prm["T"], prm["T_i"], prm["L"], prm["measurement_rate"]) == (0.02, 1.0, 6, 10)
+    res = o.run_metropolis(prm["T"], prm["T_i"], 20000, 30000, int(prm["measurement_rate"]))
     s = res["series"]
     e_err = orc.log_binning_error(s[:, 0])
-    assert abs(s[:, 0].mean() - (-3.540997)) < 5 * e_err + 3e-4
-    assert abs(orc.specific_heat(s[:, 0], s[:, 1], 50.0, 36) - 2.933) < 0.25
-    assert abs(s[:, 2].mean() - 0.993221) < 2e-4
-    assert abs(s[:, 3].mean() - 0.02001) < 2e-3
-    assert abs(s[:, 4].mean() - 0.02885) < 2e-3
-    assert 0.4 < res["acc_rate"] < 0.6          # cells 11/15/17/19: 0.497 - 0.5125
+    assert abs(s[:, 0].mean() - g["energy/mean"]) < 5 * np.hypot(e_err, g["energy/error"]) + 3e-4
+    assert abs(orc.specific_heat(s[:, 0], s[:, 1], 1 / prm["T"], 36) - g["heat/mean"]) < 0.25
+    assert abs(s[:, 2].mean() - g["σ/mean"]) < 2e-4
+    assert abs(s[:, 3].mean() - g["τ/mean"]) < 2e-3
+    assert abs(s[:, 4].mean() - g["στ/mean"]) < 2e-3
+    lo, hi = min(golden["metropolis"]["measurement_acceptance"]), max(golden["metropolis"]["measurement_acceptance"])
+    assert lo - 0.1 < res["acc_rate"] < hi + 0.1          # cells 11/15/17/19: 0.497 - 0.5125
 
 
 @pytest.mark.timeout(300)
-def test_notebook_annealing_energy():
+def test_notebook_annealing_energy(golden):
     """examples.ipynb cell 25 (L = 12): E/N -> -3.597 after SA, -3.599993 after 10 optimisation sweeps; exact -3.6.  L = 6 here for speed."""
     o, _, _ = tri_oracle(6)
     o.seed(7); o.randomize()
-    res = o.run_annealing(3.0, T_fac=0.98, N_max=20000, N_o=10, N_per_T=100, min_acc_per_site=10, min_accrate=1e-3, sigma_min=0.05)
-    assert -3.6 - 1e-9 <= res["E"] / 36 < -3.595
+    a = golden["annealing"]["params"]
+    res = o.run_annealing(a["T_i"], T_fac=a["T_fac"], N_max=20000, N_o=int(a["N_o"]), N_per_T=int(a["N_per_T"]),
+                          min_acc_per_site=int(a["min_acc_per_site"]), min_accrate=a["min_accrate"], sigma_min=a["σ_min"])
+    assert golden["annealing"]["exact_E_per_site"] - 1e-9 <= res["E"] / 36 < -3.595
+    assert abs(golden["annealing"]["optimization_E"][-1] - golden["annealing"]["exact_E_per_site"]) < 1e-5      # the reference's own end point
 
 
 def test_structure_factor_identity():
