@@ -50,14 +50,18 @@ template <> struct GenOps<3> {
 };
 
 // ------------------------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void mulhilo(uint32_t m, uint32_t x, uint32_t& hi, uint32_t& lo) {
+    // one IMAD.WIDE.U32; written in PTX so the 64-bit product is split without extra carry/IADD3 instructions
+    asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1, %0}, p;\n\t}" : "=r"(hi), "=r"(lo) : "r"(m), "r"(x));
+}
 __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
-        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo(0xD2511F53u, c0, hi0, lo0);
+        mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+        c0 = hi1 ^ c1 ^ k0; c2 = hi0 ^ c3 ^ k1;
+        c1 = lo1; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
@@ -121,6 +125,45 @@ __device__ __forceinline__ void field_from_sums(const Couplings<R, NL>& cp, cons
             for (int b = 0; b < NG; b++) acc = fma(cp.J[l][a * NG + b], S[l][b], acc);
         h[a] = acc;
     }
+}
+
+// Shared-memory variant used by the sweep kernels: sJt[l][b][a] = J_l^{ab} (transposed so that consecutive a are adjacent).
+// FP32: 128-bit broadcast LDS + packed fma.rn.f32x2 (FFMA2: two h components per instruction), 64 LDS + 128 FFMA2 per label
+// instead of 256 FFMA fed through spilling uniform registers.
+template <int NL>
+__device__ __forceinline__ void field_from_sums_smem(const float* sJt, const float (*S)[NG], float* h) {
+    unsigned long long hp[NG / 2];
+#pragma unroll
+    for (int i = 0; i < NG / 2; i++) hp[i] = 0ull;
+#pragma unroll
+    for (int l = 0; l < NL; l++)
+#pragma unroll
+        for (int b = 0; b < NG; b++) {
+            unsigned long long sb;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(sb) : "f"(S[l][b]));
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float4 j4 = *reinterpret_cast<const float4*>(sJt + (l * NG + b) * NG + 4 * q);
+                unsigned long long j01, j23;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(j01) : "f"(j4.x), "f"(j4.y));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(j23) : "f"(j4.z), "f"(j4.w));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(hp[2 * q]) : "l"(j01), "l"(sb));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(hp[2 * q + 1]) : "l"(j23), "l"(sb));
+            }
+        }
+#pragma unroll
+    for (int i = 0; i < NG / 2; i++) asm("mov.b64 {%0, %1}, %2;" : "=f"(h[2 * i]), "=f"(h[2 * i + 1]) : "l"(hp[i]));
+}
+template <int NL>
+__device__ __forceinline__ void field_from_sums_smem(const double* sJt, const double (*S)[NG], double* h) {
+#pragma unroll
+    for (int a = 0; a < NG; a++) h[a] = 0.0;
+#pragma unroll
+    for (int l = 0; l < NL; l++)
+#pragma unroll
+        for (int b = 0; b < NG; b++)
+#pragma unroll
+            for (int a = 0; a < NG; a++) h[a] = fma(sJt[(l * NG + b) * NG + a], S[l][b], h[a]);
 }
 
 // ------------------------------------------------------------------------------------------------ one Metropolis hit

@@ -58,6 +58,7 @@ struct scmc_handle {
     int32_t *nbr = nullptr, *d_orig = nullptr;
     int8_t* lab = nullptr;
     void *beta = nullptr, *sigma = nullptr;      // [R] reals of the handle's precision
+    void* d_Jt = nullptr;                        // [MAXL][16][16] transposed couplings (kernel stages them into shared memory)
     unsigned long long* acc = nullptr;           // [R] accepted-update counters
     uint8_t* active = nullptr;                   // [R] replica still running (annealing) -- nullptr semantics handled by callers
     double* obs = nullptr;                       // [R][SCMC_NOBS] scratch rows

@@ -45,12 +45,19 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #define SCMC_SWEEP_THREADS 128
 #define SCMC_SWEEP_BLOCKS 5
 #endif
+#ifndef SCMC_SWEEP_PREFETCH
+#define SCMC_SWEEP_PREFETCH 0  // measured on B200: L2 prefetch of the next tile costs more issue slots than it hides (2.57e10 vs 2.90e10 upd/s)
+#endif
+#ifndef SCMC_SWEEP_TILES
+#define SCMC_SWEEP_TILES 4      // site tiles (of SCMC_SWEEP_THREADS sites) a block walks over
+#endif
 struct SweepArgs {
     int32_t colour, hits;
     int64_t r0, rcount;        // replica batch [r0, r0 + rcount)
     uint64_t visit0, seed;     // visit number of hit 0 of this pass; stream key
     int64_t roff;              // global replica id of replica 0
     const void *beta, *sigma;  // [R] reals
+    const void* Jt;            // [NL][16][16] transposed couplings Jt[l][b][a] = J_l^{ab} in the handle's precision (global)
     const uint8_t* active;     // [R] or nullptr
     unsigned long long* acc;   // [R]
     // deterministic test mode (nullptr in production): injected randoms / recorded decisions, caller's site order
@@ -70,19 +77,28 @@ __device__ __forceinline__ void neighbour_sums(const DevModel<R, NL>& M, int64_t
         for (int a = 0; a < NG; a++) S[l][a] = R(0);
     const int32_t* nb = M.nbr + p;
     const int8_t* lb = M.lab + p;
+    // opaque 64-bit bases of the replica's four T planes: a neighbour load is then ONE mad.wide (base + 16 * index)
+    unsigned long long Tq[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        Tq[q] = (unsigned long long)(M.T + rbase + q * ps);
+        asm volatile("" : "+l"(Tq[q]));
+    }
+    const unsigned stride = (unsigned)M.N;
 #pragma unroll 2
     for (int k = 0; k < M.z; k += 3) {
-        int j[3], l[3];
+        unsigned j[3];
+        int l[3];
 #pragma unroll
         for (int t = 0; t < 3; t++) {
-            j[t] = nb[(size_t)(k + t) * M.N];
-            l[t] = NL == 1 ? 0 : lb[(size_t)(k + t) * M.N];
+            j[t] = (unsigned)nb[(unsigned)(k + t) * stride];
+            l[t] = NL == 1 ? 0 : lb[(unsigned)(k + t) * stride];
         }
         vec4<R> v[3][4];
 #pragma unroll
         for (int t = 0; t < 3; t++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) v[t][q] = M.T[rbase + j[t] + q * ps];
+            for (int q = 0; q < 4; q++) v[t][q] = *reinterpret_cast<const vec4<R>*>(Tq[q] + (unsigned long long)j[t] * sizeof(vec4<R>));
 #pragma unroll
         for (int t = 0; t < 3; t++) {
 #pragma unroll
@@ -97,34 +113,59 @@ __device__ __forceinline__ void neighbour_sums(const DevModel<R, NL>& M, int64_t
     }
 }
 
+// Software prefetch of everything the NEXT site tile of this thread will read (psi planes, neighbour T planes) into L2:
+// no registers are held across the hit loop, and the DRAM round trip of the next tile overlaps with the current tile's hits.
+template <class R, int NL, int D>
+__device__ __forceinline__ void prefetch_site(const DevModel<R, NL>& M, int64_t rbase, size_t ps, int p) {
+#pragma unroll
+    for (int v = 0; v < D / 2; v++) asm volatile("prefetch.global.L2 [%0];" ::"l"(M.psi + rbase + p + v * ps));
+    const int32_t* nb = M.nbr + p;
+    const unsigned stride = (unsigned)M.N;
+    for (int k = 0; k < M.z; k++) {
+        const unsigned j = (unsigned)nb[(unsigned)k * stride];
+#pragma unroll
+        for (int q = 0; q < 4; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(M.T + rbase + j + q * ps));
+    }
+}
+
 // One colour pass: every (replica, site of this colour) gets `hits` consecutive Metropolis updates.
-// grid = (ceil(n_colour_sites / 256), replicas of the batch); INJECT = deterministic test mode (host-supplied randoms).
+// grid = (blocks per replica, replicas of the batch); a block walks over tiles of blockDim.x sites of its replica so that the
+// coupling table (global -> shared, coalesced) is staged once per block.  INJECT = deterministic test mode (host-supplied randoms).
 template <class R, int GEN, bool ONSITE, int NL, bool INJECT>
 __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep_colour(const __grid_constant__ DevModel<R, NL> M, const SweepArgs A) {
     constexpr int D = GenOps<GEN>::D;
     const int nc = M.col_off[A.colour + 1] - M.col_off[A.colour];
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r = A.r0 + blockIdx.y;
-    const bool live = s < nc && (A.active == nullptr || A.active[r]);
+    __shared__ __align__(16) R sJt[NL * NG * NG];
+    for (int t = threadIdx.x; t < NL * NG * NG; t += blockDim.x) sJt[t] = ((const R*)A.Jt)[t];
+    const bool alive = (A.active == nullptr || A.active[r]);
+    const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+    const R nbeta = neg_beta_scaled(beta);
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const int64_t rbase = r * M.Ns;
+    __syncthreads();
     unsigned nacc = 0;
-    if (live) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nc && alive; s += gridDim.x * blockDim.x) {
         const int p = M.col_off[A.colour] + s;
-        const size_t ps = (size_t)M.nrep * M.Ns;
-        const int64_t rbase = r * M.Ns;
         R re[D], im[D], T[NG], Tsq[NG], h[NG];
         load_psi<R, D>(M.psi + rbase + p, ps, re, im);
-        const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
         const int site = M.orig[p];
         {
             R S[NL][NG];
             neighbour_sums<R, NL>(M, rbase, ps, p, S);
-            field_from_sums<R, NL>(M.cp, S, h);
+            field_from_sums_smem<NL>(sJt, S, h);
         }
         GenOps<GEN>::expect(re, im, T);
         if (ONSITE) GenOps<GEN>::expect_sq(re, im, Tsq);
         // e_loc = T.h (+ K.Tsq): dE of a proposal is e_loc' - e_loc, which needs one dot product per hit
         R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
-        const R nbeta = neg_beta_scaled(beta);
+#if SCMC_SWEEP_PREFETCH
+        {
+            const int sn = s + gridDim.x * blockDim.x;
+            if (sn < nc) prefetch_site<R, NL, D>(M, rbase, ps, M.col_off[A.colour] + sn);
+        }
+#endif
+        unsigned mine = 0;
         for (int hit = 0; hit < A.hits; hit++) {
             R xr[D], xi[D], u, dE;
             if (INJECT) {
@@ -141,15 +182,16 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
                 A.out_acc[t] = ok ? 1 : 0;
                 if (A.out_dE) A.out_dE[t] = (double)dE;
             }
-            nacc += ok ? 1u : 0u;
+            mine += ok ? 1u : 0u;
         }
-        if (nacc) {
+        if (mine) {
             store_psi<R, D>(M.psi + rbase + p, ps, re, im);
             store_T<R>(M.T + rbase + p, ps, T);
             if (ONSITE) store_T<R>(M.Tsq + rbase + p, ps, Tsq);
         }
+        nacc += mine;
     }
-    // acceptance counters: one atomic per warp (a warp never spans two replicas)
+    // acceptance counters: one atomic per warp (a block never spans two replicas)
     const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
     if ((threadIdx.x & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
 }
@@ -409,7 +451,9 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
         for (int64_t y0 = 0; y0 < A.rcount; y0 += 65535) {      // gridDim.y limit
             SweepArgs B = A;
             B.r0 = A.r0 + y0; B.rcount = std::min<int64_t>(65535, A.rcount - y0);
-            const dim3 grid(grid_for(nc, SCMC_SWEEP_THREADS), (unsigned)B.rcount);
+            B.Jt = h->d_Jt;
+            const unsigned tiles = grid_for(nc, SCMC_SWEEP_THREADS);
+            const dim3 grid((tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES, (unsigned)B.rcount);
             if (A.inj_xi) k_sweep_colour<R, GEN, ONS, NL, true><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
             else k_sweep_colour<R, GEN, ONS, NL, false><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
             h->launches++;
@@ -600,6 +644,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     A((void**)&h->nbr, nb.size() * sizeof(int32_t));
     A((void**)&h->lab, lb.size());
     A((void**)&h->d_orig, N * sizeof(int32_t));
+    A(&h->d_Jt, (size_t)MAXL * 256 * h->esz());
     A(&h->beta, h->R * h->esz());
     A(&h->sigma, h->R * h->esz());
     A((void**)&h->acc, h->R * sizeof(unsigned long long));
@@ -612,6 +657,17 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     C(cudaMemcpy(h->nbr, nb.data(), nb.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     C(cudaMemcpy(h->lab, lb.data(), lb.size(), cudaMemcpyHostToDevice));
     C(cudaMemcpy(h->d_orig, h->orig.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
+    {
+        std::vector<char> jt((size_t)MAXL * 256 * h->esz(), 0);
+        for (int l = 0; l < n_labels; l++)
+            for (int a = 0; a < 16; a++)
+                for (int b = 0; b < 16; b++) {
+                    const double v = h->J[l][a * 16 + b];
+                    if (precision == 64) ((double*)jt.data())[(l * 16 + b) * 16 + a] = v;
+                    else ((float*)jt.data())[(l * 16 + b) * 16 + a] = (float)v;
+                }
+        C(cudaMemcpy(h->d_Jt, jt.data(), jt.size(), cudaMemcpyHostToDevice));
+    }
     C(cudaMemset(h->psi, 0, plane * (d / 2)));
     C(cudaMemset(h->T, 0, plane * 4));
     if (h->onsite) C(cudaMemset(h->Tsq, 0, plane * 4));
@@ -625,7 +681,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
 int32_t scmc_destroy(scmc_t* h) {
     if (!h) return SCMC_OK;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs};
+    void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     delete h;

@@ -151,7 +151,7 @@ def test_replica_sharding_is_invisible(scmc):
 def test_invariants_after_sweeps(scmc, precision):
     """Size-independent properties on a large lattice (128 x 128 triangular, BASELINE C5 shape, fewer replicas)."""
     cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 128, 1, n_replicas=4, precision=precision, seed=99)
-    assert cfg.info()["n_colours"] == 4
+    assert cfg.info()["n_colours"] == 6          # 3 large classes + seam classes (lattice.colourSites)
     E0 = cfg.energies()
     acc, att = cfg.sweep(3, np.array([0.5, 2.0, 10.0, 1e9]), np.array([0.5, 0.3, 0.2, 0.2]))
     assert np.all(acc > 0) and np.all(acc <= att)

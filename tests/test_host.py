@@ -45,7 +45,7 @@ def test_unknown_model_returns_none(scmc, caplog):
 
 def test_colourings(scmc):
     from scmc_b200 import lattice as pl
-    for name, L, ncol in (("triangular", 6, 3), ("triangular", 128, 4), ("triangular", 48, 3), ("triangular", 36, 3), ("honeycomb", 96, 2),
+    for name, L, ncol in (("triangular", 6, 3), ("triangular", 128, 6), ("triangular", 48, 3), ("triangular", 36, 3), ("honeycomb", 96, 2),
                           ("triangular", 5, None), ("square", 4, 2)):
         lat = pl.getLatticePeriodic(pl.getUnitcell(name), L)
         col = pl.colourSites(lat)
@@ -53,6 +53,11 @@ def test_colourings(scmc):
             assert col.max() + 1 == ncol
         for k in range(lat.nbr_site.shape[1]):
             assert np.all(col != col[lat.nbr_site[:, k]])
+    # L % 3 != 0: three large classes + O(L) seam sites in the extra ones (each T is read by 2 other passes instead of 3)
+    lat = pl.getLatticePeriodic(pl.getUnitcell("triangular"), 128)
+    sizes = np.bincount(pl.colourSites(lat))
+    assert sizes[:3].sum() > 0.98 * lat.n_sites and sizes[:3].min() > 5000
+    assert pl.colourSites(lat, prefer_few_passes=False).max() + 1 == 4
 
 
 def test_log_binner_against_oracle_formula(scmc, oracle_mod):
