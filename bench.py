@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--coupling", default="notebook", choices=["notebook", "dense"])
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 streaming, 2 resident")
     ap.add_argument("--batch", type=int, default=0, help="replicas per L2 batch (streaming path)")
+    ap.add_argument("--colouring", default="auto", choices=["auto", "few", "balanced"], help="few = 3 large + seam classes, balanced = 2x2 parity (4 equal classes)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -189,8 +190,12 @@ def run_ours(args):
     J = couplings(args.coupling)
     Ts_all = temperatures(R_total)
     Ts = Ts_all[roff:roff + R]
+    colour = None
+    if args.colouring != "auto":
+        from scmc_b200 import lattice as _pl
+        colour = _pl.colourSites(_pl.getLatticePeriodic(_pl.getUnitcell("triangular"), args.L), prefer_few_passes=(args.colouring == "few"))
     cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [J], args.L, 1, n_replicas=R, precision=args.precision, device=local,
-                             seed=SEED, replica_offset=roff)
+                             seed=SEED, replica_offset=roff, colour=colour)
     cfg.set_sweep_mode(args.mode, args.batch)
     lib, h = cfg._lib, cfg._h
     N = cfg.nSites
@@ -270,6 +275,8 @@ def run_ours(args):
         d, w = cfg.d, args.precision // 8
         info = cfg.info()
         n_launch_local = max(1, launches // world)
+        uses_resident = info["resident"] and (args.mode == 2 or (args.mode == 0 and info["cluster"] <= 4 and (args.sweeps >= 4 or R * N / info["n_colours"] < 300000)))
+        kernel_name = f"replica-resident cluster({info['cluster']})" if uses_resident else "streaming colour-pass"
         # algorithmic bytes per kernel launch: state in + state out (4 d w bytes) of every site the launch visits
         sites_per_launch = R * N * args.sweeps * args.steps / n_launch_local
         alg_bytes = sites_per_launch * 4 * d * w
@@ -288,7 +295,7 @@ def run_ours(args):
                 "config": {"workload": f"C5: triangular {args.L}x{args.L} n=1, {R_total} replicas (64 T in [0.02,2] x copies), {args.coupling} J applied dense 16x16, "
                                        f"{args.sweeps} sweep(s)/step x {args.hits} hits/site-visit, {info['n_colours']}-colour schedule",
                            "replicas_per_gpu": R, "sites": N, "hits_per_visit": args.hits, "sweeps_per_step": args.sweeps,
-                           "kernel": "streaming colour-pass" if not info["resident"] else f"replica-resident cluster({info['cluster']})",
+                           "kernel": kernel_name,
                            "cache_note": f"state {info['device_bytes'] / 2**30:.1f} GiB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
                            "acceptance_rate": acc_rate, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -36,6 +36,7 @@ struct DevModel {
     const int32_t* nbr;   // [z][N]        neighbour (permuted index) or -1
     const int8_t* lab;    // [z][N]        coupling label of that bond
     const int32_t* orig;  // [N]           permuted index -> caller's site number
+    const int32_t* col_list;  // [N]       permuted indices grouped by colour: class c = col_list[col_off[c] .. col_off[c+1])
     int32_t N, Ns, z, n_col;
     int64_t nrep;
     int32_t col_off[MAXC + 1];
@@ -55,7 +56,8 @@ struct scmc_handle {
     double e_const = 0.0;     // N * sum_a K^a when (G^a)^2 = 1 (n = 1, 3): constant on-site energy
     // device memory
     void *psi = nullptr, *T = nullptr, *Tsq = nullptr;
-    int32_t *nbr = nullptr, *d_orig = nullptr;
+    int32_t *nbr = nullptr, *d_orig = nullptr, *d_col_list = nullptr;
+    uint16_t* d_nbr16 = nullptr;                 // [z][N] resident-kernel neighbour codes: owner CTA << 12 | local index
     int8_t* lab = nullptr;
     void *beta = nullptr, *sigma = nullptr;      // [R] reals of the handle's precision
     void* d_Jt = nullptr;                        // [MAXL][16][16] transposed couplings (kernel stages them into shared memory)
@@ -65,6 +67,13 @@ struct scmc_handle {
     void* pinned = nullptr;                      // pinned host staging for the beta / sigma tables
     int64_t bytes = 0, launches = 0;
     int32_t sweep_mode = 0;
+    // replica-resident kernel plan (scmc_resident.cu): a cluster of `cs` CTAs keeps one replica in distributed shared memory
+    struct {
+        int eligible = 0, cs = 0, n_own_max = 0, cap = 0, nthreads = 0, max_clusters = 0;
+        size_t smem = 0;
+        int cta_off[17] = {0};                    // first permuted site of every CTA's chunk
+        int cta_col_off[16][scmc::MAXC + 1] = {{0}};   // local offsets of the colour classes inside a chunk
+    } res;
     int64_t batch = 0;
     size_t esz() const { return prec == 64 ? 8 : 4; }
 };
@@ -75,4 +84,7 @@ int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma);
 int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active);
 int32_t launch_measure(scmc_handle* h, double* d_rows /* device [R][SCMC_NOBS] */);
 int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes);
+// implemented in scmc_resident.cu
+void plan_resident(scmc_handle* h, const std::vector<int>& owner_of_perm);
+int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active);
 }  // namespace scmc

@@ -52,7 +52,7 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #define SCMC_SWEEP_TILES 4      // site tiles (of SCMC_SWEEP_THREADS sites) a block walks over
 #endif
 struct SweepArgs {
-    int32_t colour, hits;
+    int32_t colour, colour_last, hits;   // classes [colour, colour_last] are visited in order by ONE block per replica when colour_last > colour
     int64_t r0, rcount;        // replica batch [r0, r0 + rcount)
     uint64_t visit0, seed;     // visit number of hit 0 of this pass; stream key
     int64_t roff;              // global replica id of replica 0
@@ -134,7 +134,6 @@ __device__ __forceinline__ void prefetch_site(const DevModel<R, NL>& M, int64_t 
 template <class R, int GEN, bool ONSITE, int NL, bool INJECT>
 __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep_colour(const __grid_constant__ DevModel<R, NL> M, const SweepArgs A) {
     constexpr int D = GenOps<GEN>::D;
-    const int nc = M.col_off[A.colour + 1] - M.col_off[A.colour];
     const int64_t r = A.r0 + blockIdx.y;
     __shared__ __align__(16) R sJt[NL * NG * NG];
     for (int t = threadIdx.x; t < NL * NG * NG; t += blockDim.x) sJt[t] = ((const R*)A.Jt)[t];
@@ -145,8 +144,10 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
     const int64_t rbase = r * M.Ns;
     __syncthreads();
     unsigned nacc = 0;
+    for (int colour = A.colour; colour <= A.colour_last; colour++) {
+    const int nc = M.col_off[colour + 1] - M.col_off[colour];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nc && alive; s += gridDim.x * blockDim.x) {
-        const int p = M.col_off[A.colour] + s;
+        const int p = M.col_list[M.col_off[colour] + s];
         R re[D], im[D], T[NG], Tsq[NG], h[NG];
         load_psi<R, D>(M.psi + rbase + p, ps, re, im);
         const int site = M.orig[p];
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
 #if SCMC_SWEEP_PREFETCH
         {
             const int sn = s + gridDim.x * blockDim.x;
-            if (sn < nc) prefetch_site<R, NL, D>(M, rbase, ps, M.col_off[A.colour] + sn);
+            if (sn < nc) prefetch_site<R, NL, D>(M, rbase, ps, M.col_list[M.col_off[colour] + sn]);
         }
 #endif
         unsigned mine = 0;
@@ -190,6 +191,8 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
             if (ONSITE) store_T<R>(M.Tsq + rbase + p, ps, Tsq);
         }
         nacc += mine;
+    }
+    if (colour < A.colour_last) __syncthreads();     // small seam classes: same block, next colour sees this colour's stores
     }
     // acceptance counters: one atomic per warp (a block never spans two replicas)
     const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
@@ -392,7 +395,7 @@ static DevModel<R, NL> make_model(const scmc_handle* h) {
     DevModel<R, NL> M;
     memset(&M, 0, sizeof M);
     M.psi = (vec4<R>*)h->psi; M.T = (vec4<R>*)h->T; M.Tsq = (vec4<R>*)h->Tsq;
-    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig;
+    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig; M.col_list = h->d_col_list;
     M.N = (int32_t)h->N; M.Ns = (int32_t)h->Ns; M.z = h->z; M.n_col = h->n_col; M.nrep = h->R;
     for (int c = 0; c <= MAXC; c++) M.col_off[c] = h->col_off[c];
     for (int l = 0; l < NL; l++)
@@ -445,7 +448,8 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
         constexpr bool ONS = decltype(ons)::value != 0;
-        const int nc = h->col_off[A.colour + 1] - h->col_off[A.colour];
+        int nc = 0;
+        for (int c = A.colour; c <= A.colour_last; c++) nc = std::max(nc, h->col_off[c + 1] - h->col_off[c]);
         if (nc == 0 || A.rcount == 0) return SCMC_OK;
         auto M = make_model<R, NL>(h);
         for (int64_t y0 = 0; y0 < A.rcount; y0 += 65535) {      // gridDim.y limit
@@ -453,7 +457,7 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
             B.r0 = A.r0 + y0; B.rcount = std::min<int64_t>(65535, A.rcount - y0);
             B.Jt = h->d_Jt;
             const unsigned tiles = grid_for(nc, SCMC_SWEEP_THREADS);
-            const dim3 grid((tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES, (unsigned)B.rcount);
+            const dim3 grid(A.colour_last > A.colour ? 1u : (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES, (unsigned)B.rcount);
             if (A.inj_xi) k_sweep_colour<R, GEN, ONS, NL, true><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
             else k_sweep_colour<R, GEN, ONS, NL, false><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
             h->launches++;
@@ -466,16 +470,30 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
 // Streaming path: replicas are processed in batches (sized to stay L2-resident across the colour passes of all
 // n_sweeps when h->batch > 0); within a batch, sweeps x colours launches.
 int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active) {
+    if (h->sweep_mode == 2 && !h->res.eligible) { set_error("resident sweep kernel requested but this lattice does not fit in cluster shared memory"); return SCMC_ERR_UNSUPPORTED; }
+    if (h->sweep_mode == 2) return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active);
+    if (h->sweep_mode == 0 && h->res.eligible) {
+        // measured on B200 (profiles/README.md): the resident kernel wins when colour passes are small (launch-bound) or many
+        // sweeps run per call; the streaming kernel wins for one-replica-per-8-CTA lattices (C5) and single-sweep calls of big batches
+        const int64_t work_per_pass = h->R * h->N / std::max(1, h->n_col);
+        if (h->res.cs <= 4 && (n_sweeps >= 4 || work_per_pass < 300000)) return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active);
+    }
     const int64_t batch = h->batch > 0 ? std::min<int64_t>(h->batch, h->R) : h->R;
     for (int64_t r0 = 0; r0 < h->R; r0 += batch) {
         const int64_t rc = std::min<int64_t>(batch, h->R - r0);
+        // trailing colour classes that are small (seam repairs) are visited by one block per replica in a single launch
+        int first_small = h->n_col;
+        while (first_small > 1 && h->col_off[first_small] - h->col_off[first_small - 1] <= 2 * SCMC_SWEEP_THREADS) first_small--;
+        if (first_small == h->n_col - 1) first_small = h->n_col;      // a single small class gains nothing
         for (int64_t s = 0; s < n_sweeps; s++)
             for (int c = 0; c < h->n_col; c++) {
                 SweepArgs A{};
-                A.colour = c; A.hits = hits; A.r0 = r0; A.rcount = rc;
+                A.colour = c; A.colour_last = c; A.hits = hits; A.r0 = r0; A.rcount = rc;
+                if (c >= first_small) { A.colour_last = h->n_col - 1; }
                 A.visit0 = (sweep_counter + (uint64_t)s) * (uint64_t)hits; A.seed = seed; A.roff = h->roff;
                 A.beta = h->beta; A.sigma = h->sigma; A.active = active; A.acc = h->acc;
                 SCMC_TRY(launch_colour_pass(h, A));
+                if (A.colour_last > c) c = A.colour_last;
             }
     }
     return SCMC_OK;
@@ -615,13 +633,33 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
         }
     h->n_col = ncol;
     h->perm.resize(N); h->orig.resize(N);
+    // Site order on the device: (owner CTA of the resident kernel, colour, caller's index).  The owner is a contiguous
+    // block of the caller's numbering (a strip of the lattice), so that a CTA's chunk is contiguous in every plane; with one
+    // CTA per replica this is plain colour-major order.  col_list groups the permuted indices by colour for the streaming kernel.
+    std::vector<int> owner_of_perm(N, 0);
+    std::vector<int32_t> col_list(N);
     {
-        int32_t at = 0;
-        for (int c = 0; c < ncol; c++) {
-            h->col_off[c] = at;
-            for (int64_t i = 0; i < N; i++) if (h->colour[i] == c) { h->perm[i] = at; h->orig[at] = (int32_t)i; at++; }
+        const size_t w = precision == 64 ? 8 : 4;
+        const size_t per_site = 16 * w * (4 + d / 2 + (h->onsite ? 4 : 0)) / 4 + 2 * (size_t)h->z + (n_labels > 1 ? (size_t)h->z : 0);
+        int cs = 0;
+        for (int c : {1, 2, 4, 8}) {
+            const int64_t n_own = (N + c - 1) / c;
+            const size_t cap = (size_t)(n_own + 1 + 7) / 8 * 8;
+            if (cap * per_site + (size_t)MAXL * 256 * w + 1024 <= (size_t)226 * 1024 && n_own + 1 <= 4096 && N >= c) { cs = c; break; }
         }
-        for (int c = ncol; c <= MAXC; c++) h->col_off[c] = at;
+        const int64_t n_nom = cs ? (N + cs - 1) / cs : N;
+        int32_t at = 0;
+        for (int b = 0; b < (cs ? cs : 1); b++)
+            for (int c = 0; c < ncol; c++)
+                for (int64_t i = b * n_nom; i < std::min<int64_t>(N, (b + 1) * n_nom); i++)
+                    if (h->colour[i] == c) { h->perm[i] = at; h->orig[at] = (int32_t)i; owner_of_perm[at] = b; at++; }
+        h->res.cs = cs;
+        int32_t cl = 0;
+        for (int c = 0; c < ncol; c++) {
+            h->col_off[c] = cl;
+            for (int32_t q = 0; q < N; q++) if (h->colour[h->orig[q]] == c) col_list[cl++] = q;
+        }
+        for (int c = ncol; c <= MAXC; c++) h->col_off[c] = cl;
     }
 
     // --- device
@@ -644,6 +682,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     A((void**)&h->nbr, nb.size() * sizeof(int32_t));
     A((void**)&h->lab, lb.size());
     A((void**)&h->d_orig, N * sizeof(int32_t));
+    A((void**)&h->d_col_list, N * sizeof(int32_t));
     A(&h->d_Jt, (size_t)MAXL * 256 * h->esz());
     A(&h->beta, h->R * h->esz());
     A(&h->sigma, h->R * h->esz());
@@ -657,6 +696,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     C(cudaMemcpy(h->nbr, nb.data(), nb.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     C(cudaMemcpy(h->lab, lb.data(), lb.size(), cudaMemcpyHostToDevice));
     C(cudaMemcpy(h->d_orig, h->orig.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
+    C(cudaMemcpy(h->d_col_list, col_list.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
     {
         std::vector<char> jt((size_t)MAXL * 256 * h->esz(), 0);
         for (int l = 0; l < n_labels; l++)
@@ -674,6 +714,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     C(cudaMemset(h->acc, 0, h->R * sizeof(unsigned long long)));
     C(cudaMemset(h->active, 1, h->R));
     if (ce != cudaSuccess) { scmc_destroy(h); return cuda_fail(ce, "scmc_create upload", __FILE__, __LINE__); }
+    plan_resident(h, owner_of_perm);     // neighbour codes, launch geometry, eligibility of the replica-resident kernel
     *out = h;
     return SCMC_OK;
 }
@@ -681,7 +722,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
 int32_t scmc_destroy(scmc_t* h) {
     if (!h) return SCMC_OK;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt};
+    void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_col_list, h->d_nbr16};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     delete h;
@@ -696,7 +737,7 @@ int32_t scmc_set_stream(scmc_t* h, void* s) {
 
 int32_t scmc_info(scmc_t* h, int64_t* info) {
     SCMC_ARG(h && info, "null argument");
-    info[0] = h->n_col; info[1] = h->gen_id; info[2] = h->bytes; info[3] = 0; info[4] = 0; info[5] = h->launches; info[6] = h->N; info[7] = h->R;
+    info[0] = h->n_col; info[1] = h->gen_id; info[2] = h->bytes; info[3] = h->res.eligible; info[4] = h->res.cs; info[5] = h->launches; info[6] = h->N; info[7] = h->R;
     return SCMC_OK;
 }
 
@@ -898,7 +939,7 @@ int32_t scmc_sweep_deterministic(scmc_t* h, int32_t hits, const double* beta, co
     }
     for (int c = 0; c < h->n_col && st == SCMC_OK; c++) {
         SweepArgs A{};
-        A.colour = c; A.hits = hits; A.r0 = 0; A.rcount = h->R; A.visit0 = 0; A.seed = 0; A.roff = h->roff;
+        A.colour = c; A.colour_last = c; A.hits = hits; A.r0 = 0; A.rcount = h->R; A.visit0 = 0; A.seed = 0; A.roff = h->roff;
         A.beta = h->beta; A.sigma = h->sigma; A.active = nullptr; A.acc = h->acc;
         A.inj_xi = dxi; A.inj_u = du; A.out_acc = dacc; A.out_dE = ddE;
         st = launch_colour_pass(h, A);

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(128) k_optimize_colour(const __grid_constant__
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M.nrep * nc) return;
     const int64_t r = idx / nc;
-    const int p = M.col_off[colour] + (int)(idx - r * nc);
+    const int p = M.col_list[M.col_off[colour] + (int)(idx - r * nc)];
     const size_t ps = (size_t)M.nrep * M.Ns;
     const int64_t rbase = r * M.Ns;
     R re[D], im[D], h[NG], Hr[D * D], Hi[D * D];
@@ -207,7 +207,7 @@ static DevModel<R, NL> make_model_d(const scmc_handle* h) {
     DevModel<R, NL> M;
     memset(&M, 0, sizeof M);
     M.psi = (vec4<R>*)h->psi; M.T = (vec4<R>*)h->T; M.Tsq = (vec4<R>*)h->Tsq;
-    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig;
+    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig; M.col_list = h->d_col_list;
     M.N = (int32_t)h->N; M.Ns = (int32_t)h->Ns; M.z = h->z; M.n_col = h->n_col; M.nrep = h->R;
     for (int c = 0; c <= MAXC; c++) M.col_off[c] = h->col_off[c];
     for (int l = 0; l < NL; l++)

@@ -1,0 +1,350 @@
+// scmc_resident.cu -- replica-resident Metropolis sweeps: one thread-block cluster keeps ONE replica's whole lattice
+// (psi, T, (Tsq), neighbour codes, couplings) in distributed shared memory for all sweeps of a launch.
+//
+// Replaces the same reference loops as the streaming kernel (2N-update loops + localUpdate!, /root/reference/src/MonteCarlo.jl:40-44,
+// 76-80, 152-156, 263-286) and produces bit-identical chains (same stream v1, same colour order, same arithmetic).
+//
+// Why: the streaming colour-pass kernel re-reads every neighbour T vector from HBM in every colour pass (272-332 B of DRAM
+// traffic per site visit, profiles/).  Here HBM is touched once per launch (state in, state out = the algorithmic 4 d w bytes
+// per site, plus the T cache), every neighbour read is a shared-memory read (own CTA) or a DSMEM read (ld.shared::cluster into
+// the neighbouring strip's CTA), and colour passes are separated by cluster barriers instead of kernel launches.
+//   C5 (128 x 128 triangular, FP32): 16384 sites x 96 B = 1.5 MB  ->  cluster of 8 CTAs x 216 KB.
+#include <algorithm>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+#include <cooperative_groups.h>
+#include "handle.h"
+
+namespace cg = cooperative_groups;
+
+namespace scmc {
+
+struct ResidentArgs {
+    int64_t nrep, roff;
+    int32_t n_sweeps, hits, cs, n_own_max, cap, n_clusters;
+    uint64_t visit0, seed;
+    const void *beta, *sigma, *Jt;
+    const uint8_t* active;
+    unsigned long long* acc;
+    const uint16_t* nbr16;          // [z][N]
+    int32_t cta_off[17];
+    int32_t cta_col_off[16][MAXC + 1];
+};
+
+// ---- shared-memory / DSMEM access helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+template <bool CLUSTER> __device__ __forceinline__ float4 ld_v4(uint32_t addr, float) {
+    float4 v;
+    if (CLUSTER) asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    else asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+template <bool CLUSTER> __device__ __forceinline__ double4 ld_v4(uint32_t addr, double) {
+    double4 v;
+    if (CLUSTER) {
+        asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+        asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.z), "=d"(v.w) : "r"(addr + 16));
+    } else {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.z), "=d"(v.w) : "r"(addr + 16));
+    }
+    return v;
+}
+
+// One replica at a time per cluster; grid = n_clusters * cs CTAs, persistent over replicas.
+template <class R, int GEN, bool ONSITE, int NL, bool CLUSTER>
+__global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ DevModel<R, NL> M, const __grid_constant__ ResidentArgs A) {
+    constexpr int D = GenOps<GEN>::D;
+    constexpr int NPV = D / 2;
+    using V = vec4<R>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cap = A.cap, nmax = A.n_own_max;
+    V* sT = reinterpret_cast<V*>(smem_raw);                       // [4][cap]
+    V* sPsi = sT + 4 * cap;                                       // [NPV][cap]
+    V* sTsq = sPsi + NPV * cap;                                   // [4][cap] (ONSITE only)
+    R* sJt = reinterpret_cast<R*>(sTsq + (ONSITE ? 4 * cap : 0)); // [NL][16][16]
+    uint16_t* sNbr = reinterpret_cast<uint16_t*>(sJt + NL * NG * NG);        // [z][nmax]
+    int8_t* sLab = reinterpret_cast<int8_t*>(sNbr + (size_t)M.z * nmax);     // [z][nmax] (NL > 1 only)
+    __shared__ unsigned s_acc;
+
+    unsigned rank = 0, cluster_id = blockIdx.x;
+    if (CLUSTER) {
+        cg::cluster_group cl = cg::this_cluster();
+        rank = cl.block_rank();
+        cluster_id = blockIdx.x / A.cs;
+    }
+    const int my_off = A.cta_off[rank];
+    const int n_own = A.cta_off[rank + 1] - my_off;
+    const int tid = threadIdx.x, nth = blockDim.x;
+
+    // ---- one-time staging: couplings, neighbour codes (and labels) of my sites, the all-zero padding slot
+    for (int t = tid; t < NL * NG * NG; t += nth) sJt[t] = ((const R*)A.Jt)[t];
+    for (int k = 0; k < M.z; k++)
+        for (int q = tid; q < n_own; q += nth) {
+            sNbr[k * nmax + q] = A.nbr16[(size_t)k * M.N + my_off + q];
+            if (NL > 1) sLab[k * nmax + q] = M.lab[(size_t)k * M.N + my_off + q];
+        }
+    if (tid < 4) sT[tid * cap + nmax] = make_v4<R>(R(0), R(0), R(0), R(0));
+    if (tid == 0) s_acc = 0;
+    __syncthreads();
+
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const uint32_t sT_u32 = smem_u32(sT);
+    const uint32_t plane_bytes = (uint32_t)cap * (uint32_t)sizeof(V);
+
+    for (int64_t r = cluster_id; r < A.nrep; r += A.n_clusters) {
+        if (A.active != nullptr && !A.active[r]) continue;          // uniform over the cluster
+        const int64_t gbase = r * M.Ns + my_off;
+        // ---- load my strip of the replica (coalesced 128-bit loads, state in)
+        for (int q = tid; q < n_own; q += nth) {
+#pragma unroll
+            for (int v = 0; v < NPV; v++) sPsi[v * cap + q] = M.psi[gbase + q + v * ps];
+#pragma unroll
+            for (int v = 0; v < 4; v++) sT[v * cap + q] = M.T[gbase + q + v * ps];
+            if (ONSITE) {
+#pragma unroll
+                for (int v = 0; v < 4; v++) sTsq[v * cap + q] = M.Tsq[gbase + q + v * ps];
+            }
+        }
+        const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+        const R nbeta = neg_beta_scaled(beta);
+        if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
+        unsigned nacc = 0;
+        for (int sweep = 0; sweep < A.n_sweeps; sweep++) {
+            const uint64_t visit_base = A.visit0 + (uint64_t)sweep * (uint64_t)A.hits;
+            for (int c = 0; c < M.n_col; c++) {
+                const int c0 = A.cta_col_off[rank][c], cnt = A.cta_col_off[rank][c + 1] - c0;
+                for (int s = tid; s < cnt; s += nth) {
+                    const int q = c0 + s;
+                    R re[D], im[D], T[NG], Tsq[NG], h[NG];
+                    load_psi<R, D>(sPsi + q, (size_t)cap, re, im);
+                    load_T<R>(sT + q, (size_t)cap, T);
+                    if (ONSITE) load_T<R>(sTsq + q, (size_t)cap, Tsq);
+                    const int site = M.orig[my_off + q];
+                    {
+                        R S[NL][NG];
+#pragma unroll
+                        for (int l = 0; l < NL; l++)
+#pragma unroll
+                            for (int a = 0; a < NG; a++) S[l][a] = R(0);
+#pragma unroll 3
+                        for (int k = 0; k < M.z; k++) {
+                            const unsigned code = sNbr[k * nmax + q];
+                            const int l = NL == 1 ? 0 : sLab[k * nmax + q];
+                            uint32_t addr = sT_u32 + (code & 0xFFFu) * (uint32_t)sizeof(V);
+                            if (CLUSTER) addr = map_to_rank(addr, code >> 12);
+                            V v[4];
+#pragma unroll
+                            for (int p4 = 0; p4 < 4; p4++) v[p4] = ld_v4<CLUSTER>(addr + p4 * plane_bytes, R(0));
+#pragma unroll
+                            for (int ll = 0; ll < NL; ll++)
+                                if (NL == 1 || l == ll) {
+#pragma unroll
+                                    for (int p4 = 0; p4 < 4; p4++) {
+                                        S[ll][4 * p4] += v[p4].x; S[ll][4 * p4 + 1] += v[p4].y; S[ll][4 * p4 + 2] += v[p4].z; S[ll][4 * p4 + 3] += v[p4].w;
+                                    }
+                                }
+                        }
+                        field_from_sums_smem<NL>(sJt, S, h);
+                    }
+                    R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
+                    unsigned mine = 0;
+                    for (int hit = 0; hit < A.hits; hit++) {
+                        R xr[D], xi[D], u, dE;
+                        stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
+                        mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+                    }
+                    if (mine) {
+                        store_psi<R, D>(sPsi + q, (size_t)cap, re, im);
+                        store_T<R>(sT + q, (size_t)cap, T);
+                        if (ONSITE) store_T<R>(sTsq + q, (size_t)cap, Tsq);
+                    }
+                    nacc += mine;
+                }
+                // all CTAs finish the colour class before anyone reads its T vectors (release/acquire at cluster scope)
+                if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
+            }
+        }
+        // ---- store my strip (state out) and the acceptance count
+        for (int q = tid; q < n_own; q += nth) {
+#pragma unroll
+            for (int v = 0; v < NPV; v++) M.psi[gbase + q + v * ps] = sPsi[v * cap + q];
+#pragma unroll
+            for (int v = 0; v < 4; v++) M.T[gbase + q + v * ps] = sT[v * cap + q];
+            if (ONSITE) {
+#pragma unroll
+                for (int v = 0; v < 4; v++) M.Tsq[gbase + q + v * ps] = sTsq[v * cap + q];
+            }
+        }
+        const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
+        if ((tid & 31) == 0 && tot) atomicAdd(&s_acc, tot);
+        __syncthreads();
+        if (tid == 0) {
+            if (s_acc) atomicAdd(A.acc + r, (unsigned long long)s_acc);
+            s_acc = 0;
+        }
+        // the next replica's loads overwrite shared memory that remote CTAs may still be reading in their last colour pass:
+        // the cluster barrier that ended that pass already ordered those reads before this point.
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <int V> using ic = std::integral_constant<int, V>;
+template <class R, int NL>
+static DevModel<R, NL> make_model_r(const scmc_handle* h) {
+    DevModel<R, NL> M;
+    memset(&M, 0, sizeof M);
+    M.psi = (vec4<R>*)h->psi; M.T = (vec4<R>*)h->T; M.Tsq = (vec4<R>*)h->Tsq;
+    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig; M.col_list = h->d_col_list;
+    M.N = (int32_t)h->N; M.Ns = (int32_t)h->Ns; M.z = h->z; M.n_col = h->n_col; M.nrep = h->R;
+    for (int c = 0; c <= MAXC; c++) M.col_off[c] = h->col_off[c];
+    for (int l = 0; l < NL; l++)
+        for (int t = 0; t < 256; t++) M.cp.J[l][t] = l < h->n_labels ? (R)h->J[l][t] : R(0);
+    for (int a = 0; a < NG; a++) M.cp.K[a] = (R)h->K[a];
+    return M;
+}
+template <class F>
+static int32_t dispatch_r(const scmc_handle* h, F&& f) {
+    auto with_nl = [&](auto rt, auto gen, auto ons) -> int32_t {
+        if (h->n_labels == 1) return f(rt, gen, ons, ic<1>{});
+        return f(rt, gen, ons, ic<MAXL>{});
+    };
+    auto with_gen = [&](auto rt) -> int32_t {
+        switch (h->gen_id) {
+            case 1: return with_nl(rt, ic<1>{}, ic<0>{});
+            case 2: return h->onsite ? with_nl(rt, ic<2>{}, ic<1>{}) : with_nl(rt, ic<2>{}, ic<0>{});
+            case 3: return with_nl(rt, ic<3>{}, ic<0>{});
+        }
+        return SCMC_ERR_ARG;
+    };
+    return h->prec == 64 ? with_gen(double{}) : with_gen(float{});
+}
+
+template <class K>
+static int32_t configure_and_count(K kernel, scmc_handle* h, int* max_clusters) {
+    auto& P = h->res;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem) != cudaSuccess) { cudaGetLastError(); return SCMC_ERR_UNSUPPORTED; }
+    int n = 0;
+    if (P.cs > 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(P.cs * 148); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = P.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return SCMC_ERR_UNSUPPORTED; }
+    } else {
+        int per_sm = 0, dev = 0, sms = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, P.nthreads, P.smem) != cudaSuccess) { cudaGetLastError(); return SCMC_ERR_UNSUPPORTED; }
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        n = per_sm * sms;
+    }
+    *max_clusters = n;
+    return n > 0 ? SCMC_OK : SCMC_ERR_UNSUPPORTED;
+}
+
+// Called at the end of scmc_create: neighbour codes, chunk tables, launch geometry.  Leaves res.eligible = 0 when the lattice
+// does not fit (the streaming kernel is then the only path).
+void plan_resident(scmc_handle* h, const std::vector<int>& owner_of_perm) {
+    auto& P = h->res;
+    P.eligible = 0;
+    if (P.cs == 0) return;
+    const int64_t N = h->N;
+    const int cs = P.cs;
+    std::vector<int> n_own(cs, 0);
+    for (int64_t q = 0; q < N; q++) n_own[owner_of_perm[q]]++;
+    P.cta_off[0] = 0;
+    for (int b = 0; b < cs; b++) P.cta_off[b + 1] = P.cta_off[b] + n_own[b];
+    P.n_own_max = *std::max_element(n_own.begin(), n_own.end());
+    P.cap = (P.n_own_max + 1 + 7) / 8 * 8;
+    int max_cnt = 1;
+    for (int b = 0; b < cs; b++) {
+        int at = 0;
+        for (int c = 0; c < h->n_col; c++) {
+            P.cta_col_off[b][c] = at;
+            int cnt = 0;
+            for (int q = P.cta_off[b]; q < P.cta_off[b + 1]; q++) cnt += (h->colour[h->orig[q]] == c);
+            at += cnt;
+            max_cnt = std::max(max_cnt, cnt);
+        }
+        for (int c = h->n_col; c <= MAXC; c++) P.cta_col_off[b][c] = at;
+    }
+    const int rounds = (max_cnt + 511) / 512;
+    P.nthreads = std::min(512, std::max(32, ((max_cnt + rounds - 1) / rounds + 31) / 32 * 32));
+    const size_t w = h->esz();
+    P.smem = (size_t)P.cap * 4 * w * (4 + h->d / 2 + (h->onsite ? 4 : 0)) + (size_t)MAXL * 256 * w + (size_t)h->z * P.n_own_max * 2 +
+             (h->n_labels > 1 ? (size_t)h->z * P.n_own_max : 0) + 64;
+    P.smem = (P.smem + 15) / 16 * 16;
+    // neighbour codes in permuted order: owner CTA << 12 | local index; padding slots -> my own zero slot (local index n_own_max)
+    std::vector<uint16_t> code((size_t)h->z * N);
+    std::vector<int32_t> nb((size_t)h->z * N);
+    if (cudaMemcpy(nb.data(), h->nbr, nb.size() * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return; }
+    for (int k = 0; k < h->z; k++)
+        for (int64_t q = 0; q < N; q++) {
+            const int32_t j = nb[(size_t)k * N + q];
+            if (j >= N) code[(size_t)k * N + q] = (uint16_t)((owner_of_perm[q] << 12) | P.n_own_max);
+            else code[(size_t)k * N + q] = (uint16_t)((owner_of_perm[j] << 12) | (j - P.cta_off[owner_of_perm[j]]));
+        }
+    if (dev_alloc(h, (void**)&h->d_nbr16, code.size() * sizeof(uint16_t)) != SCMC_OK) return;
+    if (cudaMemcpy(h->d_nbr16, code.data(), code.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return; }
+    int maxc = 0;
+    const int32_t st = dispatch_r(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+        constexpr bool ONS = decltype(ons)::value != 0;
+        if (cs > 1) return configure_and_count(k_resident<R, GEN, ONS, NL, true>, h, &maxc);
+        return configure_and_count(k_resident<R, GEN, ONS, NL, false>, h, &maxc);
+    });
+    if (st != SCMC_OK) return;
+    P.max_clusters = maxc;
+    P.eligible = 1;
+}
+
+int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active) {
+    auto& P = h->res;
+    if (n_sweeps <= 0) return SCMC_OK;
+    return dispatch_r(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+        constexpr bool ONS = decltype(ons)::value != 0;
+        auto M = make_model_r<R, NL>(h);
+        ResidentArgs A;
+        memset(&A, 0, sizeof A);
+        A.nrep = h->R; A.roff = h->roff; A.hits = hits; A.cs = P.cs; A.n_own_max = P.n_own_max; A.cap = P.cap;
+        A.seed = seed; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.active = active; A.acc = h->acc; A.nbr16 = h->d_nbr16;
+        memcpy(A.cta_off, P.cta_off, sizeof A.cta_off);
+        memcpy(A.cta_col_off, P.cta_col_off, sizeof A.cta_col_off);
+        A.n_clusters = (int32_t)std::min<int64_t>(h->R, P.max_clusters);
+        // sweeps per launch bounded so that visit numbers stay in int32 loop counters and launches stay preemptible
+        for (int64_t done = 0; done < n_sweeps;) {
+            const int64_t chunk = std::min<int64_t>(n_sweeps - done, 4096);
+            A.n_sweeps = (int32_t)chunk;
+            A.visit0 = (sweep_counter + (uint64_t)done) * (uint64_t)hits;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)(A.n_clusters * P.cs)); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem; cfg.stream = h->stream;
+            cudaLaunchAttribute at[1];
+            cfg.attrs = at; cfg.numAttrs = 0;
+            if (P.cs > 1) {
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = P.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.numAttrs = 1;
+                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident<R, GEN, ONS, NL, true>, M, A));
+            } else {
+                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident<R, GEN, ONS, NL, false>, M, A));
+            }
+            h->launches++;
+            done += chunk;
+        }
+        return SCMC_OK;
+    });
+}
+
+}  // namespace scmc
