@@ -1,0 +1,119 @@
+"""BASELINE.json configs at their full lattice sizes (-m gpu), checked through size-independent properties and, where the
+oracle finishes in seconds, against the oracle.  C5 (128 x 128, 8192 replicas) is bench.py's workload; its kernel paths are
+covered at full lattice size by test_gpu_parity.py::test_invariants_after_sweeps / test_resident_kernel_equals_streaming_kernel."""
+import numpy as np
+import pytest
+
+from conftest import NOTEBOOK_J, make_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def ground_state_triangular(L):
+    """FM spin (x) 120-degree valley order: E/N = -3.6 exactly for the notebook couplings when L % 3 == 0."""
+    psi = np.zeros((L * L, 4), dtype=complex)
+    for i in range(L):
+        for j in range(L):
+            ang = 2 * np.pi / 3 * ((i - j) % 3)
+            psi[j + L * i] = np.kron([1, 0], [np.cos(ang / 2), np.sin(ang / 2)])
+    return psi
+
+
+def test_C1_heisenberg_honeycomb_full_run(scmc, oracle_mod):
+    """C1: su(4) Heisenberg J = delta^ab, n = 1, honeycomb 6x6 (72 sites), Metropolis T = 0.1, 1e4 sweeps -- the whole run."""
+    R = 32
+    cfg = scmc.initializeCfg("nearest-neighbor", "honeycomb", [np.eye(16)], 6, 1, n_replicas=R, precision=32, seed=11)
+    obs = scmc.initializeObservables(scmc.ObservablesGeneric, cfg)
+    res = scmc.run_(cfg, obs, 0.1, 1.0, 5000, 5000, measurement_rate=10)
+    assert res["rows"] == 500 and obs.energy[0].count == 500
+    e = res["mean"][:, 0]
+    o = make_oracle(cfg, oracle_mod)
+    es = []
+    for k in range(4):
+        o.seed(50 + k); o.randomize()
+        es.append(o.run_metropolis(0.1, 1.0, 5000, 5000, 10)["series"][:, 0].mean())
+    err = np.hypot(e.std(ddof=1) / np.sqrt(R), np.std(es, ddof=1) / 2)
+    assert abs(e.mean() - np.mean(es)) < 4.5 * err + 2e-4, (e.mean(), np.mean(es), err)
+    m = scmc.means(obs, cfg, 10.0, replica=3)
+    assert m["heat"][0] > 0 and m["energy"][1] > 0 and m["magnetizationVec"][0].shape == (16,)
+    assert np.isclose(m["magnetizationVec"][0][0], 1.0, atol=1e-5)          # T^1 = identity expectation
+
+
+def test_C2_temperature_sweep_48x48(scmc):
+    """C2: spin-valley couplings, n = 1, triangular 48x48, 64 temperatures in one launch.  Started from the exact ground state;
+    low-T equipartition e = -3.6 + (d - 1) T (CP^3 has 6 real modes per site), e(T) monotone, sigma adapts to ~50 % acceptance."""
+    Ts = np.geomspace(0.02, 2.0, 64)
+    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 48, 1, n_replicas=64, precision=32, seed=5)
+    assert cfg.info()["n_colours"] == 3
+    cfg.set_state(np.tile(ground_state_triangular(48)[None], (64, 1, 1)))
+    assert np.allclose(cfg.energies() / cfg.nSites, -3.6, atol=1e-5)
+    res = scmc.run_(cfg, None, Ts, Ts, 400, 600, measurement_rate=10, σ=0.3 * np.sqrt(Ts))
+    e = res["mean"][:, 0]
+    low = Ts <= 0.06
+    assert np.allclose(e[low], -3.6 + 3 * Ts[low], atol=0.012), (e[low], -3.6 + 3 * Ts[low])
+    assert np.all(np.diff(e) > -0.02) and e[-1] > e[0] + 1.5
+    assert np.all(np.abs(res["acc_rate"][Ts < 1.0] - 0.5) < 0.12)
+    c = (res["mean"][:, 1] - e ** 2) * cfg.nSites / Ts ** 2
+    assert abs(np.mean(c[low]) - 3.0) < 0.5                                  # c -> d - 1 = 3 as T -> 0 (notebook: 2.93 +- 0.06)
+
+
+def test_C3_n2_honeycomb_96x96_structure_factor(scmc):
+    """C3: n = 2 (d = 6) on honeycomb 96x96 (18432 sites), 256 replicas, on-site K != 0 (Tsq path), thermal sweep + S^a(k)."""
+    R = 256
+    J = np.eye(16); J[0, 0] = 0.0
+    K = np.diag(np.r_[0.0, np.linspace(-0.2, 0.2, 15)])
+    cfg = scmc.initializeCfg("nearest-neighbor", "honeycomb", [K, J], 96, 2, n_replicas=R, precision=32, seed=8)
+    info = cfg.info()
+    assert info["n_colours"] == 2 and info["generator_table"] == 2 and not info["resident"]
+    E0 = cfg.energies()
+    acc, att = cfg.sweep(2, np.full(R, 4.0), np.full(R, 0.3))
+    assert np.all(acc > 0.1 * att) and np.all(cfg.energies() < E0)
+    psi = cfg.get_state(3, 1)[0]
+    assert np.allclose(np.linalg.norm(psi, axis=-1), 1.0, atol=2e-6)
+    T, Tsq = cfg.get_T(3, squared=True)
+    assert np.allclose(T[:, 0], 2.0, atol=1e-5)
+    assert np.allclose(T, np.einsum("ij,ajk,ik->ia", psi.conj(), cfg.generators, psi).real, atol=2e-5)
+    assert np.allclose(Tsq, np.einsum("ij,ajk,ik->ia", psi.conj(), cfg.generatorsSq, psi).real, atol=4e-5)
+    # energy of replica 3 from the host copy of T: sum over bonds + on-site
+    nb = cfg.interactionSites
+    E_host = 0.5 * np.einsum("ia,ab,ikb->", T, J, T[nb]) + (Tsq * np.diag(K)).sum()
+    assert abs(cfg.energies()[3] - E_host) < 1e-5 * cfg.nSites
+    # structure factor on allowed momenta vs the direct Fourier sum (= the reference's correlation route)
+    B = 2 * np.pi * np.linalg.inv(np.stack(cfg.unitVectors) * cfg.L).T
+    ks = np.array([a * B[0] + b * B[1] for a, b in ((0, 0), (1, 0), (0, 1), (32, 32), (48, 0), (5, 91), (64, 64), (96, 96))])
+    S = scmc.structureFactor(cfg, ks)
+    assert S.shape == (R, 16, len(ks))
+    direct = np.abs(np.einsum("ia,ki->ak", T, np.exp(1j * ks @ cfg.positions.T))) ** 2 / (2 * cfg.nSites)
+    assert np.allclose(S[3], direct, rtol=1e-6, atol=1e-6 * direct.max())
+    assert np.isclose(S[3, 0, 0], (2.0 * cfg.nSites) ** 2 / (2 * cfg.nSites), rtol=1e-5)     # identity component at k = 0
+
+
+def test_C4_annealing_restarts_36x36(scmc):
+    """C4: simulated annealing + local optimisation on triangular 36x36 with the notebook's annealing parameters (cell 25),
+    64 of the 4096 restarts, capped sweep count: energies approach the exact -3.6 and optimisation sweeps never raise them."""
+    R = 64
+    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 36, 1, n_replicas=R, precision=64, seed=3)
+    res = scmc.runAnnealing_(cfg, 3.0, T_fac=0.98, N_max=2500, N_o=0, N_per_T=100, min_acc_per_site=10, min_accrate=1e-3, σ_min=0.05)
+    e_sa = res["E"] / cfg.nSites
+    assert np.all(e_sa < -3.3) and np.all(e_sa > -3.6)
+    assert np.all(res["sweeps"] == 2499)                        # N_max reached before the acceptance-rate stop
+    assert np.all(res["beta"] > 1 / 3.0 * 1.5)
+    E_prev = res["E"]
+    for _ in range(3):
+        E_new = scmc.localOptimization_(cfg, n_sweeps=20)
+        assert np.all(E_new <= E_prev + 1e-9)
+        E_prev = E_new
+    assert np.all(E_prev / cfg.nSites > -3.6 - 1e-9) and np.min(E_prev / cfg.nSites) < -3.5
+
+
+def test_tghbn_model_runs_and_conserves_invariants(scmc, oracle_mod):
+    """tg-hbn model (3 labels, 12 neighbours, on-site K, n = 2) through the production sweep."""
+    cfg = scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.15, 0.8], 12, 2, n_replicas=8, precision=64, seed=21)
+    assert cfg.info()["n_colours"] == 4
+    acc, att = cfg.sweep(5, np.linspace(1, 8, 8), np.full(8, 0.3))
+    assert np.all(acc > 0)
+    o = make_oracle(cfg, oracle_mod, replica=5)
+    assert abs(o.energy() - cfg.energies()[5]) < 1e-9 * cfg.nSites
+    T, Tsq = cfg.get_T(5, squared=True)
+    To, Tsqo = o.get_T()
+    assert np.allclose(T, To, atol=1e-12) and np.allclose(Tsq, Tsqo, atol=1e-12)
