@@ -285,8 +285,8 @@ def run_ours(args):
         traffic = None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            key = f"mode{info.get('kernel_mode', args.mode)}"
-            traffic = prof.get(key, {}).get("dram_bytes_per_launch")
+            if not uses_resident and args.precision == 32 and args.L == 128:      # the configuration the ncu capture was taken on
+                traffic = prof["dram_bytes_per_site_visit"] * sites_per_launch
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": "site-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
