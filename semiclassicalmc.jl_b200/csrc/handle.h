@@ -67,6 +67,7 @@ struct scmc_handle {
     void* pinned = nullptr;                      // pinned host staging for the beta / sigma tables
     int64_t bytes = 0, launches = 0;
     int32_t sweep_mode = 0;
+    int32_t async_pipeline = 0;                  // streaming path: 1 = cp.async-pipelined kernel (measured slower on B200: issue-bound at 16 warps/SM, profiles/README.md)
     // replica-resident kernel plan (scmc_resident.cu): a cluster of `cs` CTAs keeps one replica in distributed shared memory
     struct {
         int eligible = 0, cs = 0, n_own_max = 0, cap = 0, nthreads = 0, max_clusters = 0;

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include "handle.h"
@@ -44,6 +45,19 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #ifndef SCMC_SWEEP_THREADS
 #define SCMC_SWEEP_THREADS 128
 #define SCMC_SWEEP_BLOCKS 5
+#endif
+#ifndef SCMC_ABLATE
+#define SCMC_ABLATE 0            // performance ablations of the direct streaming kernel (profiles/README.md); 0 = production
+#endif
+#ifndef SCMC_ASYNC_THREADS
+#define SCMC_ASYNC_THREADS 128
+#define SCMC_ASYNC_BLOCKS 4
+#endif
+#ifndef SCMC_ASYNC_CP
+#define SCMC_ASYNC_CP "cp.async.cg.shared.global"
+#endif
+#ifndef SCMC_ASYNC_TILES
+#define SCMC_ASYNC_TILES 11      // visits per thread in the cp.async-pipelined kernel
 #endif
 #ifndef SCMC_SWEEP_PREFETCH
 #define SCMC_SWEEP_PREFETCH 0  // measured on B200: L2 prefetch of the next tile costs more issue slots than it hides (2.57e10 vs 2.90e10 upd/s)
@@ -92,6 +106,9 @@ __device__ __forceinline__ void neighbour_sums(const DevModel<R, NL>& M, int64_t
 #pragma unroll
         for (int t = 0; t < 3; t++) {
             j[t] = (unsigned)nb[(unsigned)(k + t) * stride];
+#if SCMC_ABLATE == 2
+            j[t] = (unsigned)p;      // ablation: neighbour = self (no gather traffic)
+#endif
             l[t] = NL == 1 ? 0 : lb[(unsigned)(k + t) * stride];
         }
         vec4<R> v[3][4];
@@ -148,26 +165,52 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
     const int nc = M.col_off[colour + 1] - M.col_off[colour];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nc && alive; s += gridDim.x * blockDim.x) {
         const int p = M.col_list[M.col_off[colour] + s];
+#if SCMC_SWEEP_PREFETCH
+        // indices of this thread's NEXT visit: loaded now, used for L2 prefetches after the mat-vec (no stall, no data registers)
+        const int sn = s + gridDim.x * blockDim.x;
+        int pn = 0;
+        unsigned jn[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        if (sn < nc) {
+            pn = M.col_list[M.col_off[colour] + sn];
+#pragma unroll
+            for (int k = 0; k < 6; k++) jn[k] = k < M.z ? (unsigned)M.nbr[(unsigned)k * (unsigned)M.N + pn] : 0u;
+        }
+#endif
         R re[D], im[D], T[NG], Tsq[NG], h[NG];
         load_psi<R, D>(M.psi + rbase + p, ps, re, im);
         const int site = M.orig[p];
         {
             R S[NL][NG];
             neighbour_sums<R, NL>(M, rbase, ps, p, S);
+#if SCMC_ABLATE == 3
+            for (int a = 0; a < NG; a++) h[a] = S[0][a];      // ablation: no mat-vec
+#else
             field_from_sums_smem<NL>(sJt, S, h);
+#endif
         }
         GenOps<GEN>::expect(re, im, T);
         if (ONSITE) GenOps<GEN>::expect_sq(re, im, Tsq);
         // e_loc = T.h (+ K.Tsq): dE of a proposal is e_loc' - e_loc, which needs one dot product per hit
         R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
 #if SCMC_SWEEP_PREFETCH
-        {
-            const int sn = s + gridDim.x * blockDim.x;
-            if (sn < nc) prefetch_site<R, NL, D>(M, rbase, ps, M.col_list[M.col_off[colour] + sn]);
+        if (sn < nc) {
+#pragma unroll
+            for (int v = 0; v < D / 2; v++) asm volatile("prefetch.global.L2 [%0];" ::"l"(M.psi + rbase + pn + v * ps));
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                if (k < M.z) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(M.T + rbase + jn[k] + q * ps));
+                }
         }
 #endif
         unsigned mine = 0;
+#if SCMC_ABLATE == 4
+        mine = (h[3] > R(1e30)) ? 1u : 0u;                    // ablation: no hits (keeps h alive)
+        for (int hit = 0; hit < 0; hit++) {
+#else
         for (int hit = 0; hit < A.hits; hit++) {
+#endif
             R xr[D], xi[D], u, dE;
             if (INJECT) {
                 const size_t t = ((size_t)hit * M.nrep + r) * M.N + site;
@@ -185,7 +228,11 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
             }
             mine += ok ? 1u : 0u;
         }
+#if SCMC_ABLATE == 1
+        if (mine > 1000u) {                                   // ablation: no write-back
+#else
         if (mine) {
+#endif
             store_psi<R, D>(M.psi + rbase + p, ps, re, im);
             store_T<R>(M.T + rbase + p, ps, T);
             if (ONSITE) store_T<R>(M.Tsq + rbase + p, ps, Tsq);
@@ -197,6 +244,138 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
     // acceptance counters: one atomic per warp (a block never spans two replicas)
     const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
     if ((threadIdx.x & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
+}
+
+// Software-pipelined variant of k_sweep_colour (FP32, one label, <= 6 neighbour slots): every thread walks over several site
+// visits of its replica; while the hits of visit t run, the neighbour T vectors and psi of visit t+1 are already in flight as
+// cp.async (LDGSTS) copies into a per-thread shared-memory slot -- no registers are held and the DRAM round trip disappears
+// behind ~1000 instructions of arithmetic.  Same arithmetic and order as k_sweep_colour => bit-identical chains.
+constexpr int ASYNC_Z = 6;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile(SCMC_ASYNC_CP " [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+template <int GEN, bool ONSITE>
+__global__ void __launch_bounds__(SCMC_ASYNC_THREADS, SCMC_ASYNC_BLOCKS) k_sweep_colour_async(const __grid_constant__ DevModel<float, 1> M, const SweepArgs A) {
+    using R = float;
+    constexpr int D = GenOps<GEN>::D, NPV = D / 2;
+    extern __shared__ __align__(16) float4 stage[];          // [z * 4 + NPV][blockDim.x]
+    __shared__ __align__(16) R sJt[NG * NG];
+    const int64_t r = A.r0 + blockIdx.y;
+    const int bd = blockDim.x, tid = threadIdx.x;
+    for (int t = tid; t < NG * NG; t += bd) sJt[t] = ((const R*)A.Jt)[t];
+    const bool alive = (A.active == nullptr || A.active[r]);
+    const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+    const R nbeta = neg_beta_scaled(beta);
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const int64_t rbase = r * M.Ns;
+    const float4* Tr = M.T + rbase;
+    const float4* Pr = M.psi + rbase;
+    const unsigned stride = (unsigned)M.N;
+    const int z = M.z;
+    __syncthreads();
+    unsigned nacc = 0;
+    for (int colour = A.colour; colour <= A.colour_last; colour++) {
+        const int nc = M.col_off[colour + 1] - M.col_off[colour];
+        const int32_t* clist = M.col_list + M.col_off[colour];
+        const int step = gridDim.x * bd;
+        int s = blockIdx.x * bd + tid;
+        // Pipeline: indices (colour list -> site -> neighbour slots) are fetched TWO visits ahead into registers, the T / psi
+        // data ONE visit ahead into shared memory, so the steady state never waits on a dependent round trip.
+        int p = 0, site = 0, pn = 0, site_n = 0;
+        unsigned jn[ASYNC_Z];
+#pragma unroll
+        for (int k = 0; k < ASYNC_Z; k++) jn[k] = 0u;
+        if (s < nc && alive) {       // prologue: stage visit 0, fetch the indices of visit 1
+            p = clist[s];
+            site = M.orig[p];
+#pragma unroll
+            for (int k = 0; k < ASYNC_Z; k++)
+                if (k < z) {
+                    const unsigned j = (unsigned)M.nbr[(unsigned)k * stride + p];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) cp_async16(&stage[(k * 4 + q) * bd + tid], Tr + j + q * ps);
+                }
+#pragma unroll
+            for (int v = 0; v < NPV; v++) cp_async16(&stage[(z * 4 + v) * bd + tid], Pr + p + v * ps);
+            if (s + step < nc) {
+                pn = clist[s + step];
+#pragma unroll
+                for (int k = 0; k < ASYNC_Z; k++) jn[k] = k < z ? (unsigned)M.nbr[(unsigned)k * stride + pn] : 0u;
+                site_n = M.orig[pn];
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (; s < nc && alive; s += step) {
+            const bool has_next = s + step < nc;
+            const bool has_next2 = s + 2 * step < nc;
+            // indices of visit t+2: issued now, consumed at the end of this visit
+            int pnn = 0, site_nn = 0;
+            unsigned jnn[ASYNC_Z];
+            if (has_next2) {
+                pnn = clist[s + 2 * step];
+#pragma unroll
+                for (int k = 0; k < ASYNC_Z; k++) jnn[k] = k < z ? (unsigned)M.nbr[(unsigned)k * stride + pnn] : 0u;
+                site_nn = M.orig[pnn];
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            R re[D], im[D], T[NG], Tsq[NG], h[NG];
+#pragma unroll
+            for (int v = 0; v < NPV; v++) {
+                const float4 q4 = stage[(z * 4 + v) * bd + tid];
+                re[2 * v] = q4.x; im[2 * v] = q4.y; re[2 * v + 1] = q4.z; im[2 * v + 1] = q4.w;
+            }
+            {
+                R S[1][NG];
+#pragma unroll
+                for (int a = 0; a < NG; a++) S[0][a] = R(0);
+#pragma unroll
+                for (int k = 0; k < ASYNC_Z; k++)
+                    if (k < z) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const float4 v4 = stage[(k * 4 + q) * bd + tid];
+                            S[0][4 * q] += v4.x; S[0][4 * q + 1] += v4.y; S[0][4 * q + 2] += v4.z; S[0][4 * q + 3] += v4.w;
+                        }
+                    }
+                // the slot is free again: launch the copies of the next visit (its indices arrived a visit ago)
+                if (has_next) {
+#pragma unroll
+                    for (int k = 0; k < ASYNC_Z; k++)
+                        if (k < z) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) cp_async16(&stage[(k * 4 + q) * bd + tid], Tr + jn[k] + q * ps);
+                        }
+#pragma unroll
+                    for (int v = 0; v < NPV; v++) cp_async16(&stage[(z * 4 + v) * bd + tid], Pr + pn + v * ps);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                field_from_sums_smem<1>(sJt, S, h);
+            }
+            GenOps<GEN>::expect(re, im, T);
+            if (ONSITE) GenOps<GEN>::expect_sq(re, im, Tsq);
+            R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
+            unsigned mine = 0;
+            for (int hit = 0; hit < A.hits; hit++) {
+                R xr[D], xi[D], u, dE;
+                stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+                mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+            }
+            if (mine) {
+                store_psi<R, D>(M.psi + rbase + p, ps, re, im);
+                store_T<R>(M.T + rbase + p, ps, T);
+                if (ONSITE) store_T<R>(M.Tsq + rbase + p, ps, Tsq);
+            }
+            nacc += mine;
+            p = pn; site = site_n;
+            pn = pnn; site_n = site_nn;
+#pragma unroll
+            for (int k = 0; k < ASYNC_Z; k++) jn[k] = jnn[k];
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (colour < A.colour_last) __syncthreads();
+    }
+    const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
+    if ((tid & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
 }
 
 // Energy + magnetisation of every replica; one CTA per replica; FP64 accumulation.
@@ -458,8 +637,22 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
             B.Jt = h->d_Jt;
             const unsigned tiles = grid_for(nc, SCMC_SWEEP_THREADS);
             const dim3 grid(A.colour_last > A.colour ? 1u : (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES, (unsigned)B.rcount);
-            if (A.inj_xi) k_sweep_colour<R, GEN, ONS, NL, true><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
-            else k_sweep_colour<R, GEN, ONS, NL, false><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+            if (A.inj_xi) {
+                k_sweep_colour<R, GEN, ONS, NL, true><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+            } else if constexpr (std::is_same<R, float>::value && NL == 1) {
+                if (h->z <= ASYNC_Z && h->async_pipeline) {
+                    // pipelined kernel: a block walks over SCMC_ASYNC_TILES visits per thread
+                    const size_t smem = (size_t)(h->z * 4 + GenOps<GEN>::D / 2) * SCMC_ASYNC_THREADS * sizeof(float4);
+                    SCMC_CK(cudaFuncSetAttribute(k_sweep_colour_async<GEN, ONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                    const unsigned tiles2 = grid_for(nc, SCMC_ASYNC_THREADS);
+                    const dim3 g2(A.colour_last > A.colour ? 1u : (tiles2 + SCMC_ASYNC_TILES - 1) / SCMC_ASYNC_TILES, (unsigned)B.rcount);
+                    k_sweep_colour_async<GEN, ONS><<<g2, SCMC_ASYNC_THREADS, smem, h->stream>>>(M, B);
+                } else {
+                    k_sweep_colour<R, GEN, ONS, NL, false><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+                }
+            } else {
+                k_sweep_colour<R, GEN, ONS, NL, false><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+            }
             h->launches++;
         }
         SCMC_CK(cudaGetLastError());
@@ -592,6 +785,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     scmc_handle* h = new scmc_handle();
     h->device = device; h->prec = precision; h->d = d; h->z = z_max; h->n_labels = n_labels; h->gen_id = gen_id;
     h->N = N; h->R = n_replicas; h->roff = replica_offset;
+    if (const char* e = getenv("SCMC_ASYNC")) h->async_pipeline = atoi(e);      // kernel experiments: 0 = direct-load streaming kernel
     h->Ns = (N + 1 + 7) / 8 * 8;          // site N of every replica is the all-zero padding site
     h->z = (z_max + 2) / 3 * 3;           // neighbour slots padded to a multiple of 3 (chunked loads)
     for (int l = 0; l < n_labels; l++) memcpy(h->J[l], J + (size_t)l * 256, sizeof(double) * 256);
