@@ -35,18 +35,27 @@ template <> struct GenOps<1> {
     template <class R> static __device__ __forceinline__ void expect(const R* re, const R* im, R* T) { gen::spin_expect_g1(re, im, T); }
     template <class R> static __device__ __forceinline__ void expect_sq(const R* re, const R* im, R* T) { gen::spin_expect_sq_g1(re, im, T); }
     template <class R, bool O> static __device__ __forceinline__ void hloc(const R* h, const R* K, R* Hr, R* Hi) { gen::hloc_g1<R, O>(h, K, Hr, Hi); }
+    static constexpr int NDENS = gen::NDENS_g1;
+    template <class R> static __device__ __forceinline__ void density_acc(const R* re, const R* im, R* P) { gen::density_acc_g1(re, im, P); }
+    template <class R> static __device__ __forceinline__ void expect_from_density(const R* P, R* T) { gen::expect_from_density_g1(P, T); }
 };
 template <> struct GenOps<2> {
     static constexpr int D = 6;
     template <class R> static __device__ __forceinline__ void expect(const R* re, const R* im, R* T) { gen::spin_expect_g2(re, im, T); }
     template <class R> static __device__ __forceinline__ void expect_sq(const R* re, const R* im, R* T) { gen::spin_expect_sq_g2(re, im, T); }
     template <class R, bool O> static __device__ __forceinline__ void hloc(const R* h, const R* K, R* Hr, R* Hi) { gen::hloc_g2<R, O>(h, K, Hr, Hi); }
+    static constexpr int NDENS = gen::NDENS_g2;
+    template <class R> static __device__ __forceinline__ void density_acc(const R* re, const R* im, R* P) { gen::density_acc_g2(re, im, P); }
+    template <class R> static __device__ __forceinline__ void expect_from_density(const R* P, R* T) { gen::expect_from_density_g2(P, T); }
 };
 template <> struct GenOps<3> {
     static constexpr int D = 4;
     template <class R> static __device__ __forceinline__ void expect(const R* re, const R* im, R* T) { gen::spin_expect_g3(re, im, T); }
     template <class R> static __device__ __forceinline__ void expect_sq(const R* re, const R* im, R* T) { gen::spin_expect_sq_g3(re, im, T); }
     template <class R, bool O> static __device__ __forceinline__ void hloc(const R* h, const R* K, R* Hr, R* Hi) { gen::hloc_g3<R, O>(h, K, Hr, Hi); }
+    static constexpr int NDENS = gen::NDENS_g3;
+    template <class R> static __device__ __forceinline__ void density_acc(const R* re, const R* im, R* P) { gen::density_acc_g3(re, im, P); }
+    template <class R> static __device__ __forceinline__ void expect_from_density(const R* P, R* T) { gen::expect_from_density_g3(P, T); }
 };
 
 // ------------------------------------------------------------------------------------------------ Philox4x32-10

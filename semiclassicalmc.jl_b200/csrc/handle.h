@@ -66,7 +66,9 @@ struct scmc_handle {
     double* obs = nullptr;                       // [R][SCMC_NOBS] scratch rows
     void* pinned = nullptr;                      // pinned host staging for the beta / sigma tables
     int64_t bytes = 0, launches = 0;
-    int32_t sweep_mode = 0;
+    int32_t sweep_mode = 0;                      // 0 auto, 1 streaming T-gather, 2 replica-resident, 3 streaming psi-gather
+    bool res_family_T = false;                   // reserved: force the T-gather arithmetic family in auto mode
+    bool T_stale = false;                        // psi-gather sweeps leave the T / Tsq planes behind; ensure_T() refreshes them on demand
     int32_t async_pipeline = 0;                  // streaming path: 1 = cp.async-pipelined kernel (measured slower on B200: issue-bound at 16 warps/SM, profiles/README.md)
     // replica-resident kernel plan (scmc_resident.cu): a cluster of `cs` CTAs keeps one replica in distributed shared memory
     struct {
@@ -85,6 +87,8 @@ int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma);
 int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active);
 int32_t launch_measure(scmc_handle* h, double* d_rows /* device [R][SCMC_NOBS] */);
 int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes);
+int32_t ensure_T(scmc_handle* h);      // recompute the cached T (Tsq) planes from psi if a psi-gather sweep left them stale
+bool uses_psi_gather(const scmc_handle* h);
 // implemented in scmc_resident.cu
 void plan_resident(scmc_handle* h, const std::vector<int>& owner_of_perm);
 int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active);

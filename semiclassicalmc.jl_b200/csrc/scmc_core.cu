@@ -246,6 +246,101 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
     if ((threadIdx.x & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
 }
 
+// psi-gather variant of the colour pass: neighbours contribute through their STATE (d/2 x 16 bytes) instead of the cached T vector
+// (64 bytes).  sum_j T_j = map(sum_j P_j) with P = conj(psi) psi^T, so the gather accumulates density-matrix entries with
+// FMAs and maps once per visit.  Nothing but psi is read or written: DRAM traffic per visit drops from ~272 B to ~150 B and
+// the T planes become a lazily refreshed cache (ensure_T).  Rounding differs from the T-gather kernels at the 1-ulp level.
+template <class R, int GEN, bool ONSITE>
+__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep_colour_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A) {
+    constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
+    const int64_t r = A.r0 + blockIdx.y;
+    __shared__ __align__(16) R sJt[NG * NG];
+    for (int t = threadIdx.x; t < NG * NG; t += blockDim.x) sJt[t] = ((const R*)A.Jt)[t];
+    const bool alive = (A.active == nullptr || A.active[r]);
+    const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+    const R nbeta = neg_beta_scaled(beta);
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const int64_t rbase = r * M.Ns;
+    unsigned long long Pq[NPV];               // opaque bases of the replica's psi planes (one mad.wide per gather load)
+#pragma unroll
+    for (int v = 0; v < NPV; v++) {
+        Pq[v] = (unsigned long long)(M.psi + rbase + v * ps);
+        asm volatile("" : "+l"(Pq[v]));
+    }
+    const unsigned stride = (unsigned)M.N;
+    __syncthreads();
+    unsigned nacc = 0;
+    for (int colour = A.colour; colour <= A.colour_last; colour++) {
+        const int nc = M.col_off[colour + 1] - M.col_off[colour];
+        for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nc && alive; s += gridDim.x * blockDim.x) {
+            const int p = M.col_list[M.col_off[colour] + s];
+            R re[D], im[D], T[NG], Tsq[NG], h[NG];
+            load_psi<R, D>(M.psi + rbase + p, ps, re, im);
+            const int site = M.orig[p];
+            {
+                R P[NP];
+#pragma unroll
+                for (int t = 0; t < NP; t++) P[t] = R(0);
+                const int32_t* nb = M.nbr + p;
+#pragma unroll 2
+                for (int k = 0; k < M.z; k += 3) {
+                    unsigned j[3];
+#pragma unroll
+                    for (int t = 0; t < 3; t++) j[t] = (unsigned)nb[(unsigned)(k + t) * stride];
+                    vec4<R> v[3][NPV];
+#pragma unroll
+                    for (int t = 0; t < 3; t++)
+#pragma unroll
+                        for (int q = 0; q < NPV; q++) v[t][q] = *reinterpret_cast<const vec4<R>*>(Pq[q] + (unsigned long long)j[t] * sizeof(vec4<R>));
+#pragma unroll
+                    for (int t = 0; t < 3; t++) {
+                        R nr[D], ni[D];
+#pragma unroll
+                        for (int q = 0; q < NPV; q++) { nr[2 * q] = v[t][q].x; ni[2 * q] = v[t][q].y; nr[2 * q + 1] = v[t][q].z; ni[2 * q + 1] = v[t][q].w; }
+                        GenOps<GEN>::density_acc(nr, ni, P);
+                    }
+                }
+                R S[1][NG];
+                GenOps<GEN>::expect_from_density(P, S[0]);
+                field_from_sums_smem<1>(sJt, S, h);
+            }
+            GenOps<GEN>::expect(re, im, T);
+            if (ONSITE) GenOps<GEN>::expect_sq(re, im, Tsq);
+            R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
+            unsigned mine = 0;
+            for (int hit = 0; hit < A.hits; hit++) {
+                R xr[D], xi[D], u, dE;
+                stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+                mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+            }
+            if (mine) store_psi<R, D>(M.psi + rbase + p, ps, re, im);
+            nacc += mine;
+        }
+        if (colour < A.colour_last) __syncthreads();
+    }
+    const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
+}
+
+// T (and Tsq) planes from psi for every site of every replica: refreshes the cache after psi-gather sweeps
+template <class R, int GEN, bool ONSITE, int NL>
+__global__ void __launch_bounds__(256) k_refresh_T(const __grid_constant__ DevModel<R, NL> M) {
+    constexpr int D = GenOps<GEN>::D;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M.nrep * M.N) return;
+    const int64_t r = idx / M.N;
+    const int p = (int)(idx - r * M.N);
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    R re[D], im[D], T[NG];
+    load_psi<R, D>(M.psi + r * M.Ns + p, ps, re, im);
+    GenOps<GEN>::expect(re, im, T);
+    store_T<R>(M.T + r * M.Ns + p, ps, T);
+    if (ONSITE) {
+        GenOps<GEN>::expect_sq(re, im, T);
+        store_T<R>(M.Tsq + r * M.Ns + p, ps, T);
+    }
+}
+
 // Software-pipelined variant of k_sweep_colour (FP32, one label, <= 6 neighbour slots): every thread walks over several site
 // visits of its replica; while the hits of visit t run, the neighbour T vectors and psi of visit t+1 are already in flight as
 // cp.async (LDGSTS) copies into a per-thread shared-memory slot -- no registers are held and the DRAM round trip disappears
@@ -622,7 +717,32 @@ int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma) 
     return SCMC_OK;
 }
 
+// Which arithmetic family the production (stream-driven) sweeps of this handle use.  It depends on the model only -- never on
+// the replica count or the number of sweeps per call -- so that a replica's chain is identical however replicas are sharded.
+bool uses_psi_gather(const scmc_handle* h) {
+    if (h->sweep_mode == 3) return h->n_labels == 1;
+    if (h->sweep_mode == 1 || h->sweep_mode == 2) return false;
+    return h->n_labels == 1 && h->d == 4 && !h->res_family_T;
+}
+
+int32_t ensure_T(scmc_handle* h) {
+    if (!h->T_stale) return SCMC_OK;
+    h->T_stale = false;
+    return dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+        constexpr bool ONS = decltype(ons)::value != 0;
+        auto M = make_model<R, NL>(h);
+        k_refresh_T<R, GEN, ONS, NL><<<grid_for(h->R * h->N), 256, 0, h->stream>>>(M);
+        h->launches++;
+        SCMC_CK(cudaGetLastError());
+        return SCMC_OK;
+    });
+}
+
 static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
+    const bool psi = !A.inj_xi && uses_psi_gather(h);
+    if (!psi) SCMC_TRY(ensure_T(h));
     return dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
@@ -639,6 +759,9 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
             const dim3 grid(A.colour_last > A.colour ? 1u : (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES, (unsigned)B.rcount);
             if (A.inj_xi) {
                 k_sweep_colour<R, GEN, ONS, NL, true><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+            } else if (psi) {
+                if constexpr (NL == 1) k_sweep_colour_psi<R, GEN, ONS><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+                h->T_stale = true;
             } else if constexpr (std::is_same<R, float>::value && NL == 1) {
                 if (h->z <= ASYNC_Z && h->async_pipeline) {
                     // pipelined kernel: a block walks over SCMC_ASYNC_TILES visits per thread
@@ -664,12 +787,12 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
 // n_sweeps when h->batch > 0); within a batch, sweeps x colours launches.
 int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active) {
     if (h->sweep_mode == 2 && !h->res.eligible) { set_error("resident sweep kernel requested but this lattice does not fit in cluster shared memory"); return SCMC_ERR_UNSUPPORTED; }
-    if (h->sweep_mode == 2) return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active);
-    if (h->sweep_mode == 0 && h->res.eligible) {
+    if (h->sweep_mode == 2) { SCMC_TRY(ensure_T(h)); return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active); }
+    if (h->sweep_mode == 0 && h->res.eligible && !uses_psi_gather(h)) {
         // measured on B200 (profiles/README.md): the resident kernel wins when colour passes are small (launch-bound) or many
         // sweeps run per call; the streaming kernel wins for one-replica-per-8-CTA lattices (C5) and single-sweep calls of big batches
         const int64_t work_per_pass = h->R * h->N / std::max(1, h->n_col);
-        if (h->res.cs <= 4 && (n_sweeps >= 4 || work_per_pass < 300000)) return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active);
+        if (h->res.cs <= 4 && (n_sweeps >= 4 || work_per_pass < 300000)) { SCMC_TRY(ensure_T(h)); return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active); }
     }
     const int64_t batch = h->batch > 0 ? std::min<int64_t>(h->batch, h->R) : h->R;
     for (int64_t r0 = 0; r0 < h->R; r0 += batch) {
@@ -693,6 +816,7 @@ int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t s
 }
 
 int32_t launch_measure(scmc_handle* h, double* d_rows) {
+    SCMC_TRY(ensure_T(h));
     return dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
@@ -937,7 +1061,7 @@ int32_t scmc_info(scmc_t* h, int64_t* info) {
 
 int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch) {
     SCMC_ARG(h, "null handle");
-    SCMC_ARG(mode >= 0 && mode <= 2 && batch >= 0, "scmc_set_sweep_mode: bad mode / batch");
+    SCMC_ARG(mode >= 0 && mode <= 3 && batch >= 0, "scmc_set_sweep_mode: bad mode / batch");
     h->sweep_mode = mode; h->batch = batch;
     return SCMC_OK;
 }
@@ -1007,6 +1131,7 @@ int32_t scmc_get_T(scmc_t* h, int64_t r, double* T, double* Tsq) {
     SCMC_ARG(h && T, "null argument");
     SCMC_ARG(r >= 0 && r < h->R, "replica out of range");
     SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(ensure_T(h));
     double *dT = nullptr, *dTsq = nullptr;
     const size_t bytes = (size_t)h->N * 16 * 8;
     SCMC_CK(cudaMalloc(&dT, bytes));
@@ -1034,6 +1159,7 @@ int32_t scmc_get_T(scmc_t* h, int64_t r, double* T, double* Tsq) {
 int32_t scmc_energy(scmc_t* h, double* E) {
     SCMC_ARG(h && E, "null argument");
     SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(ensure_T(h));
     double* dE = nullptr;
     SCMC_CK(cudaMalloc(&dE, h->R * 8));
     int32_t st = dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
@@ -1059,6 +1185,7 @@ int32_t scmc_local_field(scmc_t* h, int64_t r, double* out) {
     SCMC_ARG(h && out, "null argument");
     SCMC_ARG(r >= 0 && r < h->R, "replica out of range");
     SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(ensure_T(h));
     double* dH = nullptr;
     const size_t bytes = (size_t)h->N * 16 * 8;
     SCMC_CK(cudaMalloc(&dH, bytes));
@@ -1152,6 +1279,7 @@ int32_t scmc_update_deterministic(scmc_t* h, int64_t r, int64_t site, const doub
     SCMC_ARG(h && xi, "null argument");
     SCMC_ARG(r >= 0 && r < h->R && site >= 0 && site < h->N, "replica / site out of range");
     SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(ensure_T(h));
     double* dbuf = nullptr;
     SCMC_CK(cudaMalloc(&dbuf, (2 * h->d + 2) * 8));
     int32_t st = SCMC_OK;

@@ -395,6 +395,7 @@ int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results*
 int32_t scmc_optimize(scmc_t* h, int64_t n_sweeps, double* E) {
     SCMC_ARG(h && n_sweeps >= 0, "bad argument");
     SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(ensure_T(h));
     for (int64_t s = 0; s < n_sweeps; s++)
         for (int c = 0; c < h->n_col; c++) {
             SCMC_TRY(dispatch_d(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
@@ -419,6 +420,7 @@ int32_t scmc_structure_factor(scmc_t* h, const double* ks, const double* pos, in
     SCMC_ARG(h && ks && pos && Sak, "null argument");
     SCMC_ARG(nk >= 1 && dim >= 1 && dim <= 3 && n_rs > 0, "scmc_structure_factor: bad nk / dim / n_rs");
     SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(ensure_T(h));
     std::vector<double> ppos((size_t)h->N * dim);
     for (int64_t q = 0; q < h->N; q++)
         for (int x = 0; x < dim; x++) ppos[(size_t)q * dim + x] = pos[(size_t)h->orig[q] * dim + x];
@@ -447,6 +449,7 @@ int32_t scmc_correlations(scmc_t* h, int64_t r, const int32_t* project, int64_t 
     SCMC_ARG(h->N <= 46340, "scmc_correlations: N too large for the all-pairs reference algorithm");
     for (int64_t t = 0; t < h->N * h->N; t++) SCMC_ARG(project[t] >= 0 && project[t] < n_rs, "scmc_correlations: project index out of range");
     SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(ensure_T(h));
     DevBuf dproj, dperm, dC;
     SCMC_CK(dproj.alloc((size_t)h->N * h->N * 4)); SCMC_CK(dperm.alloc(h->N * 4)); SCMC_CK(dC.alloc((size_t)16 * n_rs * 8));
     SCMC_CK(cudaMemcpyAsync(dproj.p, project, (size_t)h->N * h->N * 4, cudaMemcpyHostToDevice, h->stream));

@@ -129,6 +129,55 @@ def _emit_hloc(fname, g, gsq):
     return out
 
 
+def _density_terms(g):
+    """(j, k, part) entries of P_jk = conj(psi_j) psi_k (j <= k) that any generator uses, in a fixed order."""
+    gre, gim = _quantise(g)
+    d = g.shape[1]
+    used = []
+    for j in range(d):
+        for k in range(j, d):
+            if j == k:
+                if np.any(gre[:, j, j] != 0):
+                    used.append((j, j, "r"))
+            else:
+                if np.any(gre[:, j, k] != 0):
+                    used.append((j, k, "r"))
+                if np.any(gim[:, j, k] != 0):
+                    used.append((j, k, "i"))
+    return used
+
+
+def _emit_density(fname_acc, fname_map, g):
+    """T^a is linear in the density matrix: sum_j T_j = map(sum_j P_j).  `acc` adds one site's P entries into an
+    accumulator with FMAs (no separate adds), `map` turns the accumulated entries into the 16-vector."""
+    gre, gim = _quantise(g)
+    d = g.shape[1]
+    terms = _density_terms(g)
+    idx = {t: n for n, t in enumerate(terms)}
+    acc = [f"template <class R> __device__ __forceinline__ void {fname_acc}(const R* re, const R* im, R* P) {{"]
+    for (j, k, part) in terms:
+        n = idx[(j, k, part)]
+        if part == "r":
+            acc.append(f"    P[{n}] = fma(re[{j}], re[{k}], P[{n}]); P[{n}] = fma(im[{j}], im[{k}], P[{n}]);")
+        else:
+            acc.append(f"    P[{n}] = fma(re[{j}], im[{k}], P[{n}]); P[{n}] = fma(-im[{j}], re[{k}], P[{n}]);")
+    acc.append("}")
+    mp = [f"template <class R> __device__ __forceinline__ void {fname_map}(const R* P, R* T) {{"]
+    for a in range(16):
+        expr = ""
+        for j in range(d):
+            if gre[a, j, j]:
+                expr += _term(gre[a, j, j], f"P[{idx[(j, j, 'r')]}]")
+            for k in range(j + 1, d):
+                if gre[a, j, k]:
+                    expr += _term(2 * gre[a, j, k], f"P[{idx[(j, k, 'r')]}]")
+                if gim[a, j, k]:
+                    expr += _term(-2 * gim[a, j, k], f"P[{idx[(j, k, 'i')]}]")
+        mp.append(f"    T[{a}] = R(0){expr};")
+    mp.append("}")
+    return acc + mp, len(terms)
+
+
 def emit_cuda_tables(path):
     """Write csrc/gen_code.h: unrolled expectation-value / local-Hamiltonian code and integer tables for n = 1, 2, 3."""
     lines = [
@@ -138,6 +187,7 @@ def emit_cuda_tables(path):
         "// spin_expect_*   : T^a   = <psi|G^a|psi>      (replaces the dense loop of src/Configuration.jl:166-194)",
         "// spin_expect_sq_*: Tsq^a = <psi|(G^a)^2|psi>  (generatorsSq, src/Configuration.jl:52,59)",
         "// hloc_*          : H_loc = sum_a h^a G^a + K^a (G^a)^2, upper triangle (for the on-device local optimiser)",
+        "// density_acc_* / expect_from_density_*: sum_j T_j = map(sum_j P_j), P = conj(psi) psi^T entries (psi-gather sweep kernel)",
         "#pragma once",
         "#include <cstdint>",
         "namespace scmc { namespace gen {",
@@ -147,6 +197,9 @@ def emit_cuda_tables(path):
         lines += _emit_expect(f"spin_expect_g{n}", g)
         lines += _emit_expect(f"spin_expect_sq_g{n}", q)
         lines += _emit_hloc(f"hloc_g{n}", g, q)
+        dens, nterms = _emit_density(f"density_acc_g{n}", f"expect_from_density_g{n}", g)
+        lines += dens
+        lines.append(f"constexpr int NDENS_g{n} = {nterms};   // density-matrix entries used by the generators at filling {n}")
         for name, arr in (("G", g), ("Gsq", q)):
             re_, im_ = _quantise(arr)
             for part, tab in (("re", re_), ("im", im_)):
