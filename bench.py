@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--hits", type=int, default=2)
     ap.add_argument("--precision", type=int, default=32)
     ap.add_argument("--coupling", default="notebook", choices=["notebook", "dense"])
-    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1 streaming, 2 resident")
+    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1/2 streaming/resident T-gather, 3/4 streaming/resident psi-gather")
     ap.add_argument("--batch", type=int, default=0, help="replicas per L2 batch (streaming path)")
     ap.add_argument("--colouring", default="auto", choices=["auto", "few", "balanced"], help="few = 3 large + seam classes, balanced = 2x2 parity (4 equal classes)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
@@ -275,8 +275,10 @@ def run_ours(args):
         d, w = cfg.d, args.precision // 8
         info = cfg.info()
         n_launch_local = max(1, launches // world)
-        uses_resident = info["resident"] and (args.mode == 2 or (args.mode == 0 and info["cluster"] <= 4 and (args.sweeps >= 4 or R * N / info["n_colours"] < 300000)))
-        kernel_name = f"replica-resident cluster({info['cluster']})" if uses_resident else "streaming colour-pass"
+        psi_family = args.mode in (3, 4) or (args.mode == 0 and cfg.d == 4)
+        small = 1 <= info["cluster"] <= 2 and (args.sweeps >= 4 or R * N / info["n_colours"] < 300000)
+        uses_resident = args.mode in (2, 4) or (args.mode == 0 and small and (info["resident_psi"] if psi_family else info["resident"]))
+        kernel_name = (f"replica-resident cluster({info['cluster']})" if uses_resident else "streaming colour-pass") + (", psi-gather" if psi_family else ", T-gather")
         # algorithmic bytes per kernel launch: state in + state out (4 d w bytes) of every site the launch visits
         sites_per_launch = R * N * args.sweeps * args.steps / n_launch_local
         alg_bytes = sites_per_launch * 4 * d * w
@@ -285,7 +287,7 @@ def run_ours(args):
         traffic = None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if not uses_resident and args.precision == 32 and args.L == 128:      # the configuration the ncu capture was taken on
+            if not uses_resident and psi_family and args.precision == 32 and args.L == 128:      # the configuration the ncu capture was taken on
                 traffic = prof["dram_bytes_per_site_visit"] * sites_per_launch
         except Exception:
             pass

@@ -56,7 +56,7 @@ int32_t scmc_create(scmc_t** h, int32_t device, int32_t precision /* 32 | 64 */,
 int32_t scmc_destroy(scmc_t* h);
 /* Use an existing CUDA stream (cudaStream_t as void*) for all launches/copies of this handle; NULL = legacy default stream. */
 int32_t scmc_set_stream(scmc_t* h, void* cuda_stream);
-/* info[0]=n_colours, [1]=generator table id (1,2,3), [2]=device bytes allocated, [3]=resident-kernel eligible (0/1),
+/* info[0]=n_colours, [1]=generator table id (1,2,3), [2]=device bytes allocated, [3]=resident-kernel eligibility bits (1: T-gather family, 2: psi-gather family),
  * [4]=cluster size of the resident kernel, [5]=kernel launches issued so far, [6]=n_sites, [7]=n_replicas */
 int32_t scmc_info(scmc_t* h, int64_t* info8);
 
@@ -90,8 +90,11 @@ int32_t scmc_sweep(scmc_t* h, int64_t n_sweeps, int32_t hits, const double* beta
                    uint64_t seed, uint64_t sweep_counter, int64_t* accepted, int64_t* attempted);
 /* Same, but betas/sigmas stay as last set and nothing is copied back (for graphs / async pipelines). */
 int32_t scmc_sweep_async(scmc_t* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter);
-/* kernel selection for scmc_sweep: 0 = auto, 1 = streaming colour-pass kernels, 2 = replica-resident cluster kernel;
- * batch = replicas per L2-resident batch for the streaming path (0 = all at once). */
+/* kernel selection for the stream-driven sweeps: 0 = auto; T-gather family (neighbours enter through the cached T vectors):
+ * 1 = streaming colour-pass kernel, 2 = replica-resident cluster kernel; psi-gather family (neighbours enter through their
+ * states via density-matrix sums, one coupling label only): 3 = streaming, 4 = replica-resident.  Kernels of one family produce
+ * bit-identical chains; the two families differ by rounding.  Auto picks the family from the model alone (never from the replica
+ * count), so sharding replicas over GPUs cannot change a chain.  batch = replicas per batch for the streaming path (0 = all). */
 int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch);
 
 /* ---- observables (measure!, ObservablesGeneric.jl:32-46; getMagnetization, Observables.jl:16-18) -------------------- */

@@ -1,5 +1,5 @@
-"""Times colour-ordered sweeps for the smaller BASELINE workloads (C1, C2, C4 shapes) with the streaming (mode 1) and the
-replica-resident (mode 2) kernels: python profiles/bench_small.py"""
+"""Times colour-ordered sweeps for the smaller BASELINE workloads (C1, C2, C4 shapes) with the streaming (modes 1, 3) and the
+replica-resident (modes 2, 4) kernels of both arithmetic families: python profiles/bench_small.py"""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
@@ -11,10 +11,11 @@ cases = [("C1 honeycomb 6x6", "honeycomb", 6, 1, 4096, [np.eye(16)]), ("C1 singl
          ("C2 tri 48x48 x64T", "triangular", 48, 1, 64, [J]), ("C4 tri 36x36 x512", "triangular", 36, 1, 512, [J]),
          ("C2 tri 48x48 x4096", "triangular", 48, 1, 4096, [J])]
 for name, lat, L, n, R, Js in cases:
-    for mode in (1, 2):
+    for mode in (1, 2, 3, 4):
         cfg = scmc.initializeCfg("nearest-neighbor", lat, Js, L, n, n_replicas=R, precision=32, seed=1)
         info = cfg.info()
-        if mode == 2 and not info["resident"]:
+        if (mode == 2 and not info["resident"]) or (mode == 4 and not info["resident_psi"]):
+            cfg.close()
             continue
         cfg.set_sweep_mode(mode)
         beta = np.full(R, 5.0); sigma = np.full(R, 0.2)

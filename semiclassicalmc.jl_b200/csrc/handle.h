@@ -66,14 +66,14 @@ struct scmc_handle {
     double* obs = nullptr;                       // [R][SCMC_NOBS] scratch rows
     void* pinned = nullptr;                      // pinned host staging for the beta / sigma tables
     int64_t bytes = 0, launches = 0;
-    int32_t sweep_mode = 0;                      // 0 auto, 1 streaming T-gather, 2 replica-resident, 3 streaming psi-gather
+    int32_t sweep_mode = 0;                      // 0 auto, 1 streaming T-gather, 2 resident T-gather, 3 streaming psi-gather, 4 resident psi-gather
     bool res_family_T = false;                   // reserved: force the T-gather arithmetic family in auto mode
     bool T_stale = false;                        // psi-gather sweeps leave the T / Tsq planes behind; ensure_T() refreshes them on demand
     int32_t async_pipeline = 0;                  // streaming path: 1 = cp.async-pipelined kernel (measured slower on B200: issue-bound at 16 warps/SM, profiles/README.md)
     // replica-resident kernel plan (scmc_resident.cu): a cluster of `cs` CTAs keeps one replica in distributed shared memory
     struct {
-        int eligible = 0, cs = 0, n_own_max = 0, cap = 0, nthreads = 0, max_clusters = 0;
-        size_t smem = 0;
+        int eligible = 0, eligible_psi = 0, cs = 0, n_own_max = 0, cap = 0, nthreads = 0, max_clusters = 0, max_clusters_psi = 0;
+        size_t smem = 0, smem_psi = 0;            // T-gather family (psi + T resident) / psi-gather family (psi only)
         int cta_off[17] = {0};                    // first permuted site of every CTA's chunk
         int cta_col_off[16][scmc::MAXC + 1] = {{0}};   // local offsets of the colour classes inside a chunk
     } res;
@@ -91,5 +91,5 @@ int32_t ensure_T(scmc_handle* h);      // recompute the cached T (Tsq) planes fr
 bool uses_psi_gather(const scmc_handle* h);
 // implemented in scmc_resident.cu
 void plan_resident(scmc_handle* h, const std::vector<int>& owner_of_perm);
-int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active);
+int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active, bool psi);
 }  // namespace scmc

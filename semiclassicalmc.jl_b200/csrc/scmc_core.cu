@@ -720,7 +720,7 @@ int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma) 
 // Which arithmetic family the production (stream-driven) sweeps of this handle use.  It depends on the model only -- never on
 // the replica count or the number of sweeps per call -- so that a replica's chain is identical however replicas are sharded.
 bool uses_psi_gather(const scmc_handle* h) {
-    if (h->sweep_mode == 3) return h->n_labels == 1;
+    if (h->sweep_mode == 3 || h->sweep_mode == 4) return h->n_labels == 1;
     if (h->sweep_mode == 1 || h->sweep_mode == 2) return false;
     return h->n_labels == 1 && h->d == 4 && !h->res_family_T;
 }
@@ -786,13 +786,23 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
 // Streaming path: replicas are processed in batches (sized to stay L2-resident across the colour passes of all
 // n_sweeps when h->batch > 0); within a batch, sweeps x colours launches.
 int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active) {
-    if (h->sweep_mode == 2 && !h->res.eligible) { set_error("resident sweep kernel requested but this lattice does not fit in cluster shared memory"); return SCMC_ERR_UNSUPPORTED; }
-    if (h->sweep_mode == 2) { SCMC_TRY(ensure_T(h)); return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active); }
-    if (h->sweep_mode == 0 && h->res.eligible && !uses_psi_gather(h)) {
-        // measured on B200 (profiles/README.md): the resident kernel wins when colour passes are small (launch-bound) or many
-        // sweeps run per call; the streaming kernel wins for one-replica-per-8-CTA lattices (C5) and single-sweep calls of big batches
+    if (h->sweep_mode == 2) {
+        if (!h->res.eligible) { set_error("resident T-gather kernel requested but this lattice does not fit in cluster shared memory"); return SCMC_ERR_UNSUPPORTED; }
+        SCMC_TRY(ensure_T(h));
+        return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active, false);
+    }
+    if (h->sweep_mode == 4) {
+        if (!h->res.eligible_psi) { set_error("resident psi-gather kernel requested but not available for this model / lattice"); return SCMC_ERR_UNSUPPORTED; }
+        return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active, true);
+    }
+    if (h->sweep_mode == 0) {
+        // Kernel choice inside one arithmetic family (measured on B200, profiles/README.md): the resident kernel wins when colour
+        // passes are small (launch-bound) or many sweeps run per call; the streaming kernel wins for big batches of large lattices.
+        const bool psi = uses_psi_gather(h);
         const int64_t work_per_pass = h->R * h->N / std::max(1, h->n_col);
-        if (h->res.cs <= 4 && (n_sweeps >= 4 || work_per_pass < 300000)) { SCMC_TRY(ensure_T(h)); return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active); }
+        const bool want_resident = h->res.cs >= 1 && h->res.cs <= 2 && (n_sweeps >= 4 || work_per_pass < 300000);
+        if (want_resident && psi && h->res.eligible_psi) return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active, true);
+        if (want_resident && !psi && h->res.eligible) { SCMC_TRY(ensure_T(h)); return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active, false); }
     }
     const int64_t batch = h->batch > 0 ? std::min<int64_t>(h->batch, h->R) : h->R;
     for (int64_t r0 = 0; r0 < h->R; r0 += batch) {
@@ -958,12 +968,14 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     std::vector<int32_t> col_list(N);
     {
         const size_t w = precision == 64 ? 8 : 4;
-        const size_t per_site = 16 * w * (4 + d / 2 + (h->onsite ? 4 : 0)) / 4 + 2 * (size_t)h->z + (n_labels > 1 ? (size_t)h->z : 0);
+        // footprint per site of the arithmetic family this model uses in auto mode (uses_psi_gather): psi only, or psi + T (+ Tsq)
+        const bool psi_family = n_labels == 1 && d == 4;
+        const size_t per_site = (psi_family ? 4 * w * (d / 2) : 4 * w * (4 + d / 2 + (h->onsite ? 4 : 0))) + 2 * (size_t)h->z + (n_labels > 1 ? (size_t)h->z : 0);
         int cs = 0;
         for (int c : {1, 2, 4, 8}) {
             const int64_t n_own = (N + c - 1) / c;
             const size_t cap = (size_t)(n_own + 1 + 7) / 8 * 8;
-            if (cap * per_site + (size_t)MAXL * 256 * w + 1024 <= (size_t)226 * 1024 && n_own + 1 <= 4096 && N >= c) { cs = c; break; }
+            if (cap * per_site + (size_t)MAXL * 256 * w + 1024 <= (size_t)226 * 1024 && n_own + 1 <= 8191 && N >= c) { cs = c; break; }
         }
         const int64_t n_nom = cs ? (N + cs - 1) / cs : N;
         int32_t at = 0;
@@ -1055,13 +1067,13 @@ int32_t scmc_set_stream(scmc_t* h, void* s) {
 
 int32_t scmc_info(scmc_t* h, int64_t* info) {
     SCMC_ARG(h && info, "null argument");
-    info[0] = h->n_col; info[1] = h->gen_id; info[2] = h->bytes; info[3] = h->res.eligible; info[4] = h->res.cs; info[5] = h->launches; info[6] = h->N; info[7] = h->R;
+    info[0] = h->n_col; info[1] = h->gen_id; info[2] = h->bytes; info[3] = h->res.eligible | (h->res.eligible_psi << 1); info[4] = h->res.cs; info[5] = h->launches; info[6] = h->N; info[7] = h->R;
     return SCMC_OK;
 }
 
 int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch) {
     SCMC_ARG(h, "null handle");
-    SCMC_ARG(mode >= 0 && mode <= 3 && batch >= 0, "scmc_set_sweep_mode: bad mode / batch");
+    SCMC_ARG(mode >= 0 && mode <= 4 && batch >= 0, "scmc_set_sweep_mode: bad mode / batch");
     h->sweep_mode = mode; h->batch = batch;
     return SCMC_OK;
 }

@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
                         for (int k = 0; k < M.z; k++) {
                             const unsigned code = sNbr[k * nmax + q];
                             const int l = NL == 1 ? 0 : sLab[k * nmax + q];
-                            uint32_t addr = sT_u32 + (code & 0xFFFu) * (uint32_t)sizeof(V);
-                            if (CLUSTER) addr = map_to_rank(addr, code >> 12);
+                            uint32_t addr = sT_u32 + (code & 0x1FFFu) * (uint32_t)sizeof(V);
+                            if (CLUSTER) addr = map_to_rank(addr, code >> 13);
                             V v[4];
 #pragma unroll
                             for (int p4 = 0; p4 < 4; p4++) v[p4] = ld_v4<CLUSTER>(addr + p4 * plane_bytes, R(0));
@@ -195,6 +195,107 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
     }
 }
 
+// psi-gather family (same arithmetic as k_sweep_colour_psi, bit-identical chains): only psi lives in shared memory
+// (d/2 x 16 B per site instead of psi + T), neighbours are read as states through DSMEM and enter through density-matrix sums.
+// C5 (128 x 128, FP32): 16384 x (32 + 12) B = 704 KB -> cluster of 4 CTAs x 177 KB, all 148 SMs busy.
+template <class R, int GEN, bool ONSITE, bool CLUSTER>
+__global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__ DevModel<R, 1> M, const __grid_constant__ ResidentArgs A) {
+    constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
+    using V = vec4<R>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cap = A.cap, nmax = A.n_own_max;
+    V* sPsi = reinterpret_cast<V*>(smem_raw);                     // [NPV][cap]
+    R* sJt = reinterpret_cast<R*>(sPsi + NPV * cap);              // [16][16]
+    uint16_t* sNbr = reinterpret_cast<uint16_t*>(sJt + NG * NG);  // [z][nmax]
+    __shared__ unsigned s_acc;
+    unsigned rank = 0, cluster_id = blockIdx.x;
+    if (CLUSTER) {
+        rank = cg::this_cluster().block_rank();
+        cluster_id = blockIdx.x / A.cs;
+    }
+    const int my_off = A.cta_off[rank];
+    const int n_own = A.cta_off[rank + 1] - my_off;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int t = tid; t < NG * NG; t += nth) sJt[t] = ((const R*)A.Jt)[t];
+    for (int k = 0; k < M.z; k++)
+        for (int q = tid; q < n_own; q += nth) sNbr[k * nmax + q] = A.nbr16[(size_t)k * M.N + my_off + q];
+    if (tid < NPV) sPsi[tid * cap + nmax] = make_v4<R>(R(0), R(0), R(0), R(0));     // all-zero padding slot
+    if (tid == 0) s_acc = 0;
+    __syncthreads();
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const uint32_t sPsi_u32 = smem_u32(sPsi);
+    const uint32_t plane_bytes = (uint32_t)cap * (uint32_t)sizeof(V);
+    for (int64_t r = cluster_id; r < A.nrep; r += A.n_clusters) {
+        if (A.active != nullptr && !A.active[r]) continue;
+        const int64_t gbase = r * M.Ns + my_off;
+        for (int q = tid; q < n_own; q += nth) {
+#pragma unroll
+            for (int v = 0; v < NPV; v++) sPsi[v * cap + q] = M.psi[gbase + q + v * ps];
+        }
+        const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+        const R nbeta = neg_beta_scaled(beta);
+        if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
+        unsigned nacc = 0;
+        for (int sweep = 0; sweep < A.n_sweeps; sweep++) {
+            const uint64_t visit_base = A.visit0 + (uint64_t)sweep * (uint64_t)A.hits;
+            for (int c = 0; c < M.n_col; c++) {
+                const int c0 = A.cta_col_off[rank][c], cnt = A.cta_col_off[rank][c + 1] - c0;
+                for (int s = tid; s < cnt; s += nth) {
+                    const int q = c0 + s;
+                    R re[D], im[D], T[NG], Tsq[NG], h[NG];
+                    load_psi<R, D>(sPsi + q, (size_t)cap, re, im);
+                    const int site = M.orig[my_off + q];
+                    {
+                        R P[NP];
+#pragma unroll
+                        for (int t = 0; t < NP; t++) P[t] = R(0);
+#pragma unroll 3
+                        for (int k = 0; k < M.z; k++) {
+                            const unsigned code = sNbr[k * nmax + q];
+                            uint32_t addr = sPsi_u32 + (code & 0x1FFFu) * (uint32_t)sizeof(V);
+                            if (CLUSTER) addr = map_to_rank(addr, code >> 13);
+                            R nr[D], ni[D];
+#pragma unroll
+                            for (int v = 0; v < NPV; v++) {
+                                const V w4 = ld_v4<CLUSTER>(addr + v * plane_bytes, R(0));
+                                nr[2 * v] = w4.x; ni[2 * v] = w4.y; nr[2 * v + 1] = w4.z; ni[2 * v + 1] = w4.w;
+                            }
+                            GenOps<GEN>::density_acc(nr, ni, P);
+                        }
+                        R S[1][NG];
+                        GenOps<GEN>::expect_from_density(P, S[0]);
+                        field_from_sums_smem<1>(sJt, S, h);
+                    }
+                    GenOps<GEN>::expect(re, im, T);
+                    if (ONSITE) GenOps<GEN>::expect_sq(re, im, Tsq);
+                    R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
+                    unsigned mine = 0;
+                    for (int hit = 0; hit < A.hits; hit++) {
+                        R xr[D], xi[D], u, dE;
+                        stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
+                        mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+                    }
+                    if (mine) store_psi<R, D>(sPsi + q, (size_t)cap, re, im);
+                    nacc += mine;
+                }
+                if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
+            }
+        }
+        for (int q = tid; q < n_own; q += nth) {
+#pragma unroll
+            for (int v = 0; v < NPV; v++) M.psi[gbase + q + v * ps] = sPsi[v * cap + q];
+        }
+        const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
+        if ((tid & 31) == 0 && tot) atomicAdd(&s_acc, tot);
+        __syncthreads();
+        if (tid == 0) {
+            if (s_acc) atomicAdd(A.acc + r, (unsigned long long)s_acc);
+            s_acc = 0;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 template <int V> using ic = std::integral_constant<int, V>;
 template <class R, int NL>
@@ -228,13 +329,14 @@ static int32_t dispatch_r(const scmc_handle* h, F&& f) {
 }
 
 template <class K>
-static int32_t configure_and_count(K kernel, scmc_handle* h, int* max_clusters) {
+static int32_t configure_and_count(K kernel, scmc_handle* h, size_t smem, int* max_clusters) {
     auto& P = h->res;
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem) != cudaSuccess) { cudaGetLastError(); return SCMC_ERR_UNSUPPORTED; }
+    if (smem > (size_t)227 * 1024) return SCMC_ERR_UNSUPPORTED;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return SCMC_ERR_UNSUPPORTED; }
     int n = 0;
     if (P.cs > 1) {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(P.cs * 148); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem;
+        cfg.gridDim = dim3(P.cs * 148); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = smem;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = P.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -242,7 +344,7 @@ static int32_t configure_and_count(K kernel, scmc_handle* h, int* max_clusters) 
         if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return SCMC_ERR_UNSUPPORTED; }
     } else {
         int per_sm = 0, dev = 0, sms = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, P.nthreads, P.smem) != cudaSuccess) { cudaGetLastError(); return SCMC_ERR_UNSUPPORTED; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, P.nthreads, smem) != cudaSuccess) { cudaGetLastError(); return SCMC_ERR_UNSUPPORTED; }
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         n = per_sm * sms;
@@ -283,34 +385,45 @@ void plan_resident(scmc_handle* h, const std::vector<int>& owner_of_perm) {
     P.smem = (size_t)P.cap * 4 * w * (4 + h->d / 2 + (h->onsite ? 4 : 0)) + (size_t)MAXL * 256 * w + (size_t)h->z * P.n_own_max * 2 +
              (h->n_labels > 1 ? (size_t)h->z * P.n_own_max : 0) + 64;
     P.smem = (P.smem + 15) / 16 * 16;
-    // neighbour codes in permuted order: owner CTA << 12 | local index; padding slots -> my own zero slot (local index n_own_max)
+    P.smem_psi = (size_t)P.cap * 4 * w * (h->d / 2) + (size_t)256 * w + (size_t)h->z * P.n_own_max * 2 + 64;
+    P.smem_psi = (P.smem_psi + 15) / 16 * 16;
+    // neighbour codes in permuted order: owner CTA << 13 | local index; padding slots -> my own zero slot (local index n_own_max)
     std::vector<uint16_t> code((size_t)h->z * N);
     std::vector<int32_t> nb((size_t)h->z * N);
     if (cudaMemcpy(nb.data(), h->nbr, nb.size() * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return; }
     for (int k = 0; k < h->z; k++)
         for (int64_t q = 0; q < N; q++) {
             const int32_t j = nb[(size_t)k * N + q];
-            if (j >= N) code[(size_t)k * N + q] = (uint16_t)((owner_of_perm[q] << 12) | P.n_own_max);
-            else code[(size_t)k * N + q] = (uint16_t)((owner_of_perm[j] << 12) | (j - P.cta_off[owner_of_perm[j]]));
+            if (j >= N) code[(size_t)k * N + q] = (uint16_t)((owner_of_perm[q] << 13) | P.n_own_max);
+            else code[(size_t)k * N + q] = (uint16_t)((owner_of_perm[j] << 13) | (j - P.cta_off[owner_of_perm[j]]));
         }
     if (dev_alloc(h, (void**)&h->d_nbr16, code.size() * sizeof(uint16_t)) != SCMC_OK) return;
     if (cudaMemcpy(h->d_nbr16, code.data(), code.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); return; }
-    int maxc = 0;
+    int maxc = 0, maxc_psi = 0;
     const int32_t st = dispatch_r(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
         constexpr bool ONS = decltype(ons)::value != 0;
-        if (cs > 1) return configure_and_count(k_resident<R, GEN, ONS, NL, true>, h, &maxc);
-        return configure_and_count(k_resident<R, GEN, ONS, NL, false>, h, &maxc);
+        if (cs > 1) return configure_and_count(k_resident<R, GEN, ONS, NL, true>, h, P.smem, &maxc);
+        return configure_and_count(k_resident<R, GEN, ONS, NL, false>, h, P.smem, &maxc);
     });
-    if (st != SCMC_OK) return;
-    P.max_clusters = maxc;
-    P.eligible = 1;
+    if (st == SCMC_OK) { P.max_clusters = maxc; P.eligible = 1; }
+    if (h->n_labels == 1) {
+        const int32_t st2 = dispatch_r(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+            using R = decltype(rt);
+            constexpr int GEN = decltype(gen)::value;
+            constexpr bool ONS = decltype(ons)::value != 0;
+            if (cs > 1) return configure_and_count(k_resident_psi<R, GEN, ONS, true>, h, P.smem_psi, &maxc_psi);
+            return configure_and_count(k_resident_psi<R, GEN, ONS, false>, h, P.smem_psi, &maxc_psi);
+        });
+        if (st2 == SCMC_OK) { P.max_clusters_psi = maxc_psi; P.eligible_psi = 1; }
+    }
 }
 
-int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active) {
+int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active, bool psi) {
     auto& P = h->res;
     if (n_sweeps <= 0) return SCMC_OK;
+    if (psi) h->T_stale = true;
     return dispatch_r(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
@@ -322,23 +435,26 @@ int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t
         A.seed = seed; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.active = active; A.acc = h->acc; A.nbr16 = h->d_nbr16;
         memcpy(A.cta_off, P.cta_off, sizeof A.cta_off);
         memcpy(A.cta_col_off, P.cta_col_off, sizeof A.cta_col_off);
-        A.n_clusters = (int32_t)std::min<int64_t>(h->R, P.max_clusters);
+        A.n_clusters = (int32_t)std::min<int64_t>(h->R, psi ? P.max_clusters_psi : P.max_clusters);
+        const size_t smem = psi ? P.smem_psi : P.smem;
         // sweeps per launch bounded so that visit numbers stay in int32 loop counters and launches stay preemptible
         for (int64_t done = 0; done < n_sweeps;) {
             const int64_t chunk = std::min<int64_t>(n_sweeps - done, 4096);
             A.n_sweeps = (int32_t)chunk;
             A.visit0 = (sweep_counter + (uint64_t)done) * (uint64_t)hits;
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)(A.n_clusters * P.cs)); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem; cfg.stream = h->stream;
+            cfg.gridDim = dim3((unsigned)(A.n_clusters * P.cs)); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
             cudaLaunchAttribute at[1];
             cfg.attrs = at; cfg.numAttrs = 0;
             if (P.cs > 1) {
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = P.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                 cfg.numAttrs = 1;
-                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident<R, GEN, ONS, NL, true>, M, A));
+                if (psi) { if constexpr (NL == 1) SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, true>, M, A)); }
+                else SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident<R, GEN, ONS, NL, true>, M, A));
             } else {
-                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident<R, GEN, ONS, NL, false>, M, A));
+                if (psi) { if constexpr (NL == 1) SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, false>, M, A)); }
+                else SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident<R, GEN, ONS, NL, false>, M, A));
             }
             h->launches++;
             done += chunk;
