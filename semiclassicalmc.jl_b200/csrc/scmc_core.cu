@@ -63,7 +63,7 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #define SCMC_SWEEP_PREFETCH 0  // measured on B200: L2 prefetch of the next tile costs more issue slots than it hides (2.57e10 vs 2.90e10 upd/s)
 #endif
 #ifndef SCMC_SWEEP_TILES
-#define SCMC_SWEEP_TILES 4      // site tiles (of SCMC_SWEEP_THREADS sites) a block walks over
+#define SCMC_SWEEP_TILES 16     // site tiles (of SCMC_SWEEP_THREADS sites) a block walks over
 #endif
 struct SweepArgs {
     int32_t colour, colour_last, hits;   // classes [colour, colour_last] are visited in order by ONE block per replica when colour_last > colour
@@ -83,6 +83,12 @@ struct SweepArgs {
 // S_l = sum of T_j over the neighbours with label l.  The neighbour table is padded to a multiple of 3 slots; padding slots
 // (and missing bonds) point at site N, whose T planes are identically zero, so the loop is branch-free and every chunk
 // issues 3 index loads followed by 12 independent 128-bit loads (memory-level parallelism instead of 2 serial latencies per bond).
+// cp.async (LDGSTS) staging used by the software-pipelined kernels
+constexpr int ASYNC_Z = 6;
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile(SCMC_ASYNC_CP " [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
 template <class R, int NL>
 __device__ __forceinline__ void neighbour_sums(const DevModel<R, NL>& M, int64_t rbase, size_t ps, int p, R (*S)[NG]) {
 #pragma unroll
@@ -322,6 +328,129 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
     if ((threadIdx.x & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
 }
 
+// cp.async-pipelined form of k_sweep_colour_psi (FP32): the next visit's neighbour states and own state are staged in shared
+// memory (14 x 16 B per thread for d = 4, z = 6 -> 28 KB per CTA, 5 CTAs/SM), indices two visits ahead in registers.
+template <int GEN, bool ONSITE>
+__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep_colour_psi_async(const __grid_constant__ DevModel<float, 1> M, const SweepArgs A) {
+    using R = float;
+    constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
+    extern __shared__ __align__(16) float4 stage[];          // [(z + 1) * NPV][blockDim.x]
+    __shared__ __align__(16) R sJt[NG * NG];
+    const int64_t r = A.r0 + blockIdx.y;
+    const int bd = blockDim.x, tid = threadIdx.x;
+    for (int t = tid; t < NG * NG; t += bd) sJt[t] = ((const R*)A.Jt)[t];
+    const bool alive = (A.active == nullptr || A.active[r]);
+    const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+    const R nbeta = neg_beta_scaled(beta);
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const int64_t rbase = r * M.Ns;
+    const float4* Pr = M.psi + rbase;
+    const unsigned stride = (unsigned)M.N;
+    const int z = M.z;
+    __syncthreads();
+    unsigned nacc = 0;
+    for (int colour = A.colour; colour <= A.colour_last; colour++) {
+        const int nc = M.col_off[colour + 1] - M.col_off[colour];
+        const int32_t* clist = M.col_list + M.col_off[colour];
+        const int step = gridDim.x * bd;
+        int s = blockIdx.x * bd + tid;
+        int p = 0, site = 0, pn = 0, site_n = 0;
+        unsigned jn[ASYNC_Z];
+#pragma unroll
+        for (int k = 0; k < ASYNC_Z; k++) jn[k] = 0u;
+        if (s < nc && alive) {
+            p = clist[s];
+            site = M.orig[p];
+#pragma unroll
+            for (int k = 0; k < ASYNC_Z; k++)
+                if (k < z) {
+                    const unsigned j = (unsigned)M.nbr[(unsigned)k * stride + p];
+#pragma unroll
+                    for (int q = 0; q < NPV; q++) cp_async16(&stage[(k * NPV + q) * bd + tid], Pr + j + q * ps);
+                }
+#pragma unroll
+            for (int v = 0; v < NPV; v++) cp_async16(&stage[(z * NPV + v) * bd + tid], Pr + p + v * ps);
+            if (s + step < nc) {
+                pn = clist[s + step];
+#pragma unroll
+                for (int k = 0; k < ASYNC_Z; k++) jn[k] = k < z ? (unsigned)M.nbr[(unsigned)k * stride + pn] : 0u;
+                site_n = M.orig[pn];
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        for (; s < nc && alive; s += step) {
+            const bool has_next = s + step < nc;
+            const bool has_next2 = s + 2 * step < nc;
+            int pnn = 0, site_nn = 0;
+            unsigned jnn[ASYNC_Z];
+#pragma unroll
+            for (int k = 0; k < ASYNC_Z; k++) jnn[k] = 0u;
+            if (has_next2) {
+                pnn = clist[s + 2 * step];
+#pragma unroll
+                for (int k = 0; k < ASYNC_Z; k++) jnn[k] = k < z ? (unsigned)M.nbr[(unsigned)k * stride + pnn] : 0u;
+                site_nn = M.orig[pnn];
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            R re[D], im[D], T[NG], Tsq[NG], h[NG];
+#pragma unroll
+            for (int v = 0; v < NPV; v++) {
+                const float4 q4 = stage[(z * NPV + v) * bd + tid];
+                re[2 * v] = q4.x; im[2 * v] = q4.y; re[2 * v + 1] = q4.z; im[2 * v + 1] = q4.w;
+            }
+            {
+                R P[NP];
+#pragma unroll
+                for (int t = 0; t < NP; t++) P[t] = R(0);
+#pragma unroll
+                for (int k = 0; k < ASYNC_Z; k++)
+                    if (k < z) {
+                        R nr[D], ni[D];
+#pragma unroll
+                        for (int q = 0; q < NPV; q++) {
+                            const float4 w4 = stage[(k * NPV + q) * bd + tid];
+                            nr[2 * q] = w4.x; ni[2 * q] = w4.y; nr[2 * q + 1] = w4.z; ni[2 * q + 1] = w4.w;
+                        }
+                        GenOps<GEN>::density_acc(nr, ni, P);
+                    }
+                if (has_next) {
+#pragma unroll
+                    for (int k = 0; k < ASYNC_Z; k++)
+                        if (k < z) {
+#pragma unroll
+                            for (int q = 0; q < NPV; q++) cp_async16(&stage[(k * NPV + q) * bd + tid], Pr + jn[k] + q * ps);
+                        }
+#pragma unroll
+                    for (int v = 0; v < NPV; v++) cp_async16(&stage[(z * NPV + v) * bd + tid], Pr + pn + v * ps);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                R S[1][NG];
+                GenOps<GEN>::expect_from_density(P, S[0]);
+                field_from_sums_smem<1>(sJt, S, h);
+            }
+            GenOps<GEN>::expect(re, im, T);
+            if (ONSITE) GenOps<GEN>::expect_sq(re, im, Tsq);
+            R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
+            unsigned mine = 0;
+            for (int hit = 0; hit < A.hits; hit++) {
+                R xr[D], xi[D], u, dE;
+                stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+                mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+            }
+            if (mine) store_psi<R, D>(M.psi + rbase + p, ps, re, im);
+            nacc += mine;
+            p = pn; site = site_n;
+            pn = pnn; site_n = site_nn;
+#pragma unroll
+            for (int k = 0; k < ASYNC_Z; k++) jn[k] = jnn[k];
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (colour < A.colour_last) __syncthreads();
+    }
+    const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
+    if ((tid & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
+}
+
 // T (and Tsq) planes from psi for every site of every replica: refreshes the cache after psi-gather sweeps
 template <class R, int GEN, bool ONSITE, int NL>
 __global__ void __launch_bounds__(256) k_refresh_T(const __grid_constant__ DevModel<R, NL> M) {
@@ -345,10 +474,6 @@ __global__ void __launch_bounds__(256) k_refresh_T(const __grid_constant__ DevMo
 // visits of its replica; while the hits of visit t run, the neighbour T vectors and psi of visit t+1 are already in flight as
 // cp.async (LDGSTS) copies into a per-thread shared-memory slot -- no registers are held and the DRAM round trip disappears
 // behind ~1000 instructions of arithmetic.  Same arithmetic and order as k_sweep_colour => bit-identical chains.
-constexpr int ASYNC_Z = 6;
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    asm volatile(SCMC_ASYNC_CP " [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
 template <int GEN, bool ONSITE>
 __global__ void __launch_bounds__(SCMC_ASYNC_THREADS, SCMC_ASYNC_BLOCKS) k_sweep_colour_async(const __grid_constant__ DevModel<float, 1> M, const SweepArgs A) {
     using R = float;
@@ -760,7 +885,18 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
             if (A.inj_xi) {
                 k_sweep_colour<R, GEN, ONS, NL, true><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
             } else if (psi) {
-                if constexpr (NL == 1) k_sweep_colour_psi<R, GEN, ONS><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+                if constexpr (NL == 1) {
+                    bool launched = false;
+                    if constexpr (std::is_same<R, float>::value) {
+                        if (h->z <= ASYNC_Z && h->async_pipeline) {
+                            const size_t smem = (size_t)(h->z + 1) * (GenOps<GEN>::D / 2) * SCMC_SWEEP_THREADS * sizeof(float4);
+                            SCMC_CK(cudaFuncSetAttribute(k_sweep_colour_psi_async<GEN, ONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                            k_sweep_colour_psi_async<GEN, ONS><<<grid, SCMC_SWEEP_THREADS, smem, h->stream>>>(M, B);
+                            launched = true;
+                        }
+                    }
+                    if (!launched) k_sweep_colour_psi<R, GEN, ONS><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+                }
                 h->T_stale = true;
             } else if constexpr (std::is_same<R, float>::value && NL == 1) {
                 if (h->z <= ASYNC_Z && h->async_pipeline) {
