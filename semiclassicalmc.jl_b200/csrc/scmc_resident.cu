@@ -266,14 +266,25 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                         GenOps<GEN>::expect_from_density(P, S[0]);
                         field_from_sums_smem<1>(sJt, S, h);
                     }
-                    GenOps<GEN>::expect(re, im, T);
-                    if (ONSITE) GenOps<GEN>::expect_sq(re, im, Tsq);
-                    R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
                     unsigned mine = 0;
-                    for (int hit = 0; hit < A.hits; hit++) {
-                        R xr[D], xi[D], u, dE;
-                        stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
-                        mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+                    if (ONSITE) {
+                        GenOps<GEN>::expect(re, im, T);
+                        GenOps<GEN>::expect_sq(re, im, Tsq);
+                        R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
+                        for (int hit = 0; hit < A.hits; hit++) {
+                            R xr[D], xi[D], u, dE;
+                            stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
+                            mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+                        }
+                    } else {
+                        R Hq[GenOps<GEN>::NDENS];
+                        GenOps<GEN>::hq_from_field(h, Hq);
+                        R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
+                        for (int hit = 0; hit < A.hits; hit++) {
+                            R xr[D], xi[D], u, dE;
+                            stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
+                            mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+                        }
                     }
                     if (mine) store_psi<R, D>(sPsi + q, (size_t)cap, re, im);
                     nacc += mine;

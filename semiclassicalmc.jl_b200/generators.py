@@ -175,7 +175,29 @@ def _emit_density(fname_acc, fname_map, g):
                     expr += _term(-2 * gim[a, j, k], f"P[{idx[(j, k, 'i')]}]")
         mp.append(f"    T[{a}] = R(0){expr};")
     mp.append("}")
-    return acc + mp, len(terms)
+    # transpose of the map: e = sum_a h^a T^a = sum_n Hq[n] P[n],  Hq[n] = sum_a C[a][n] h[a]
+    col = [""] * len(terms)
+    for a in range(16):
+        for j in range(d):
+            if gre[a, j, j]:
+                col[idx[(j, j, "r")]] += _term(gre[a, j, j], f"h[{a}]")
+            for k in range(j + 1, d):
+                if gre[a, j, k]:
+                    col[idx[(j, k, "r")]] += _term(2 * gre[a, j, k], f"h[{a}]")
+                if gim[a, j, k]:
+                    col[idx[(j, k, "i")]] += _term(-2 * gim[a, j, k], f"h[{a}]")
+    tr = [f"template <class R> __device__ __forceinline__ void {fname_map.replace('expect_from_density', 'hq_from_field')}(const R* h, R* Hq) {{"]
+    tr += [f"    Hq[{n}] = R(0){c};" for n, c in enumerate(col)] + ["}"]
+    # e(psi) = sum_n Hq[n] P_n(psi) without materialising T
+    en = [f"template <class R> __device__ __forceinline__ R {fname_map.replace('expect_from_density', 'energy_from_state')}(const R* re, const R* im, const R* Hq) {{", "    R e = R(0);"]
+    for (j, k, part) in terms:
+        n = idx[(j, k, part)]
+        if part == "r":
+            en.append(f"    e = fma(Hq[{n}], fma(re[{j}], re[{k}], im[{j}] * im[{k}]), e);")
+        else:
+            en.append(f"    e = fma(Hq[{n}], fma(re[{j}], im[{k}], -(im[{j}] * re[{k}])), e);")
+    en += ["    return e;", "}"]
+    return acc + mp + tr + en, len(terms)
 
 
 def emit_cuda_tables(path):
