@@ -61,6 +61,8 @@ struct scmc_handle {
     int8_t* lab = nullptr;
     void *beta = nullptr, *sigma = nullptr;      // [R] reals of the handle's precision
     void* d_Jt = nullptr;                        // [MAXL][16][16] transposed couplings (kernel stages them into shared memory)
+    void* d_Jqt = nullptr;                       // [16][16] transposed couplings in the density basis, Jq = C^T J C (psi family, 16 density entries)
+    bool fused_density = false;                  // psi kernels go straight from density sums to energy coefficients (d_Jqt valid)
     unsigned long long* acc = nullptr;           // [R] accepted-update counters
     uint8_t* active = nullptr;                   // [R] replica still running (annealing) -- nullptr semantics handled by callers
     double* obs = nullptr;                       // [R][SCMC_NOBS] scratch rows

@@ -71,6 +71,7 @@ struct SweepArgs {
     uint64_t visit0, seed;     // visit number of hit 0 of this pass; stream key
     int64_t roff;              // global replica id of replica 0
     const void *beta, *sigma;  // [R] reals
+    const void* Jqt;           // [16][16] psi family with 16 density entries: transposed Jq = C^T J C, or nullptr
     const void* Jt;            // [NL][16][16] transposed couplings Jt[l][b][a] = J_l^{ab} in the handle's precision (global)
     const uint8_t* active;     // [R] or nullptr
     unsigned long long* acc;   // [R]
@@ -261,7 +262,8 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
     const int64_t r = A.r0 + blockIdx.y;
     __shared__ __align__(16) R sJt[NG * NG];
-    for (int t = threadIdx.x; t < NG * NG; t += blockDim.x) sJt[t] = ((const R*)A.Jt)[t];
+    const bool fused = !ONSITE && NP == NG && A.Jqt != nullptr;      // density sums -> energy coefficients in one 16x16 mat-vec
+    for (int t = threadIdx.x; t < NG * NG; t += blockDim.x) sJt[t] = ((const R*)(fused ? A.Jqt : A.Jt))[t];
     const bool alive = (A.active == nullptr || A.active[r]);
     const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
     const R nbeta = neg_beta_scaled(beta);
@@ -306,9 +308,13 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
                         GenOps<GEN>::density_acc(nr, ni, P);
                     }
                 }
-                R S[1][NG];
-                GenOps<GEN>::expect_from_density(P, S[0]);
-                field_from_sums_smem<1>(sJt, S, h);
+                if (!fused) {
+                    R S[1][NG];
+                    GenOps<GEN>::expect_from_density(P, S[0]);
+                    field_from_sums_smem<1>(sJt, S, h);
+                } else if constexpr (NP == NG) {
+                    field_from_sums_smem<1>(sJt, (const R(*)[NG])P, h);       // h now holds Hq = Jq . Psum
+                }
             }
             unsigned mine = 0;
             if (ONSITE) {
@@ -322,7 +328,12 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
                 }
             } else {
                 R Hq[GenOps<GEN>::NDENS];
-                GenOps<GEN>::hq_from_field(h, Hq);
+                if (fused) {
+#pragma unroll
+                    for (int t = 0; t < (NP == NG ? NG : 0); t++) Hq[t] = h[t];
+                } else {
+                    GenOps<GEN>::hq_from_field(h, Hq);
+                }
                 R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
                 for (int hit = 0; hit < A.hits; hit++) {
                     R xr[D], xi[D], u, dE;
@@ -349,7 +360,8 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
     __shared__ __align__(16) R sJt[NG * NG];
     const int64_t r = A.r0 + blockIdx.y;
     const int bd = blockDim.x, tid = threadIdx.x;
-    for (int t = tid; t < NG * NG; t += bd) sJt[t] = ((const R*)A.Jt)[t];
+    const bool fused = !ONSITE && NP == NG && A.Jqt != nullptr;
+    for (int t = tid; t < NG * NG; t += bd) sJt[t] = ((const R*)(fused ? A.Jqt : A.Jt))[t];
     const bool alive = (A.active == nullptr || A.active[r]);
     const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
     const R nbeta = neg_beta_scaled(beta);
@@ -435,9 +447,13 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
                     for (int v = 0; v < NPV; v++) cp_async16(&stage[(z * NPV + v) * bd + tid], Pr + pn + v * ps);
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
-                R S[1][NG];
-                GenOps<GEN>::expect_from_density(P, S[0]);
-                field_from_sums_smem<1>(sJt, S, h);
+                if (!fused) {
+                    R S[1][NG];
+                    GenOps<GEN>::expect_from_density(P, S[0]);
+                    field_from_sums_smem<1>(sJt, S, h);
+                } else if constexpr (NP == NG) {
+                    field_from_sums_smem<1>(sJt, (const R(*)[NG])P, h);       // h now holds Hq = Jq . Psum
+                }
             }
             unsigned mine = 0;
             if (ONSITE) {
@@ -451,7 +467,12 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
                 }
             } else {
                 R Hq[GenOps<GEN>::NDENS];
-                GenOps<GEN>::hq_from_field(h, Hq);
+                if (fused) {
+#pragma unroll
+                    for (int t = 0; t < (NP == NG ? NG : 0); t++) Hq[t] = h[t];
+                } else {
+                    GenOps<GEN>::hq_from_field(h, Hq);
+                }
                 R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
                 for (int hit = 0; hit < A.hits; hit++) {
                     R xr[D], xi[D], u, dE;
@@ -902,6 +923,7 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
             SweepArgs B = A;
             B.r0 = A.r0 + y0; B.rcount = std::min<int64_t>(65535, A.rcount - y0);
             B.Jt = h->d_Jt;
+            B.Jqt = h->fused_density ? h->d_Jqt : nullptr;
             const unsigned tiles = grid_for(nc, SCMC_SWEEP_THREADS);
             const dim3 grid(A.colour_last > A.colour ? 1u : (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES, (unsigned)B.rcount);
             if (A.inj_xi) {
@@ -1172,6 +1194,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     A((void**)&h->d_orig, N * sizeof(int32_t));
     A((void**)&h->d_col_list, N * sizeof(int32_t));
     A(&h->d_Jt, (size_t)MAXL * 256 * h->esz());
+    A(&h->d_Jqt, (size_t)256 * h->esz());
     A(&h->beta, h->R * h->esz());
     A(&h->sigma, h->R * h->esz());
     A((void**)&h->acc, h->R * sizeof(unsigned long long));
@@ -1196,6 +1219,20 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
                 }
         C(cudaMemcpy(h->d_Jt, jt.data(), jt.size(), cudaMemcpyHostToDevice));
     }
+    if (n_labels == 1 && (gen_id == 1 || gen_id == 3)) {     // 16 density entries: fuse map, couplings and transpose map into one 16x16 matrix
+        const int8_t* Cm = gen_id == 1 ? gen::DENSMAP1 : gen::DENSMAP3;
+        std::vector<char> jq((size_t)256 * h->esz(), 0);
+        for (int n = 0; n < 16; n++)
+            for (int m = 0; m < 16; m++) {
+                double v = 0.0;
+                for (int a = 0; a < 16; a++)
+                    for (int b = 0; b < 16; b++) v += (double)Cm[a * 16 + n] * h->J[0][a * 16 + b] * (double)Cm[b * 16 + m];
+                if (precision == 64) ((double*)jq.data())[m * 16 + n] = v;      // transposed: [m][n] = Jq[n][m]
+                else ((float*)jq.data())[m * 16 + n] = (float)v;
+            }
+        C(cudaMemcpy(h->d_Jqt, jq.data(), jq.size(), cudaMemcpyHostToDevice));
+        h->fused_density = true;
+    }
     C(cudaMemset(h->psi, 0, plane * (d / 2)));
     C(cudaMemset(h->T, 0, plane * 4));
     if (h->onsite) C(cudaMemset(h->Tsq, 0, plane * 4));
@@ -1210,7 +1247,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
 int32_t scmc_destroy(scmc_t* h) {
     if (!h) return SCMC_OK;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_col_list, h->d_nbr16};
+    void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     delete h;

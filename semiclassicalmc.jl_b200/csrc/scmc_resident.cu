@@ -24,7 +24,7 @@ struct ResidentArgs {
     int64_t nrep, roff;
     int32_t n_sweeps, hits, cs, n_own_max, cap, n_clusters;
     uint64_t visit0, seed;
-    const void *beta, *sigma, *Jt;
+    const void *beta, *sigma, *Jt, *Jqt;
     const uint8_t* active;
     unsigned long long* acc;
     const uint16_t* nbr16;          // [z][N]
@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
     const int my_off = A.cta_off[rank];
     const int n_own = A.cta_off[rank + 1] - my_off;
     const int tid = threadIdx.x, nth = blockDim.x;
-    for (int t = tid; t < NG * NG; t += nth) sJt[t] = ((const R*)A.Jt)[t];
+    const bool fused = !ONSITE && NP == NG && A.Jqt != nullptr;
+    for (int t = tid; t < NG * NG; t += nth) sJt[t] = ((const R*)(fused ? A.Jqt : A.Jt))[t];
     for (int k = 0; k < M.z; k++)
         for (int q = tid; q < n_own; q += nth) sNbr[k * nmax + q] = A.nbr16[(size_t)k * M.N + my_off + q];
     if (tid < NPV) sPsi[tid * cap + nmax] = make_v4<R>(R(0), R(0), R(0), R(0));     // all-zero padding slot
@@ -262,9 +263,13 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                             }
                             GenOps<GEN>::density_acc(nr, ni, P);
                         }
-                        R S[1][NG];
-                        GenOps<GEN>::expect_from_density(P, S[0]);
-                        field_from_sums_smem<1>(sJt, S, h);
+                        if (!fused) {
+                            R S[1][NG];
+                            GenOps<GEN>::expect_from_density(P, S[0]);
+                            field_from_sums_smem<1>(sJt, S, h);
+                        } else if constexpr (NP == NG) {
+                            field_from_sums_smem<1>(sJt, (const R(*)[NG])P, h);
+                        }
                     }
                     unsigned mine = 0;
                     if (ONSITE) {
@@ -278,7 +283,12 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                         }
                     } else {
                         R Hq[GenOps<GEN>::NDENS];
-                        GenOps<GEN>::hq_from_field(h, Hq);
+                        if (fused) {
+#pragma unroll
+                            for (int t = 0; t < (NP == NG ? NG : 0); t++) Hq[t] = h[t];
+                        } else {
+                            GenOps<GEN>::hq_from_field(h, Hq);
+                        }
                         R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
                         for (int hit = 0; hit < A.hits; hit++) {
                             R xr[D], xi[D], u, dE;
@@ -443,7 +453,7 @@ int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t
         ResidentArgs A;
         memset(&A, 0, sizeof A);
         A.nrep = h->R; A.roff = h->roff; A.hits = hits; A.cs = P.cs; A.n_own_max = P.n_own_max; A.cap = P.cap;
-        A.seed = seed; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.active = active; A.acc = h->acc; A.nbr16 = h->d_nbr16;
+        A.seed = seed; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.Jqt = h->fused_density ? h->d_Jqt : nullptr; A.active = active; A.acc = h->acc; A.nbr16 = h->d_nbr16;
         memcpy(A.cta_off, P.cta_off, sizeof A.cta_off);
         memcpy(A.cta_col_off, P.cta_col_off, sizeof A.cta_col_off);
         A.n_clusters = (int32_t)std::min<int64_t>(h->R, psi ? P.max_clusters_psi : P.max_clusters);

@@ -222,6 +222,14 @@ def emit_cuda_tables(path):
         dens, nterms = _emit_density(f"density_acc_g{n}", f"expect_from_density_g{n}", g)
         lines += dens
         lines.append(f"constexpr int NDENS_g{n} = {nterms};   // density-matrix entries used by the generators at filling {n}")
+        # C[a][m]: T^a = sum_m C[a][m] P[m]  (host side: couplings in the density basis, Jq = C^T J C)
+        gre_, gim_ = _quantise(g)
+        terms = _density_terms(g)
+        Cm = np.zeros((16, nterms), dtype=int)
+        for m, (j, k, part) in enumerate(terms):
+            for a in range(16):
+                Cm[a, m] = gre_[a, j, j] if j == k else (2 * gre_[a, j, k] if part == "r" else -2 * gim_[a, j, k])
+        lines.append(f"static const int8_t DENSMAP{n}[16 * {nterms}] = {{{','.join(str(int(v)) for v in Cm.reshape(-1))}}};")
         for name, arr in (("G", g), ("Gsq", q)):
             re_, im_ = _quantise(arr)
             for part, tab in (("re", re_), ("im", im_)):
