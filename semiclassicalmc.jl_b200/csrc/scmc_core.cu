@@ -46,6 +46,9 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #define SCMC_SWEEP_THREADS 128
 #define SCMC_SWEEP_BLOCKS 5
 #endif
+#ifndef SCMC_HIT_UNROLL2
+#define SCMC_HIT_UNROLL2 0
+#endif
 #ifndef SCMC_ABLATE
 #define SCMC_ABLATE 0            // performance ablations of the direct streaming kernel (profiles/README.md); 0 = production
 #endif
@@ -335,7 +338,18 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
                     GenOps<GEN>::hq_from_field(h, Hq);
                 }
                 R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
-                for (int hit = 0; hit < A.hits; hit++) {
+                int hit = 0;
+#if SCMC_HIT_UNROLL2
+                // two hits per iteration: both Philox / Box-Muller streams are independent of psi, so they interleave (ILP)
+                for (; hit + 1 < A.hits; hit += 2) {
+                    R xr0[D], xi0[D], u0, xr1[D], xi1[D], u1, dE;
+                    stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr0, xi0, u0);
+                    stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit + 1, xr1, xi1, u1);
+                    mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr0, xi0, u0, nbeta, sigma, eloc, dE) ? 1u : 0u;
+                    mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr1, xi1, u1, nbeta, sigma, eloc, dE) ? 1u : 0u;
+                }
+#endif
+                for (; hit < A.hits; hit++) {
                     R xr[D], xi[D], u, dE;
                     stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
                     mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;

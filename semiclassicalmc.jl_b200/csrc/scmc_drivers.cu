@@ -282,7 +282,13 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
     int64_t n_log = 0;
     for (int64_t sweep = (int64_t)p->sweep0 + 1; sweep <= p->n_therm; sweep++) {
         SCMC_TRY(set_beta(sweep));
-        SCMC_TRY(launch_sweeps(h, 1, p->hits, p->seed, (uint64_t)(sweep - 1), nullptr));
+        int64_t n_batch = 1;
+        if (sweep > n_anneal) {      // ramp finished: beta constant, batch up to the next sigma-adaptation point
+            const int64_t next_stop = std::min<int64_t>(p->n_therm, ((sweep + rate - 1) / rate) * rate);
+            n_batch = next_stop - sweep + 1;
+        }
+        SCMC_TRY(launch_sweeps(h, n_batch, p->hits, p->seed, (uint64_t)(sweep - 1), nullptr));
+        sweep += n_batch - 1;
         if (sweep % rate == 0) {
             if (out->therm_energy) {
                 SCMC_TRY(launch_measure(h, h->obs));
@@ -313,8 +319,13 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
         return SCMC_OK;
     };
     for (int64_t sweep = meas_start; sweep <= total; sweep++) {
-        SCMC_TRY(launch_sweeps(h, 1, p->hits, p->seed, (uint64_t)(sweep - 1), nullptr));
-        n_meas_sweeps++;
+        // beta and sigma are frozen here: all sweeps up to the next measurement point go out as ONE call (one launch of the
+        // replica-resident kernel when it applies)
+        const int64_t next_stop = std::min<int64_t>(total, ((sweep + rate - 1) / rate) * rate);
+        const int64_t n_batch = next_stop - sweep + 1;
+        SCMC_TRY(launch_sweeps(h, n_batch, p->hits, p->seed, (uint64_t)(sweep - 1), nullptr));
+        n_meas_sweeps += n_batch;
+        sweep = next_stop;
         if (sweep % rate == 0) {
             SCMC_TRY(launch_measure(h, dser.as<double>() + (size_t)in_chunk * R * SCMC_NOBS));
             in_chunk++; rows++;
