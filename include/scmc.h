@@ -106,6 +106,15 @@ int32_t scmc_structure_factor(scmc_t* h, const double* ks, const double* pos, in
 /* getCorrelations (Observables.jl:22-41) of one replica for a caller-supplied project map [N][N] (0-based), C [16][n_rs] */
 int32_t scmc_correlations(scmc_t* h, int64_t replica, const int32_t* project, int64_t n_rs, double* C);
 
+/* ---- model-specific reductions of the same T vectors (ObservablesTgHbn.jl) ----------------------------------------------- */
+/* getSublatticeMagnetization (ObservablesTgHbn.jl:211-221): mean T over the sites of every label; site_label [N] in 0..n_sub-1,
+ * out [R][n_sub][16] */
+int32_t scmc_sublattice_magnetization(scmc_t* h, const int32_t* site_label, int32_t n_sub, double* out);
+/* getChirality (ObservablesTgHbn.jl:224-249): staggered z vector chirality averaged over the two triangles of every site;
+ * tri [N][4] = sites (i2, i3, i4, i5) of getInteractionSites(cfg, i)[[1, 5, 4, 2]]; out [R][3] = kappa_sigma (components
+ * 5, 9, 13), kappa_tau (2:4), kappa_sigmatau (6:8 + 10:12 + 14:16) in the reference's 1-based component numbering */
+int32_t scmc_chirality(scmc_t* h, const int32_t* tri, double* out);
+
 /* ---- drivers -------------------------------------------------------------------------------------------------------- */
 typedef struct {
     int64_t n_therm;            /* N_therm  (run!, MonteCarlo.jl:3-18) */

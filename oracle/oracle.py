@@ -267,3 +267,46 @@ def log_binning_error(x):
 def specific_heat(e, e2, beta, N):
     """c = beta^2 (<e^2> - <e>^2) N (ObservablesGeneric.jl:63-64)."""
     return beta * beta * (np.mean(e2) - np.mean(e) ** 2) * N
+
+
+# ---- ObservablesTgHbn.jl restated (NumPy loops, FP64) ---------------------------------------------------------------
+def site_labels_triangular120(positions, unit_vectors):
+    """getSiteLabelsTriangular120 (src/Observables/ObservablesTgHbn.jl:189-209)."""
+    lv = [np.asarray(v) / np.linalg.norm(v) for v in unit_vectors]
+    basis = [lv[0] + lv[1], 2 * lv[1] - lv[0]]
+    labels = np.zeros(len(positions), dtype=np.int64)
+    for i, v1 in enumerate(positions):
+        v2 = v1 + lv[0]
+        if np.all(get_prefactors(v1, basis) % 1 == 0):
+            labels[i] = 1
+        elif np.all(get_prefactors(v2, basis) % 1 == 0):
+            labels[i] = 2
+        else:
+            labels[i] = 3
+    return labels
+
+
+def sublattice_magnetization(T, labels):
+    """getSublatticeMagnetization (ObservablesTgHbn.jl:211-221): [16, n_labels]."""
+    uniq = sorted(set(labels.tolist()))
+    m = np.zeros((16, len(uniq)))
+    for c, lab in enumerate(uniq):
+        spins = [T[j] for j in range(len(T)) if labels[j] == lab]
+        m[:, c] = sum(spins) / len(spins)
+    return m
+
+
+def _chirality3(v1, v2, v3):
+    """getChirality(v1, v2, v3) (ObservablesTgHbn.jl:246-249)."""
+    return 2 / 3 / np.sqrt(3) * (np.cross(v1, v2) + np.cross(v2, v3) + np.cross(v3, v1))[2]
+
+
+def chirality(T, nbr_site, components):
+    """getChirality(cfg, components) (ObservablesTgHbn.jl:224-243); components 0-based; neighbour slots [1,5,4,2] -> 0-based [0,4,3,1]."""
+    kap = 0.0
+    N = len(T)
+    for i in range(N):
+        i2, i3, i4, i5 = nbr_site[i][[0, 4, 3, 1]]
+        s1, s2, s3, s4, s5 = (T[j][components] for j in (i, i2, i3, i4, i5))
+        kap += _chirality3(s1, s2, s3) - _chirality3(s1, s4, s5)
+    return kap / N / 2

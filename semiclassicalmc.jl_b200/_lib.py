@@ -62,6 +62,8 @@ SIGNATURES = {
     "scmc_measure": (C.c_int32, [C.c_void_p, c_dp]),
     "scmc_structure_factor": (C.c_int32, [C.c_void_p, c_dp, c_dp, C.c_int32, C.c_int32, C.c_double, c_dp]),
     "scmc_correlations": (C.c_int32, [C.c_void_p, C.c_int64, c_ip, C.c_int64, c_dp]),
+    "scmc_sublattice_magnetization": (C.c_int32, [C.c_void_p, c_ip, C.c_int32, c_dp]),
+    "scmc_chirality": (C.c_int32, [C.c_void_p, c_ip, c_dp]),
     "scmc_run_metropolis": (C.c_int32, [C.c_void_p, C.POINTER(RunParams), C.POINTER(RunResults)]),
     "scmc_anneal": (C.c_int32, [C.c_void_p, C.POINTER(AnnealParams), C.POINTER(AnnealResults)]),
     "scmc_optimize": (C.c_int32, [C.c_void_p, C.c_int64, c_dp]),

@@ -201,6 +201,83 @@ __global__ void __launch_bounds__(256) k_correlations(const vec4<R>* __restrict_
     for (int a = 0; a < NG; a++) atomicAdd(C + (size_t)a * n_rs + m, (double)ti[a] * (double)tj[a]);
 }
 
+// mean T over the sites of each sublattice label (ObservablesTgHbn.jl:211-221); one CTA per replica, one pass per label
+template <class R>
+__global__ void __launch_bounds__(256) k_sublattice_mag(const vec4<R>* __restrict__ Tpl, int N, int Ns, int64_t nrep, const int32_t* __restrict__ label_perm,
+                                                        int n_sub, double* __restrict__ out) {
+    const int64_t r = blockIdx.x;
+    const size_t ps = (size_t)nrep * Ns;
+    __shared__ double red[8][NG + 1];
+    for (int l = 0; l < n_sub; l++) {
+        double acc[NG + 1];
+#pragma unroll
+        for (int a = 0; a <= NG; a++) acc[a] = 0.0;
+        for (int p = threadIdx.x; p < N; p += blockDim.x) {
+            if (label_perm[p] != l) continue;
+            R t[NG];
+            load_T<R>(Tpl + r * Ns + p, ps, t);
+#pragma unroll
+            for (int a = 0; a < NG; a++) acc[a] += (double)t[a];
+            acc[NG] += 1.0;
+        }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int a = 0; a <= NG; a++) {
+            double v = acc[a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp][a] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x <= NG) {
+            double v = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w][threadIdx.x];
+            red[0][threadIdx.x] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < NG) out[((size_t)r * n_sub + l) * NG + threadIdx.x] = red[0][NG] > 0.0 ? red[0][threadIdx.x] / red[0][NG] : 0.0;
+        __syncthreads();
+    }
+}
+// staggered vector chirality (ObservablesTgHbn.jl:224-249); tri in permuted site order
+template <class R>
+__global__ void __launch_bounds__(256) k_chirality(const vec4<R>* __restrict__ Tpl, int N, int Ns, int64_t nrep, const int32_t* __restrict__ tri,
+                                                   double* __restrict__ out) {
+    const int64_t r = blockIdx.x;
+    const size_t ps = (size_t)nrep * Ns;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int p = threadIdx.x; p < N; p += blockDim.x) {
+        R t[5][NG];
+        load_T<R>(Tpl + r * Ns + p, ps, t[0]);
+#pragma unroll
+        for (int m = 0; m < 4; m++) load_T<R>(Tpl + r * Ns + tri[4 * p + m], ps, t[m + 1]);
+        // (v1 x v2 + v2 x v3 + v3 x v1)_z with the first two entries of each 3-component block starting at `o` (stride `st`)
+        auto chi = [&](int i1, int i2, int i3, int o, int st) {
+            const double x1 = t[i1][o], y1 = t[i1][o + st], x2 = t[i2][o], y2 = t[i2][o + st], x3 = t[i3][o], y3 = t[i3][o + st];
+            return (x1 * y2 - y1 * x2) + (x2 * y3 - y2 * x3) + (x3 * y1 - y3 * x1);
+        };
+        auto kap = [&](int o, int st) { return chi(0, 1, 2, o, st) - chi(0, 3, 4, o, st); };
+        acc[0] += kap(4, 4);                             // components [5, 9, 13] (1-based): sigma
+        acc[1] += kap(1, 1);                             // components 2:4: tau
+        acc[2] += kap(5, 1) + kap(9, 1) + kap(13, 1);    // 6:8 + 10:12 + 14:16: sigma tau
+    }
+    __shared__ double red[8][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        double v = acc[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][a] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w][threadIdx.x];
+        out[r * 3 + threadIdx.x] = v * (2.0 / 3.0 / 1.7320508075688772) / (double)N / 2.0;
+    }
+}
+
 template <int V> using ic = std::integral_constant<int, V>;
 template <class R, int NL>
 static DevModel<R, NL> make_model_d(const scmc_handle* h) {
@@ -473,6 +550,52 @@ int32_t scmc_correlations(scmc_t* h, int64_t r, const int32_t* project, int64_t 
     h->launches++;
     SCMC_CK(cudaGetLastError());
     SCMC_CK(cudaMemcpyAsync(C, dC.p, (size_t)16 * n_rs * 8, cudaMemcpyDeviceToHost, h->stream));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    return SCMC_OK;
+}
+
+int32_t scmc_sublattice_magnetization(scmc_t* h, const int32_t* site_label, int32_t n_sub, double* out) {
+    SCMC_ARG(h && site_label && out, "null argument");
+    SCMC_ARG(n_sub >= 1 && n_sub <= 64, "scmc_sublattice_magnetization: 1..64 labels");
+    SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(ensure_T(h));
+    std::vector<int32_t> lp(h->N);
+    for (int64_t q = 0; q < h->N; q++) {
+        lp[q] = site_label[h->orig[q]];
+        SCMC_ARG(lp[q] >= 0 && lp[q] < n_sub, "scmc_sublattice_magnetization: label out of range");
+    }
+    DevBuf dl, dout;
+    const size_t ob = (size_t)h->R * n_sub * 16 * 8;
+    SCMC_CK(dl.alloc(h->N * 4)); SCMC_CK(dout.alloc(ob));
+    SCMC_CK(cudaMemcpyAsync(dl.p, lp.data(), h->N * 4, cudaMemcpyHostToDevice, h->stream));
+    if (h->prec == 64) k_sublattice_mag<double><<<(unsigned)h->R, 256, 0, h->stream>>>((const double4*)h->T, (int)h->N, (int)h->Ns, h->R, dl.as<int32_t>(), n_sub, dout.as<double>());
+    else k_sublattice_mag<float><<<(unsigned)h->R, 256, 0, h->stream>>>((const float4*)h->T, (int)h->N, (int)h->Ns, h->R, dl.as<int32_t>(), n_sub, dout.as<double>());
+    h->launches++;
+    SCMC_CK(cudaGetLastError());
+    SCMC_CK(cudaMemcpyAsync(out, dout.p, ob, cudaMemcpyDeviceToHost, h->stream));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    return SCMC_OK;
+}
+
+int32_t scmc_chirality(scmc_t* h, const int32_t* tri, double* out) {
+    SCMC_ARG(h && tri && out, "null argument");
+    SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(ensure_T(h));
+    std::vector<int32_t> tp((size_t)h->N * 4);
+    for (int64_t q = 0; q < h->N; q++)
+        for (int m = 0; m < 4; m++) {
+            const int32_t j = tri[(size_t)h->orig[q] * 4 + m];
+            SCMC_ARG(j >= 0 && j < h->N, "scmc_chirality: site index out of range");
+            tp[(size_t)q * 4 + m] = h->perm[j];
+        }
+    DevBuf dt, dout;
+    SCMC_CK(dt.alloc(tp.size() * 4)); SCMC_CK(dout.alloc((size_t)h->R * 3 * 8));
+    SCMC_CK(cudaMemcpyAsync(dt.p, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    if (h->prec == 64) k_chirality<double><<<(unsigned)h->R, 256, 0, h->stream>>>((const double4*)h->T, (int)h->N, (int)h->Ns, h->R, dt.as<int32_t>(), dout.as<double>());
+    else k_chirality<float><<<(unsigned)h->R, 256, 0, h->stream>>>((const float4*)h->T, (int)h->N, (int)h->Ns, h->R, dt.as<int32_t>(), dout.as<double>());
+    h->launches++;
+    SCMC_CK(cudaGetLastError());
+    SCMC_CK(cudaMemcpyAsync(out, dout.p, (size_t)h->R * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
     SCMC_CK(cudaStreamSynchronize(h->stream));
     return SCMC_OK;
 }

@@ -129,3 +129,102 @@ def means(obs, cfg, beta, replica=0):
     if obs.with_correlations:
         out["correlations"] = (obs.correlations[replica].mean(), obs.correlations[replica].std_error())
     return out
+
+
+# ---- tg-hbn observables (ObservablesTgHbn.jl) ----------------------------------------------------------------------
+def getPrefactors(v, basis):
+    """Coefficients of v in `basis`, rounded to 5 digits (Observables.jl:83-88)."""
+    A = np.array([[np.dot(e1, e2) for e2 in basis] for e1 in basis])
+    b = np.array([np.dot(e, v) for e in basis])
+    return np.round(np.linalg.solve(A, b), 5)
+
+
+def getSiteLabelsTriangular120(cfg):
+    """Sublattice labels 1, 2, 3 of the 120-degree order on the triangular lattice (ObservablesTgHbn.jl:189-209)."""
+    lv = [v / np.linalg.norm(v) for v in cfg.unitVectors]
+    basis = [lv[0] + lv[1], 2 * lv[1] - lv[0]]
+    labels = np.zeros(cfg.nSites, dtype=np.int64)
+    for i in range(cfg.nSites):
+        v1 = cfg.positions[i]
+        if np.all(getPrefactors(v1, basis) % 1 == 0):
+            labels[i] = 1
+        elif np.all(getPrefactors(v1 + lv[0], basis) % 1 == 0):
+            labels[i] = 2
+        else:
+            labels[i] = 3
+    return labels
+
+
+def getSublatticeMagnetization(cfg, site_labels):
+    """[R, 16, n_labels]: mean T over the sites of every label (ObservablesTgHbn.jl:211-221), device reduction."""
+    labels = np.unique(site_labels)
+    lab0 = np.ascontiguousarray(np.searchsorted(labels, site_labels), dtype=np.int32)
+    out = np.zeros((cfg.n_replicas, len(labels), 16))
+    _lib.check(cfg._lib.scmc_sublattice_magnetization(cfg._h, _lib.iptr(lab0), len(labels), _lib.dptr(out)))
+    return np.transpose(out, (0, 2, 1))
+
+
+def getChirality(cfg, tri=None):
+    """[R, 3] = (kappa_sigma, kappa_tau, kappa_sigmatau): staggered vector chiralities (ObservablesTgHbn.jl:224-249).  `tri`
+    defaults to neighbour slots [1, 5, 4, 2] (1-based) of the tg-hbn bond order, as the reference hard-codes."""
+    if tri is None:
+        tri = cfg.interactionSites[:, [0, 4, 3, 1]]
+    tri = np.ascontiguousarray(tri, dtype=np.int32)
+    out = np.zeros((cfg.n_replicas, 3))
+    _lib.check(cfg._lib.scmc_chirality(cfg._h, _lib.iptr(tri), _lib.dptr(out)))
+    return out
+
+
+_TGHBN_SETS = {"sd": [4, 8, 12], "dx": [1, 2], "dz": [3], "sx": [5, 6, 9, 10, 13, 14], "sz": [7, 11, 15]}   # 0-based component sets
+
+
+class ObservablesTgHbn(Observables):
+    """Accumulators of ObservablesTgHbn.jl:4-44 (one set per replica): energy, sublattice / total magnetisation norms,
+    vector chiralities, each with the (x^2, x^4) pair for its Binder cumulant."""
+    NAMES = ["subMsd", "subMsx", "subMsz", "subMdx", "subMdz", "msd", "msx", "msz", "mdx", "mdz",
+             "spinChirality", "valleyChirality", "spinValleyChirality"]
+
+    def __init__(self, cfg):
+        R = cfg.n_replicas
+        self.siteLabels = getSiteLabelsTriangular120(cfg)
+        self.energy = [ErrorPropagator(2) for _ in range(R)]
+        self.series = {n: [LogBinner() for _ in range(R)] for n in self.NAMES}
+        self.binder = {n: [ErrorPropagator(2) for _ in range(R)] for n in self.NAMES}
+        self.with_correlations = False
+
+    def values(self, cfg):
+        """One measurement of every replica: dict name -> [R] (the quantities pushed by measure!, ObservablesTgHbn.jl:47-98)."""
+        kap = getChirality(cfg)
+        subM = getSublatticeMagnetization(cfg, self.siteLabels)             # [R, 16, 3]
+        m = subM.mean(axis=2)                                               # [R, 16]
+        out = {"spinChirality": kap[:, 0], "valleyChirality": kap[:, 1], "spinValleyChirality": kap[:, 2]}
+        for key, comps in _TGHBN_SETS.items():
+            out["subM" + key] = np.linalg.norm(subM[:, comps, :], axis=1).mean(axis=1)
+            out["m" + key] = np.linalg.norm(m[:, comps], axis=1)
+        return out
+
+
+def measureTgHbn_(obs, cfg):
+    """measure!(::ObservablesTgHbn, cfg, E) (ObservablesTgHbn.jl:47-98); E re-summed on the device."""
+    row = cfg.measure()
+    vals = obs.values(cfg)
+    for r in range(cfg.n_replicas):
+        obs.energy[r].push(row[r, 0], row[r, 1])
+        for n in obs.NAMES:
+            x = float(vals[n][r])
+            obs.series[n][r].push(x)
+            obs.binder[n][r].push(x ** 2, x ** 4)
+
+
+def meansTgHbn(obs, cfg, beta, replica=0):
+    """The `means/*` group of saveMeans!(::ObservablesTgHbn) (ObservablesTgHbn.jl:101-186): Binder cumulant b = 1 - <x^4>/(3 <x^2>^2)."""
+    b = lambda v: 1 - v[1] / (3 * v[0] ** 2)
+    db = lambda v: np.array([2 * v[1] / (3 * v[0] ** 3), -1 / (3 * v[0] ** 2)])
+    N = cfg.nSites
+    e = obs.energy[replica]
+    out = {"energy": (e.means()[0], e.std_errors()[0]),
+           "heat": (e.mean(lambda m: beta * beta * (m[1] - m[0] ** 2) * N), e.std_error(lambda m: np.array([-2 * beta * beta * m[0] * N, beta * beta * N])))}
+    for n in obs.NAMES:
+        out[n] = (obs.series[n][replica].mean(), obs.series[n][replica].std_error())
+        out["binder_" + n] = (obs.binder[n][replica].mean(b), obs.binder[n][replica].std_error(db))
+    return out

@@ -117,3 +117,30 @@ def test_tghbn_model_runs_and_conserves_invariants(scmc, oracle_mod):
     T, Tsq = cfg.get_T(5, squared=True)
     To, Tsqo = o.get_T()
     assert np.allclose(T, To, atol=1e-12) and np.allclose(Tsq, Tsqo, atol=1e-12)
+
+
+def test_tghbn_observables_match_reference_restatement(scmc, oracle_mod):
+    """ObservablesTgHbn.jl reductions (sublattice magnetisation, vector chiralities, derived norms) on the device vs the oracle's
+    loop-by-loop restatement, on a thermalised tg-hbn configuration (L = 12: 120-degree sublattices of 48 sites each)."""
+    cfg = scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.15, 0.8], 12, 2, n_replicas=4, precision=64, seed=77)
+    cfg.sweep(3, np.array([0.5, 2.0, 6.0, 20.0]), np.full(4, 0.4))
+    obs = scmc.initializeObservables(scmc.ObservablesTgHbn, cfg)
+    labels_o = oracle_mod.site_labels_triangular120(cfg.positions, cfg.unitVectors)
+    assert np.array_equal(obs.siteLabels, labels_o) and sorted(np.bincount(labels_o)[1:]) == [48, 48, 48]
+    subM = scmc.getSublatticeMagnetization(cfg, obs.siteLabels)
+    kap = scmc.getChirality(cfg)
+    vals = obs.values(cfg)
+    for r in range(4):
+        T = cfg.get_T(r)
+        m_o = oracle_mod.sublattice_magnetization(T, labels_o)
+        assert np.allclose(subM[r], m_o, atol=1e-13)
+        k_sig = oracle_mod.chirality(T, cfg.interactionSites, [4, 8, 12])
+        k_tau = oracle_mod.chirality(T, cfg.interactionSites, [1, 2, 3])
+        k_st = sum(oracle_mod.chirality(T, cfg.interactionSites, c) for c in ([5, 6, 7], [9, 10, 11], [13, 14, 15]))
+        assert np.allclose(kap[r], [k_sig, k_tau, k_st], atol=1e-13)
+        assert np.isclose(vals["subMsd"][r], np.mean([np.linalg.norm(m_o[[4, 8, 12], n]) for n in range(3)]), atol=1e-13)
+        assert np.isclose(vals["mdx"][r], np.linalg.norm(m_o.mean(axis=1)[[1, 2]]), atol=1e-13)
+    for _ in range(3):
+        scmc.measureTgHbn_(obs, cfg)
+    mm = scmc.meansTgHbn(obs, cfg, 1.0, replica=2)
+    assert "binder_spinChirality" in mm and np.isfinite(mm["binder_subMsd"][0])
