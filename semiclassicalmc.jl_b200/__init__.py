@@ -10,10 +10,10 @@ from .build import build as build_library
 
 def __getattr__(name):   # lazy: the API modules need numpy only, the CUDA library is loaded on first use
     import importlib
-    _mods = ("generators", "lattice", "configuration", "models", "observables", "montecarlo", "launcher", "binning", "distributed")
+    _mods = ("generators", "lattice", "configuration", "models", "observables", "montecarlo", "launcher", "binning", "distributed", "io")
     if name in _mods:
         return importlib.import_module(f".{name}", __name__)
-    for mod in ("generators", "lattice", "configuration", "models", "observables", "montecarlo", "launcher", "binning", "distributed"):
+    for mod in ("generators", "lattice", "configuration", "models", "observables", "montecarlo", "launcher", "binning", "distributed", "io"):
         try:
             m = importlib.import_module(f".{mod}", __name__)
         except ModuleNotFoundError:
