@@ -33,7 +33,6 @@ end
 Base.length(cfg::Configuration) = cfg.nSites
 
 # C order [a][j][k] from a Vector of d x d matrices (Julia is column-major: permute before handing over)
-cmajor(gen) = Float64[f(gen[a][j, k]) for f in (real,), k in 1:size(gen[1], 2), j in 1:size(gen[1], 1), a in 1:16][:]
 parts(gen) = (Float64[real(gen[a][j, k]) for k in 1:size(gen[1], 2), j in 1:size(gen[1], 1), a in 1:16][:],
               Float64[imag(gen[a][j, k]) for k in 1:size(gen[1], 2), j in 1:size(gen[1], 1), a in 1:16][:])
 

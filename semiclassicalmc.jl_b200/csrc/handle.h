@@ -91,6 +91,9 @@ int32_t launch_measure(scmc_handle* h, double* d_rows /* device [R][SCMC_NOBS] *
 int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes);
 int32_t ensure_T(scmc_handle* h);      // recompute the cached T (Tsq) planes from psi if a psi-gather sweep left them stale
 bool uses_psi_gather(const scmc_handle* h);
+int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint64_t seed, double att_per_sweep, double min_accepted,
+                               double beta_fac, double min_accrate, double sigma_min, int64_t n_per_T, int64_t n_total,
+                               int64_t* d_sweeps_at_T, int64_t* d_sweeps_done, int* d_n_active);
 // implemented in scmc_resident.cu
 void plan_resident(scmc_handle* h, const std::vector<int>& owner_of_perm);
 int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active, bool psi);

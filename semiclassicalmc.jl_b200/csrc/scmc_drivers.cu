@@ -443,7 +443,22 @@ int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results*
     const unsigned gR = grid_for(R, 128);
     int n_active = (int)std::min<int64_t>(R, 1 << 30);
     const int check_every = 16;
-    for (int64_t sweep = 1; sweep < p->N_max && n_active > 0; sweep++) {
+    // Device-side driver: when every replica lives in ONE CTA of the psi-family resident kernel, the whole cooling loop
+    // (acceptance window, beta / sigma updates, stop flag) runs inside the persistent kernel, `chunk` sweeps per launch.
+    const bool device_side = uses_psi_gather(h) && h->res.eligible_psi && h->res.cs == 1 && (h->sweep_mode == 0 || h->sweep_mode == 4) && p->N_max > 1;
+    if (device_side) {
+        const int64_t n_total = p->N_max - 1;
+        for (int64_t launched = 0; launched < n_total && n_active > 0;) {
+            const int64_t chunk = std::min<int64_t>(512, n_total - launched);
+            SCMC_CK(cudaMemsetAsync(dnact.p, 0, sizeof(int), h->stream));
+            SCMC_TRY(launch_resident_anneal(h, chunk, p->hits, p->seed, att_per_sweep, min_accepted, 1.0 / p->T_fac, p->min_accrate, p->sigma_min,
+                                            p->N_per_T, n_total, dsat.as<int64_t>(), ddone.as<int64_t>(), dnact.as<int>()));
+            SCMC_CK(cudaMemcpyAsync(&n_active, dnact.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            SCMC_CK(cudaStreamSynchronize(h->stream));
+            launched += chunk;
+        }
+    }
+    for (int64_t sweep = 1; !device_side && sweep < p->N_max && n_active > 0; sweep++) {
         SCMC_TRY(launch_sweeps(h, 1, p->hits, p->seed, (uint64_t)(sweep - 1), h->active));
         const bool check = (sweep % check_every == 0) || (sweep + 1 >= p->N_max);
         SCMC_CK(cudaMemsetAsync(dnact.p, 0, sizeof(int), h->stream));

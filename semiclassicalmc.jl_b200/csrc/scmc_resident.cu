@@ -30,6 +30,13 @@ struct ResidentArgs {
     const uint16_t* nbr16;          // [z][N]
     int32_t cta_off[17];
     int32_t cta_col_off[16][MAXC + 1];
+    // device-side annealing controller (runAnnealing!, src/MonteCarlo.jl:145-204); single-CTA replicas only
+    int32_t anneal;                 // 0 = plain sweeps
+    double att_per_sweep, min_accepted, beta_fac, min_accrate, sigma_min;
+    int64_t n_per_T, n_total;       // sweeps per temperature cap; total sweep budget (N_max - 1)
+    int64_t *sweeps_at_T, *sweeps_done;
+    uint8_t* active_rw;
+    int* n_active;                  // out: replicas still running after this launch
 };
 
 // ---- shared-memory / DSMEM access helpers -----------------------------------------------------------------------------
@@ -233,12 +240,19 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
 #pragma unroll
             for (int v = 0; v < NPV; v++) sPsi[v * cap + q] = M.psi[gbase + q + v * ps];
         }
-        const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
-        const R nbeta = neg_beta_scaled(beta);
+        R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+        R nbeta = neg_beta_scaled(beta);
+        // annealing state of this replica (all threads keep identical copies; the controller is deterministic)
+        const bool anneal = !CLUSTER && A.anneal != 0;
+        int64_t an_done = anneal ? A.sweeps_done[r] : 0, an_sat = anneal ? A.sweeps_at_T[r] : 0;
+        double an_acc = anneal ? (double)A.acc[r] : 0.0;
+        bool an_still = true;
         if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
         unsigned nacc = 0;
-        for (int sweep = 0; sweep < A.n_sweeps; sweep++) {
-            const uint64_t visit_base = A.visit0 + (uint64_t)sweep * (uint64_t)A.hits;
+        for (int sweep = 0; sweep < A.n_sweeps && an_still; sweep++) {
+            if (anneal && an_done >= A.n_total) break;
+            const uint64_t visit_base = anneal ? (uint64_t)an_done * (uint64_t)A.hits : A.visit0 + (uint64_t)sweep * (uint64_t)A.hits;
+            unsigned sweep_acc = 0;
             for (int c = 0; c < M.n_col; c++) {
                 const int c0 = A.cta_col_off[rank][c], cnt = A.cta_col_off[rank][c + 1] - c0;
                 for (int s = tid; s < cnt; s += nth) {
@@ -297,14 +311,51 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                         }
                     }
                     if (mine) store_psi<R, D>(sPsi + q, (size_t)cap, re, im);
-                    nacc += mine;
+                    sweep_acc += mine;
                 }
                 if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
+            }
+            if (!anneal) {
+                nacc += sweep_acc;
+            } else {
+                // accepted updates of this sweep over the whole replica, then the cooling rule (MonteCarlo.jl:151-203)
+                const unsigned wt = __reduce_add_sync(0xffffffffu, sweep_acc);
+                if ((tid & 31) == 0 && wt) atomicAdd(&s_acc, wt);
+                __syncthreads();
+                an_acc += (double)s_acc;
+                __syncthreads();
+                if (tid == 0) s_acc = 0;
+                an_sat++; an_done++;
+                const bool last = an_done >= A.n_total;
+                if (!(an_acc < A.min_accepted && an_sat < A.n_per_T && !last)) {
+                    const double ratio = an_acc / (A.att_per_sweep * (double)an_sat);
+                    if (ratio > A.min_accrate) {
+                        beta = (R)((double)beta * A.beta_fac);
+                        sigma = (R)fmax(fmin((double)sigma * 0.5 / (1.0 - ratio), 60.0), A.sigma_min);
+                        nbeta = neg_beta_scaled(beta);
+                        an_acc = 0.0; an_sat = 0;
+                    } else {
+                        an_still = false;
+                    }
+                }
+                __syncthreads();
             }
         }
         for (int q = tid; q < n_own; q += nth) {
 #pragma unroll
             for (int v = 0; v < NPV; v++) M.psi[gbase + q + v * ps] = sPsi[v * cap + q];
+        }
+        if (anneal) {
+            if (tid == 0) {
+                ((R*)A.beta)[r] = beta; ((R*)A.sigma)[r] = sigma;
+                A.acc[r] = (unsigned long long)an_acc;
+                A.sweeps_at_T[r] = an_sat; A.sweeps_done[r] = an_done;
+                const bool running = an_still && an_done < A.n_total;
+                A.active_rw[r] = an_still ? 1 : 0;
+                if (running) atomicAdd(A.n_active, 1);
+            }
+            __syncthreads();
+            continue;
         }
         const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
         if ((tid & 31) == 0 && tot) atomicAdd(&s_acc, tot);
@@ -481,6 +532,42 @@ int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t
             done += chunk;
         }
         return SCMC_OK;
+    });
+}
+
+
+// Device-side cooling loop for single-CTA psi-family replicas: up to `chunk` sweeps per launch, controller inside the kernel.
+// Returns through *n_active how many replicas are still cooling and have budget left.
+int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint64_t seed, double att_per_sweep, double min_accepted,
+                               double beta_fac, double min_accrate, double sigma_min, int64_t n_per_T, int64_t n_total,
+                               int64_t* d_sweeps_at_T, int64_t* d_sweeps_done, int* d_n_active) {
+    auto& P = h->res;
+    h->T_stale = true;
+    return dispatch_r(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+        constexpr bool ONS = decltype(ons)::value != 0;
+        if constexpr (NL != 1) { return SCMC_ERR_UNSUPPORTED; } else {
+            auto M = make_model_r<R, NL>(h);
+            ResidentArgs A;
+            memset(&A, 0, sizeof A);
+            A.nrep = h->R; A.roff = h->roff; A.hits = hits; A.cs = P.cs; A.n_own_max = P.n_own_max; A.cap = P.cap;
+            A.seed = seed; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.Jqt = h->fused_density ? h->d_Jqt : nullptr;
+            A.active = h->active; A.acc = h->acc; A.nbr16 = h->d_nbr16;
+            memcpy(A.cta_off, P.cta_off, sizeof A.cta_off);
+            memcpy(A.cta_col_off, P.cta_col_off, sizeof A.cta_col_off);
+            A.n_clusters = (int32_t)std::min<int64_t>(h->R, P.max_clusters_psi);
+            A.n_sweeps = (int32_t)chunk; A.visit0 = 0;
+            A.anneal = 1; A.att_per_sweep = att_per_sweep; A.min_accepted = min_accepted; A.beta_fac = beta_fac; A.min_accrate = min_accrate;
+            A.sigma_min = sigma_min; A.n_per_T = n_per_T; A.n_total = n_total; A.sweeps_at_T = d_sweeps_at_T; A.sweeps_done = d_sweeps_done;
+            A.active_rw = h->active; A.n_active = d_n_active;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)A.n_clusters); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem_psi; cfg.stream = h->stream;
+            cfg.attrs = nullptr; cfg.numAttrs = 0;
+            SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, false>, M, A));
+            h->launches++;
+            return SCMC_OK;
+        }
     });
 }
 

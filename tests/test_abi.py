@@ -58,3 +58,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(base, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, os.path.join(base, f)
+
+
+def _build_client(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_client")
+    subprocess.check_call(["gcc", "-O1", "-o", exe, os.path.join(ROOT, "tests", "abi_client.c"), "-ldl"])
+    return exe
+
+
+def test_plain_c_client_binds_the_abi(scmc, tmp_path):
+    """A plain-C program (what a cgo / ccall binding amounts to) loads the library and gets clean error codes without a GPU."""
+    import subprocess
+    exe = _build_client(tmp_path)
+    out = subprocess.run([exe, scmc._lib.LIB_PATH], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "bad precision -> status -1" in out.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_client_runs_a_simulation(scmc, tmp_path):
+    import subprocess
+    exe = _build_client(tmp_path)
+    out = subprocess.run([exe, scmc._lib.LIB_PATH, "run"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "abi_client ok" in out.stdout, out.stdout + out.stderr

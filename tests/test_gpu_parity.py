@@ -302,3 +302,21 @@ def test_checkpoint_resume_continues_the_chain(scmc, tmp_path):
     assert np.array_equal(a.get_state(), c.get_state())
     m, e = scmc.getmeans([fn, str(tmp_path / "missing")], "energy")
     assert m.shape == (1, 3)
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_device_side_annealing_equals_host_driven_loop(scmc, precision):
+    """runAnnealing!'s cooling loop inside the persistent resident kernel (one CTA per replica) vs the same loop driven from the
+    host one sweep at a time: identical final beta, sigma, sweep counts and bit-identical states for every replica."""
+    mk = lambda: scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 12, 1, n_replicas=24, precision=precision, seed=4321)
+    kw = dict(T_fac=0.9, N_max=700, N_o=0, N_per_T=20, min_acc_per_site=3, min_accrate=0.02, σ_min=0.05)
+    a = mk(); a.set_sweep_mode(3)                  # streaming psi-gather kernel, host-driven controller
+    ra = scmc.runAnnealing_(a, 2.0, **kw)
+    b = mk()                                       # auto: psi family, single-CTA resident kernel, device-side controller
+    assert b.info()["resident_psi"] and b.info()["cluster"] == 1
+    rb = scmc.runAnnealing_(b, 2.0, **kw)
+    assert np.array_equal(ra["sweeps"], rb["sweeps"]) and ra["sweeps"].min() > 50
+    assert np.array_equal(ra["beta"], rb["beta"]) and np.array_equal(ra["sigma"], rb["sigma"])
+    assert np.array_equal(a.get_state(), b.get_state())
+    assert np.array_equal(ra["E"], rb["E"])
+    assert len(set(ra["sweeps"].tolist())) > 1 or ra["sweeps"][0] == 699      # replicas stop independently (or all hit N_max)
