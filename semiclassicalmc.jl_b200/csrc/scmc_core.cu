@@ -939,7 +939,12 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
             B.Jt = h->d_Jt;
             B.Jqt = h->fused_density ? h->d_Jqt : nullptr;
             const unsigned tiles = grid_for(nc, SCMC_SWEEP_THREADS);
-            const dim3 grid(A.colour_last > A.colour ? 1u : (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES, (unsigned)B.rcount);
+            // CTAs per replica: up to SCMC_SWEEP_TILES site tiles per CTA (coupling table staged once per CTA), but never fewer
+            // than ~8 waves of CTAs over the chip, so small replica counts (8-GPU shards) do not end in a long tail
+            unsigned bpr = (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES;
+            const unsigned min_bpr = (unsigned)((6000 + B.rcount - 1) / B.rcount);
+            bpr = std::min(tiles, std::max(bpr, min_bpr));
+            const dim3 grid(A.colour_last > A.colour ? 1u : bpr, (unsigned)B.rcount);
             if (A.inj_xi) {
                 k_sweep_colour<R, GEN, ONS, NL, true><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
             } else if (psi) {
