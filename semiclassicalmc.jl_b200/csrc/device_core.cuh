@@ -244,15 +244,15 @@ template <class R, int GEN>
 __device__ __forceinline__ bool metropolis_hit_psi(R* re, R* im, const R* Hq, const R* xr, const R* xi, R u, R nbeta, R sigma, R& eloc, R& dE_out) {
     constexpr int D = GenOps<GEN>::D;
     R nre[D], nim[D];
-    R n2 = R(0);
+    R na = R(0), nb = R(0);                  // two partial sums for the norm
 #pragma unroll
     for (int k = 0; k < D; k++) {
         nre[k] = fma(sigma, xr[k], re[k]);
         nim[k] = fma(sigma, xi[k], im[k]);
-        n2 = fma(nre[k], nre[k], n2);
-        n2 = fma(nim[k], nim[k], n2);
+        na = fma(nre[k], nre[k], na);
+        nb = fma(nim[k], nim[k], nb);
     }
-    const R inv = inv_sqrt(n2);
+    const R inv = inv_sqrt(na + nb);
 #pragma unroll
     for (int k = 0; k < D; k++) { nre[k] *= inv; nim[k] *= inv; }
     const R enew = GenOps<GEN>::energy_from_state(nre, nim, Hq);

@@ -37,6 +37,8 @@ struct DevModel {
     const int8_t* lab;    // [z][N]        coupling label of that bond
     const int32_t* orig;  // [N]           permuted index -> caller's site number
     const int32_t* col_list;  // [N]       permuted indices grouped by colour: class c = col_list[col_off[c] .. col_off[c+1])
+    const int32_t* cls_site;  // [N]       caller's site number by class position (= orig[col_list[.]])
+    const int32_t* cls_nbr;   // [z][N]    neighbour (permuted index) by class position: one round trip instead of two
     int32_t N, Ns, z, n_col;
     int64_t nrep;
     int32_t col_off[MAXC + 1];
@@ -56,7 +58,7 @@ struct scmc_handle {
     double e_const = 0.0;     // N * sum_a K^a when (G^a)^2 = 1 (n = 1, 3): constant on-site energy
     // device memory
     void *psi = nullptr, *T = nullptr, *Tsq = nullptr;
-    int32_t *nbr = nullptr, *d_orig = nullptr, *d_col_list = nullptr;
+    int32_t *nbr = nullptr, *d_orig = nullptr, *d_col_list = nullptr, *d_cls_site = nullptr, *d_cls_nbr = nullptr;
     uint16_t* d_nbr16 = nullptr;                 // [z][N] resident-kernel neighbour codes: owner CTA << 12 | local index
     int8_t* lab = nullptr;
     void *beta = nullptr, *sigma = nullptr;      // [R] reals of the handle's precision

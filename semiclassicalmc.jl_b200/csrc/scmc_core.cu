@@ -284,15 +284,16 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
     for (int colour = A.colour; colour <= A.colour_last; colour++) {
         const int nc = M.col_off[colour + 1] - M.col_off[colour];
         for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nc && alive; s += gridDim.x * blockDim.x) {
-            const int p = M.col_list[M.col_off[colour] + s];
+            const int cp = M.col_off[colour] + s;          // class position: p, site and neighbour slots are independent loads
+            const int p = M.col_list[cp];
+            const int site = M.cls_site[cp];
             R re[D], im[D], T[NG], Tsq[NG], h[NG];
             load_psi<R, D>(M.psi + rbase + p, ps, re, im);
-            const int site = M.orig[p];
             {
                 R P[NP];
 #pragma unroll
                 for (int t = 0; t < NP; t++) P[t] = R(0);
-                const int32_t* nb = M.nbr + p;
+                const int32_t* nb = M.cls_nbr + cp;
 #pragma unroll 2
                 for (int k = 0; k < M.z; k += 3) {
                     unsigned j[3];
@@ -851,7 +852,7 @@ static DevModel<R, NL> make_model(const scmc_handle* h) {
     DevModel<R, NL> M;
     memset(&M, 0, sizeof M);
     M.psi = (vec4<R>*)h->psi; M.T = (vec4<R>*)h->T; M.Tsq = (vec4<R>*)h->Tsq;
-    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig; M.col_list = h->d_col_list;
+    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig; M.col_list = h->d_col_list; M.cls_site = h->d_cls_site; M.cls_nbr = h->d_cls_nbr;
     M.N = (int32_t)h->N; M.Ns = (int32_t)h->Ns; M.z = h->z; M.n_col = h->n_col; M.nrep = h->R;
     for (int c = 0; c <= MAXC; c++) M.col_off[c] = h->col_off[c];
     for (int l = 0; l < NL; l++)
@@ -1212,6 +1213,8 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     A((void**)&h->lab, lb.size());
     A((void**)&h->d_orig, N * sizeof(int32_t));
     A((void**)&h->d_col_list, N * sizeof(int32_t));
+    A((void**)&h->d_cls_site, N * sizeof(int32_t));
+    A((void**)&h->d_cls_nbr, (size_t)h->z * N * sizeof(int32_t));
     A(&h->d_Jt, (size_t)MAXL * 256 * h->esz());
     A(&h->d_Jqt, (size_t)256 * h->esz());
     A(&h->beta, h->R * h->esz());
@@ -1227,6 +1230,15 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     C(cudaMemcpy(h->lab, lb.data(), lb.size(), cudaMemcpyHostToDevice));
     C(cudaMemcpy(h->d_orig, h->orig.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
     C(cudaMemcpy(h->d_col_list, col_list.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
+    {
+        std::vector<int32_t> cs_site(N), cs_nbr((size_t)h->z * N);
+        for (int64_t cp = 0; cp < N; cp++) {
+            cs_site[cp] = h->orig[col_list[cp]];
+            for (int k = 0; k < h->z; k++) cs_nbr[(size_t)k * N + cp] = nb[(size_t)k * N + col_list[cp]];
+        }
+        C(cudaMemcpy(h->d_cls_site, cs_site.data(), N * sizeof(int32_t), cudaMemcpyHostToDevice));
+        C(cudaMemcpy(h->d_cls_nbr, cs_nbr.data(), cs_nbr.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
     {
         std::vector<char> jt((size_t)MAXL * 256 * h->esz(), 0);
         for (int l = 0; l < n_labels; l++)
@@ -1266,7 +1278,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
 int32_t scmc_destroy(scmc_t* h) {
     if (!h) return SCMC_OK;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16};
+    void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16, h->d_cls_site, h->d_cls_nbr};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     delete h;

@@ -284,7 +284,7 @@ static DevModel<R, NL> make_model_d(const scmc_handle* h) {
     DevModel<R, NL> M;
     memset(&M, 0, sizeof M);
     M.psi = (vec4<R>*)h->psi; M.T = (vec4<R>*)h->T; M.Tsq = (vec4<R>*)h->Tsq;
-    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig; M.col_list = h->d_col_list;
+    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig; M.col_list = h->d_col_list; M.cls_site = h->d_cls_site; M.cls_nbr = h->d_cls_nbr;
     M.N = (int32_t)h->N; M.Ns = (int32_t)h->Ns; M.z = h->z; M.n_col = h->n_col; M.nrep = h->R;
     for (int c = 0; c <= MAXC; c++) M.col_off[c] = h->col_off[c];
     for (int l = 0; l < NL; l++)

@@ -189,14 +189,16 @@ def _emit_density(fname_acc, fname_map, g):
     tr = [f"template <class R> __device__ __forceinline__ void {fname_map.replace('expect_from_density', 'hq_from_field')}(const R* h, R* Hq) {{"]
     tr += [f"    Hq[{n}] = R(0){c};" for n, c in enumerate(col)] + ["}"]
     # e(psi) = sum_n Hq[n] P_n(psi) without materialising T
-    en = [f"template <class R> __device__ __forceinline__ R {fname_map.replace('expect_from_density', 'energy_from_state')}(const R* re, const R* im, const R* Hq) {{", "    R e = R(0);"]
+    en = [f"template <class R> __device__ __forceinline__ R {fname_map.replace('expect_from_density', 'energy_from_state')}(const R* re, const R* im, const R* Hq) {{",
+          "    R e0 = R(0), e1 = R(0), e2 = R(0), e3 = R(0);   // four partial sums: no 16-long dependent FMA chain"]
     for (j, k, part) in terms:
         n = idx[(j, k, part)]
+        part_sum = f"e{n % 4}"
         if part == "r":
-            en.append(f"    e = fma(Hq[{n}], fma(re[{j}], re[{k}], im[{j}] * im[{k}]), e);")
+            en.append(f"    {part_sum} = fma(Hq[{n}], fma(re[{j}], re[{k}], im[{j}] * im[{k}]), {part_sum});")
         else:
-            en.append(f"    e = fma(Hq[{n}], fma(re[{j}], im[{k}], -(im[{j}] * re[{k}])), e);")
-    en += ["    return e;", "}"]
+            en.append(f"    {part_sum} = fma(Hq[{n}], fma(re[{j}], im[{k}], -(im[{j}] * re[{k}])), {part_sum});")
+    en += ["    return (e0 + e1) + (e2 + e3);", "}"]
     return acc + mp + tr + en, len(terms)
 
 
