@@ -9,7 +9,9 @@ import torch
 J = np.diag([0, 0.2, 0.2, 0.2, -1, 0.2, 0.2, 0.2, -1, 0.2, 0.2, 0.2, -1, 0.2, 0.2, 0.2]).astype(float)
 cases = [("C1 honeycomb 6x6", "honeycomb", 6, 1, 4096, [np.eye(16)]), ("C1 single", "honeycomb", 6, 1, 1, [np.eye(16)]),
          ("C2 tri 48x48 x64T", "triangular", 48, 1, 64, [J]), ("C4 tri 36x36 x512", "triangular", 36, 1, 512, [J]),
-         ("C2 tri 48x48 x4096", "triangular", 48, 1, 4096, [J])]
+         ("C2 tri 48x48 x4096", "triangular", 48, 1, 4096, [J]),
+         ("C3 honeycomb 96x96 n=2 x256", "honeycomb", 96, 2, 256, [np.eye(16)]),
+         ("C3 n=2 with on-site K", "honeycomb", 96, 2, 256, [np.diag(np.r_[0.0, np.linspace(-0.2, 0.2, 15)]), np.eye(16)])]
 for name, lat, L, n, R, Js in cases:
     for mode in (1, 2, 3, 4):
         cfg = scmc.initializeCfg("nearest-neighbor", lat, Js, L, n, n_replicas=R, precision=32, seed=1)
