@@ -200,10 +200,10 @@ def run_ours(args):
     lib, h = cfg._lib, cfg._h
     N = cfg.nSites
     beta = 1.0 / Ts
-    sigma = np.clip(0.35 * np.sqrt(Ts), 0.02, 60.0)          # near-50 % acceptance cone widths (what the sigma rule converges to)
-    updates_per_step = R * N * args.hits * args.sweeps
-    # short thermalisation so that the timed steps run in the production regime (adapted sigma, ~50 % acceptance)
-    acc, att = cfg.sweep(6, beta, sigma, hits=args.hits)
+    # untimed thermalisation exactly as run! does it: cone width sigma starts at 60 and adapts towards 50 % acceptance
+    # (src/MonteCarlo.jl:17, 47-54); 48 sweeps with an adaptation every 2 sweeps, so the timed steps run in the production regime
+    therm = scmc.run_(cfg, None, Ts, np.full(R, 2.0), 48, 0, measurement_rate=2, hits=args.hits, keep_series=False)
+    sigma = therm["sigma"]
     sweep_ctr = cfg.sweep_counter
 
     def barrier():
