@@ -320,3 +320,20 @@ def test_device_side_annealing_equals_host_driven_loop(scmc, precision):
     assert np.array_equal(a.get_state(), b.get_state())
     assert np.array_equal(ra["E"], rb["E"])
     assert len(set(ra["sweeps"].tolist())) > 1 or ra["sweeps"][0] == 699      # replicas stop independently (or all hit N_max)
+
+
+@pytest.mark.parametrize("lattice,L", [("square", 5), ("cubic", 3), ("chain", 7), ("square", 4)])
+def test_other_lattices_follow_the_oracle_chain(scmc, oracle_mod, lattice, L):
+    """Neighbour counts that are not a multiple of 3 (padding slots -> zero site), odd sizes (greedy colouring), 1-D and 3-D
+    lattices: energies and the FP64 counter-based chain against the oracle."""
+    seed = 31415
+    cfg = scmc.initializeCfg("nearest-neighbor", lattice, [random_symmetric_J(5)], L, 1, n_replicas=2, precision=64, seed=seed, replica_offset=3)
+    o = make_oracle(cfg, oracle_mod)
+    o.randomize_v1(seed, 4)
+    assert np.allclose(cfg.get_state(1, 1)[0], o.get_state(), atol=1e-13)
+    assert abs(cfg.energies()[1] - o.energy()) < 1e-11 * cfg.nSites
+    acc, _ = cfg.sweep(4, np.array([1.0, 3.0]), np.array([0.5, 0.3]))
+    a = o.sweeps_colour_v1(4, 2, cfg.colour, 3.0, 0.3, seed, 4, 0)
+    assert acc[1] == a
+    assert np.allclose(cfg.get_state(1, 1)[0], o.get_state(), atol=1e-10)
+    assert abs(cfg.energies()[1] - o.energy()) < 1e-9 * cfg.nSites
