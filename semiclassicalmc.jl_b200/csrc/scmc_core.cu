@@ -1362,6 +1362,7 @@ int32_t scmc_randomize(scmc_t* h, uint64_t seed) {
         return SCMC_OK;
     }));
     SCMC_CK(cudaStreamSynchronize(h->stream));
+    h->T_stale = false;          // every replica's T cache was just rebuilt
     return SCMC_OK;
 }
 
