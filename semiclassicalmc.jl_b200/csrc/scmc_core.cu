@@ -1009,7 +1009,7 @@ int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t s
         const int64_t rc = std::min<int64_t>(batch, h->R - r0);
         // trailing colour classes that are small (seam repairs) are visited by one block per replica in a single launch
         int first_small = h->n_col;
-        while (first_small > 1 && h->col_off[first_small] - h->col_off[first_small - 1] <= 2 * SCMC_SWEEP_THREADS) first_small--;
+        while (first_small > 0 && h->col_off[first_small] - h->col_off[first_small - 1] <= 2 * SCMC_SWEEP_THREADS) first_small--;      // tiny lattices: the whole sweep is ONE launch
         if (first_small == h->n_col - 1) first_small = h->n_col;      // a single small class gains nothing
         for (int64_t s = 0; s < n_sweeps; s++)
             for (int c = 0; c < h->n_col; c++) {
