@@ -52,6 +52,19 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, uint32_
         } else if (MODE == 6) {   // 8 FADD (alu or fma pipe?)
             a0 += c; a1 += c; a2 += c; a3 += c; a4 += c; a5 += c; a6 += c; a7 += c;
             asm volatile("" : "+f"(a0), "+f"(a1), "+f"(a2), "+f"(a3), "+f"(a4), "+f"(a5), "+f"(a6), "+f"(a7));
+        } else if (MODE == 8) {   // 4 x (mul.lo + xor): 32-bit IMAD
+            x0 = (x0 * 0xD2511F53u) ^ x1; x1 = (x1 * 0xCD9E8D57u) ^ x2; x2 = (x2 * 0xD2511F53u) ^ x3; x3 = (x3 * 0xCD9E8D57u) ^ x0;
+        } else if (MODE == 9) {   // 4 x (mul.hi + xor): IMAD.HI
+            x0 = __umulhi(x0, 0xD2511F53u) ^ x1; x1 = __umulhi(x1, 0xCD9E8D57u) ^ x2; x2 = __umulhi(x2, 0xD2511F53u) ^ x3; x3 = __umulhi(x3, 0xCD9E8D57u) ^ x0;
+        } else if (MODE == 10) {  // 4 x (mul.wide.u16 + xor)
+            unsigned t0, t1, t2, t3;
+            asm volatile("mul.wide.u16 %0, %1, %2;" : "=r"(t0) : "h"((unsigned short)x0), "h"((unsigned short)0x1F53));
+            asm volatile("mul.wide.u16 %0, %1, %2;" : "=r"(t1) : "h"((unsigned short)x1), "h"((unsigned short)0x8D57));
+            asm volatile("mul.wide.u16 %0, %1, %2;" : "=r"(t2) : "h"((unsigned short)x2), "h"((unsigned short)0x1F53));
+            asm volatile("mul.wide.u16 %0, %1, %2;" : "=r"(t3) : "h"((unsigned short)x3), "h"((unsigned short)0x8D57));
+            x0 = t0 ^ x1; x1 = t1 ^ x2; x2 = t2 ^ x3; x3 = t3 ^ x0;
+        } else if (MODE == 11) {  // 8 LOP3/IADD only (ALU pipe reference)
+            x0 = (x0 ^ x1) + 0x9E3779B9u; x1 = (x1 ^ x2) + 0xBB67AE85u; x2 = (x2 ^ x3) + 0x9E3779B9u; x3 = (x3 ^ x0) + 0xBB67AE85u;
         } else if (MODE == 7) {   // 8 FFMA + 8 LOP3 (dual issue across pipes?)
             a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
             a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
@@ -85,5 +98,9 @@ int main() {
     run<5>("4 MUFU.EX2", 4, out);
     run<6>("8 FADD", 8, out);
     run<7>("8 FFMA + 4 LOP3 + 4 IADD", 16, out);
+    run<8>("4 IMAD.lo + 4 LOP", 8, out);
+    run<9>("4 IMAD.HI + 4 LOP", 8, out);
+    run<10>("4 mul.wide.u16 + 4 LOP", 8, out);
+    run<11>("4 LOP + 4 IADD", 8, out);
     return 0;
 }
