@@ -337,3 +337,26 @@ def test_other_lattices_follow_the_oracle_chain(scmc, oracle_mod, lattice, L):
     assert acc[1] == a
     assert np.allclose(cfg.get_state(1, 1)[0], o.get_state(), atol=1e-10)
     assert abs(cfg.energies()[1] - o.energy()) < 1e-9 * cfg.nSites
+
+
+def test_production_fp32_psi_family_matches_fp64_reference_arithmetic(scmc):
+    """Cross-family, cross-precision statistics: the production path (FP32, psi-gather kernels, SFU transcendentals, 24-bit
+    uniforms) against the reference-shaped arithmetic (FP64, T-gather kernels) on triangular 12x12 at three temperatures.
+    Independent chains (different seeds): energies, specific heats and |m_sigma| agree within their error bars."""
+    Ts = np.repeat([0.05, 0.3, 1.2], 24)
+    out = {}
+    for tag, precision, mode, seed in (("fp32_psi", 32, 0, 101), ("fp64_T", 64, 1, 202)):
+        cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 12, 1, n_replicas=len(Ts), precision=precision, seed=seed)
+        cfg.set_sweep_mode(mode)
+        res = scmc.run_(cfg, None, Ts, 2.0, 3000, 4000, measurement_rate=10)
+        m = res["mean"].reshape(3, 24, -1)
+        e = m[:, :, 0]
+        c = (m[:, :, 1] - e ** 2) * cfg.nSites / np.array([0.05, 0.3, 1.2])[:, None] ** 2
+        out[tag] = dict(e=(e.mean(1), e.std(1, ddof=1) / np.sqrt(24)), c=(c.mean(1), c.std(1, ddof=1) / np.sqrt(24)),
+                        ms=(m[:, :, 2].mean(1), m[:, :, 2].std(1, ddof=1) / np.sqrt(24)), acc=res["acc_rate"].reshape(3, 24).mean(1))
+    for key in ("e", "c", "ms"):
+        a, b = out["fp32_psi"][key], out["fp64_T"][key]
+        z = np.abs(a[0] - b[0]) / np.hypot(a[1], b[1])
+        assert np.all(z < 5.0), (key, a, b, z)
+    assert np.all(np.abs(out["fp32_psi"]["acc"] - out["fp64_T"]["acc"]) < 0.05)
+    assert abs(out["fp32_psi"]["e"][0][0] - (-3.6 + 3 * 0.05)) < 0.01          # low-T equipartition anchor
