@@ -99,4 +99,6 @@ int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint
 // implemented in scmc_resident.cu
 void plan_resident(scmc_handle* h, const std::vector<int>& owner_of_perm);
 int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active, bool psi);
+int32_t launch_resident_run(scmc_handle* h, int mode, int64_t chunk, int32_t hits, uint64_t seed, const double* d_T, const double* d_Ti,
+                            int64_t n_anneal, int64_t rate, int64_t sweep_first, int64_t row_base, double* d_rows);
 }  // namespace scmc

@@ -355,9 +355,21 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
         SCMC_CK(cudaGetLastError());
         return SCMC_OK;
     };
+    // Device-side driver: when every replica lives in ONE CTA of the psi-family resident kernel, the whole schedule (beta ramp, sigma
+    // adaptation, measurement rows) runs inside the persistent kernel, up to 512 sweeps per launch; chains are identical to the
+    // host-driven path below, measurement rows agree to rounding (energies re-summed from the resident states).
+    const bool device_side = uses_psi_gather(h) && h->res.eligible_psi && h->res.cs == 1 && (h->sweep_mode == 0 || h->sweep_mode == 4) &&
+                             !out->therm_energy;
     // ---- thermalisation (MonteCarlo.jl:38-66)
     int64_t n_log = 0;
-    for (int64_t sweep = (int64_t)p->sweep0 + 1; sweep <= p->n_therm; sweep++) {
+    if (device_side) {
+        for (int64_t sweep = (int64_t)p->sweep0 + 1; sweep <= p->n_therm;) {
+            const int64_t chunk = std::min<int64_t>(512, p->n_therm - sweep + 1);
+            SCMC_TRY(launch_resident_run(h, 1, chunk, p->hits, p->seed, dT.as<double>(), dTi.as<double>(), n_anneal, rate, sweep, 0, nullptr));
+            sweep += chunk;
+        }
+    }
+    for (int64_t sweep = (int64_t)p->sweep0 + 1; !device_side && sweep <= p->n_therm; sweep++) {
         SCMC_TRY(set_beta(sweep));
         int64_t n_batch = 1;
         if (sweep > n_anneal) {      // ramp finished: beta constant, batch up to the next sigma-adaptation point
@@ -395,7 +407,29 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
         in_chunk = 0;
         return SCMC_OK;
     };
-    for (int64_t sweep = meas_start; sweep <= total; sweep++) {
+    if (device_side) {
+        const int64_t row_base0 = (meas_start - 1) / rate + 1;        // g / rate of the first measurement row
+        for (int64_t sweep = meas_start; sweep <= total;) {
+            // a launch covers whole measurement intervals, at most chunk_rows rows and 512 sweeps
+            int64_t last = std::min<int64_t>(total, sweep + 511);
+            const int64_t rows_here_max = chunk_rows - in_chunk;
+            const int64_t first_row_g = ((sweep + rate - 1) / rate) * rate;
+            if (first_row_g <= last) {
+                const int64_t n_rows_possible = (last - first_row_g) / rate + 1;
+                if (n_rows_possible > rows_here_max) last = first_row_g + (rows_here_max - 1) * rate;
+            }
+            const int64_t chunk = last - sweep + 1;
+            const int64_t n_rows_here = last >= first_row_g ? (last - first_row_g) / rate + 1 : 0;
+            // rows of this launch land behind the `in_chunk` rows already waiting in the device buffer
+            SCMC_TRY(launch_resident_run(h, 2, chunk, p->hits, p->seed, dT.as<double>(), dTi.as<double>(), n_anneal, rate, sweep,
+                                         row_base0 + rows - in_chunk, dser.as<double>()));
+            n_meas_sweeps += chunk;
+            in_chunk += n_rows_here; rows += n_rows_here;
+            sweep = last + 1;
+            if (in_chunk == chunk_rows) SCMC_TRY(flush());
+        }
+    }
+    for (int64_t sweep = meas_start; !device_side && sweep <= total; sweep++) {
         // beta and sigma are frozen here: all sweeps up to the next measurement point go out as ONE call (one launch of the
         // replica-resident kernel when it applies)
         const int64_t next_stop = std::min<int64_t>(total, ((sweep + rate - 1) / rate) * rate);

@@ -37,6 +37,13 @@ struct ResidentArgs {
     int64_t *sweeps_at_T, *sweeps_done;
     uint8_t* active_rw;
     int* n_active;                  // out: replicas still running after this launch
+    // device-side run! schedule (src/MonteCarlo.jl:38-99); single-CTA replicas only.  run_mode 1 = thermalisation chunk (beta ramp
+    // per sweep, sigma adaptation every `rate` sweeps), 2 = measurement chunk (beta, sigma frozen; measure! row every `rate` sweeps)
+    int32_t run_mode;
+    const double *run_T, *run_Ti;   // [R]
+    int64_t n_anneal, rate, sweep_first, row_base;   // sweep_first: 1-based index of this launch's first sweep; row = g / rate - row_base
+    double att_window, e_const;     // attempts between two adaptations; constant on-site energy
+    double* rows;                   // [rows of this launch][R][SCMC_NOBS]
 };
 
 // ---- shared-memory / DSMEM access helpers -----------------------------------------------------------------------------
@@ -215,6 +222,7 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
     R* sJt = reinterpret_cast<R*>(sPsi + NPV * cap);              // [16][16]
     uint16_t* sNbr = reinterpret_cast<uint16_t*>(sJt + NG * NG);  // [z][nmax]
     __shared__ unsigned s_acc;
+    __shared__ double s_red[16][NG + 1];                          // measurement reduction (one row per warp)
     unsigned rank = 0, cluster_id = blockIdx.x;
     if (CLUSTER) {
         rank = cg::this_cluster().block_rank();
@@ -247,11 +255,24 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
         int64_t an_done = anneal ? A.sweeps_done[r] : 0, an_sat = anneal ? A.sweeps_at_T[r] : 0;
         double an_acc = anneal ? (double)A.acc[r] : 0.0;
         bool an_still = true;
+        // run! schedule of this replica
+        const int run = CLUSTER ? 0 : A.run_mode;
+        double run_acc = run ? (double)A.acc[r] : 0.0;
+        const double run_T = run == 1 ? A.run_T[r] : 1.0, run_Ti = run == 1 ? A.run_Ti[r] : 1.0;
         if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
         unsigned nacc = 0;
         for (int sweep = 0; sweep < A.n_sweeps && an_still; sweep++) {
             if (anneal && an_done >= A.n_total) break;
-            const uint64_t visit_base = anneal ? (uint64_t)an_done * (uint64_t)A.hits : A.visit0 + (uint64_t)sweep * (uint64_t)A.hits;
+            const int64_t g = A.sweep_first + sweep;               // 1-based global sweep index (run modes)
+            if (run == 1) {                                        // geometric ramp T_i -> T over the first n_anneal sweeps (MonteCarlo.jl:24-27)
+                double t = run_T;
+                if (g <= A.n_anneal && A.n_anneal > 1) t = run_Ti * pow(run_T / run_Ti, (double)(g - 1) / (double)(A.n_anneal - 1));
+                beta = (R)(1.0 / t);
+                nbeta = neg_beta_scaled(beta);
+            }
+            const uint64_t visit_base = anneal ? (uint64_t)an_done * (uint64_t)A.hits
+                                        : run  ? (uint64_t)(g - 1) * (uint64_t)A.hits
+                                               : A.visit0 + (uint64_t)sweep * (uint64_t)A.hits;
             unsigned sweep_acc = 0;
             for (int c = 0; c < M.n_col; c++) {
                 const int c0 = A.cta_col_off[rank][c], cnt = A.cta_col_off[rank][c + 1] - c0;
@@ -315,7 +336,102 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                 }
                 if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
             }
-            if (!anneal) {
+            if (run) {
+                const unsigned wt = __reduce_add_sync(0xffffffffu, sweep_acc);
+                if ((tid & 31) == 0 && wt) atomicAdd(&s_acc, wt);
+                __syncthreads();
+                run_acc += (double)s_acc;
+                __syncthreads();
+                if (tid == 0) s_acc = 0;
+                if (g % A.rate == 0) {
+                    if (run == 1) {                                // sigma <- min(sigma * 0.5 / (1 - R), 60)  (MonteCarlo.jl:50-53)
+                        const double ratio = run_acc / A.att_window;
+                        sigma = (R)fmin((double)sigma * 0.5 / (1.0 - ratio), 60.0);
+                        run_acc = 0.0;
+                    } else {                                       // measure! (ObservablesGeneric.jl:32-46) straight from the resident states
+                        float eacc = 0.f, macc[NG];
+#pragma unroll
+                        for (int t = 0; t < NG; t++) macc[t] = 0.f;
+                        for (int q = tid; q < n_own; q += nth) {
+                            R re[D], im[D], h[NG], P[NP];
+                            load_psi<R, D>(sPsi + q, (size_t)cap, re, im);
+#pragma unroll
+                            for (int t = 0; t < NP; t++) P[t] = R(0);
+                            for (int k = 0; k < M.z; k++) {
+                                const unsigned code = sNbr[k * nmax + q];
+                                const uint32_t addr = sPsi_u32 + (code & 0x1FFFu) * (uint32_t)sizeof(V);
+                                R nr[D], ni[D];
+#pragma unroll
+                                for (int v = 0; v < NPV; v++) {
+                                    const V w4 = ld_v4<false>(addr + v * plane_bytes, R(0));
+                                    nr[2 * v] = w4.x; ni[2 * v] = w4.y; nr[2 * v + 1] = w4.z; ni[2 * v + 1] = w4.w;
+                                }
+                                GenOps<GEN>::density_acc(nr, ni, P);
+                            }
+                            if (!fused) {
+                                R S[1][NG];
+                                GenOps<GEN>::expect_from_density(P, S[0]);
+                                field_from_sums_smem<1>(sJt, S, h);
+                                R T[NG];
+                                GenOps<GEN>::expect(re, im, T);
+                                R e = R(0);
+#pragma unroll
+                                for (int t = 0; t < NG; t++) e = fma(T[t], h[t], e);
+                                e *= R(0.5);
+                                if (ONSITE) {
+                                    R Tsq[NG];
+                                    GenOps<GEN>::expect_sq(re, im, Tsq);
+#pragma unroll
+                                    for (int t = 0; t < NG; t++) e = fma(Tsq[t], M.cp.K[t], e);
+                                }
+                                eacc += (float)e;
+#pragma unroll
+                                for (int t = 0; t < NG; t++) macc[t] += (float)T[t];
+                            } else if constexpr (NP == NG) {
+                                field_from_sums_smem<1>(sJt, (const R(*)[NG])P, h);           // h = Hq
+                                eacc += 0.5f * (float)GenOps<GEN>::energy_from_state(re, im, h);
+                                R Pown[NP];
+#pragma unroll
+                                for (int t = 0; t < NP; t++) Pown[t] = R(0);
+                                GenOps<GEN>::density_acc(re, im, Pown);
+#pragma unroll
+                                for (int t = 0; t < NG; t++) macc[t] += (float)Pown[t];
+                            }
+                        }
+                        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+                        for (int t = 0; t <= NG; t++) {
+                            double v = t < NG ? (double)macc[t < NG ? t : 0] : (double)eacc;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                            if (lane == 0) s_red[warp][t] = v;
+                        }
+                        __syncthreads();
+                        if (tid == 0) {
+                            double tot[NG + 1], Tsum[NG];
+                            for (int t = 0; t <= NG; t++) {
+                                double v = 0.0;
+                                for (int w = 0; w < (nth >> 5); w++) v += s_red[w][t];
+                                tot[t] = v;
+                            }
+                            if (fused) GenOps<GEN>::expect_from_density(tot, Tsum);           // magnetisation is linear in the density sums
+                            else for (int t = 0; t < NG; t++) Tsum[t] = tot[t];
+                            const double E = tot[NG] + A.e_const, invN = 1.0 / (double)M.N;
+                            double* row = A.rows + ((size_t)(g / A.rate - A.row_base) * A.nrep + r) * SCMC_NOBS;
+                            double m[NG];
+                            for (int t = 0; t < NG; t++) m[t] = Tsum[t] * invN;
+                            row[0] = E * invN;
+                            row[1] = (E * invN) * (E * invN);
+                            row[2] = sqrt(m[4] * m[4] + m[8] * m[8] + m[12] * m[12]);
+                            row[3] = sqrt(m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
+                            row[4] = sqrt(m[5] * m[5] + m[6] * m[6] + m[7] * m[7] + m[9] * m[9] + m[10] * m[10] + m[11] * m[11] + m[13] * m[13] +
+                                          m[14] * m[14] + m[15] * m[15]);
+                            for (int t = 0; t < NG; t++) row[5 + t] = m[t];
+                        }
+                        __syncthreads();
+                    }
+                }
+            } else if (!anneal) {
                 nacc += sweep_acc;
             } else {
                 // accepted updates of this sweep over the whole replica, then the cooling rule (MonteCarlo.jl:151-203)
@@ -344,6 +460,14 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
         for (int q = tid; q < n_own; q += nth) {
 #pragma unroll
             for (int v = 0; v < NPV; v++) M.psi[gbase + q + v * ps] = sPsi[v * cap + q];
+        }
+        if (run) {
+            if (tid == 0) {
+                ((R*)A.sigma)[r] = sigma;
+                A.acc[r] = (unsigned long long)run_acc;
+            }
+            __syncthreads();
+            continue;
         }
         if (anneal) {
             if (tid == 0) {
@@ -561,6 +685,39 @@ int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint
             A.anneal = 1; A.att_per_sweep = att_per_sweep; A.min_accepted = min_accepted; A.beta_fac = beta_fac; A.min_accrate = min_accrate;
             A.sigma_min = sigma_min; A.n_per_T = n_per_T; A.n_total = n_total; A.sweeps_at_T = d_sweeps_at_T; A.sweeps_done = d_sweeps_done;
             A.active_rw = h->active; A.n_active = d_n_active;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)A.n_clusters); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem_psi; cfg.stream = h->stream;
+            cfg.attrs = nullptr; cfg.numAttrs = 0;
+            SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, false>, M, A));
+            h->launches++;
+            return SCMC_OK;
+        }
+    });
+}
+
+
+// One chunk of the device-side run! schedule (single-CTA psi-family replicas): mode 1 = thermalisation, 2 = measurement.
+int32_t launch_resident_run(scmc_handle* h, int mode, int64_t chunk, int32_t hits, uint64_t seed, const double* d_T, const double* d_Ti,
+                            int64_t n_anneal, int64_t rate, int64_t sweep_first, int64_t row_base, double* d_rows) {
+    auto& P = h->res;
+    h->T_stale = true;
+    return dispatch_r(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
+        using R = decltype(rt);
+        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
+        constexpr bool ONS = decltype(ons)::value != 0;
+        if constexpr (NL != 1) { return SCMC_ERR_UNSUPPORTED; } else {
+            auto M = make_model_r<R, NL>(h);
+            ResidentArgs A;
+            memset(&A, 0, sizeof A);
+            A.nrep = h->R; A.roff = h->roff; A.hits = hits; A.cs = P.cs; A.n_own_max = P.n_own_max; A.cap = P.cap;
+            A.seed = seed; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.Jqt = h->fused_density ? h->d_Jqt : nullptr;
+            A.active = nullptr; A.acc = h->acc; A.nbr16 = h->d_nbr16;
+            memcpy(A.cta_off, P.cta_off, sizeof A.cta_off);
+            memcpy(A.cta_col_off, P.cta_col_off, sizeof A.cta_col_off);
+            A.n_clusters = (int32_t)std::min<int64_t>(h->R, P.max_clusters_psi);
+            A.n_sweeps = (int32_t)chunk;
+            A.run_mode = mode; A.run_T = d_T; A.run_Ti = d_Ti; A.n_anneal = n_anneal; A.rate = rate; A.sweep_first = sweep_first; A.row_base = row_base;
+            A.att_window = (double)hits * (double)h->N * (double)rate; A.e_const = h->e_const; A.rows = d_rows;
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3((unsigned)A.n_clusters); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem_psi; cfg.stream = h->stream;
             cfg.attrs = nullptr; cfg.numAttrs = 0;

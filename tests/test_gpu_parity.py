@@ -360,3 +360,27 @@ def test_production_fp32_psi_family_matches_fp64_reference_arithmetic(scmc):
         assert np.all(z < 5.0), (key, a, b, z)
     assert np.all(np.abs(out["fp32_psi"]["acc"] - out["fp64_T"]["acc"]) < 0.05)
     assert abs(out["fp32_psi"]["e"][0][0] - (-3.6 + 3 * 0.05)) < 0.01          # low-T equipartition anchor
+
+
+@pytest.mark.parametrize("precision", [32, 64])
+def test_device_side_run_equals_host_driven_schedule(scmc, precision):
+    """run! inside the persistent resident kernel (beta ramp, sigma adaptation, measure! rows) vs the host-driven loop: identical
+    chains (states, adapted sigma, acceptance), measurement rows equal to rounding (E re-summed from the resident states)."""
+    R = 10
+    Ts = np.geomspace(0.05, 1.5, R)
+    mk = lambda: scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 12, 1, n_replicas=R, precision=precision, seed=2468)
+    a = mk(); a.set_sweep_mode(3)              # streaming psi-gather kernel, host-driven schedule
+    ra = scmc.run_(a, None, Ts, 2.0, 230, 345, measurement_rate=10)
+    b = mk()                                   # auto: single-CTA resident psi kernel, device-side schedule
+    assert b.info()["resident_psi"] and b.info()["cluster"] == 1
+    rb = scmc.run_(b, None, Ts, 2.0, 230, 345, measurement_rate=10)
+    assert ra["rows"] == rb["rows"] == 34
+    assert np.array_equal(ra["sigma"], rb["sigma"]) and np.array_equal(ra["acc_rate"], rb["acc_rate"])
+    assert np.array_equal(a.get_state(), b.get_state())
+    tol = 1e-10 if precision == 64 else 2e-5
+    assert np.allclose(ra["series"], rb["series"], rtol=tol, atol=tol)
+    assert np.allclose(ra["mean"], rb["mean"], rtol=tol, atol=tol)
+    # a resumed run (current_sweep) continues both paths identically
+    ra2 = scmc.run_(a, None, Ts, 2.0, 230, 500, measurement_rate=10, current_sweep=575, σ=ra["sigma"])
+    rb2 = scmc.run_(b, None, Ts, 2.0, 230, 500, measurement_rate=10, current_sweep=575, σ=rb["sigma"])
+    assert ra2["rows"] == rb2["rows"] and np.array_equal(a.get_state(), b.get_state())
