@@ -301,7 +301,9 @@ def run_ours(args):
                            "cache_note": f"state {info['device_bytes'] / 2**30:.1f} GiB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
                            "acceptance_rate": acc_rate, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                             "updates_per_site_per_launch": args.hits, "launch_us": launch_s * 1e6},
+                             "updates_per_site_per_launch": args.hits, "launch_us": launch_s * 1e6,
+                             "note": "issue/FMA-pipe bound, not HBM bound: ncu (profiles/r01_ncu_full_k_sweep_colour_psi.txt) shows 67 % issue-slot "
+                                     "utilisation, 55 % FMA pipe, DRAM 2.3 TB/s, ~1150-1270 warp-instructions per site visit"},
                 "e2e": {"value": e2e_value, "unit": "site-updates/s", "h2d_bytes_per_step": int(2 * R * w) * world,
                         "d2h_bytes_per_step": int(R * 8 + R * _lib.NOBS * 8) * world, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks}

@@ -1069,7 +1069,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     SCMC_ARG(out != nullptr, "scmc_create: null handle pointer");
     *out = nullptr;
     SCMC_ARG(precision == 32 || precision == 64, "scmc_create: precision must be 32 or 64");
-    SCMC_ARG(n_sites > 0 && n_sites < (1ll << 30), "scmc_create: n_sites out of range");
+    SCMC_ARG(n_sites > 0 && n_sites <= (1ll << 27), "scmc_create: n_sites out of range (1 .. 2^27)");
     SCMC_ARG(n_replicas > 0, "scmc_create: n_replicas must be positive");
     SCMC_ARG(z_max > 0 && nbr_site && nbr_label, "scmc_create: neighbour tables required");
     SCMC_ARG(n_labels >= 1 && n_labels <= MAXL, "scmc_create: 1..3 coupling labels supported");

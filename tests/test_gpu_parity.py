@@ -384,3 +384,20 @@ def test_device_side_run_equals_host_driven_schedule(scmc, precision):
     ra2 = scmc.run_(a, None, Ts, 2.0, 230, 500, measurement_rate=10, current_sweep=575, σ=ra["sigma"])
     rb2 = scmc.run_(b, None, Ts, 2.0, 230, 500, measurement_rate=10, current_sweep=575, σ=rb["sigma"])
     assert ra2["rows"] == rb2["rows"] and np.array_equal(a.get_state(), b.get_state())
+
+
+def test_more_replicas_than_the_grid_y_limit(scmc):
+    """70 000 replicas of a tiny lattice: launches are chunked over the 65 535 gridDim.y limit, and a replica beyond the boundary
+    follows exactly the chain of a single-replica handle with the same global id."""
+    R = 70000
+    big = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 3, 1, n_replicas=R, precision=32, seed=7)
+    big.set_sweep_mode(3)
+    acc, att = big.sweep(3, 2.0, 0.4)
+    assert np.all(att == 3 * 2 * 9) and acc.min() > 0
+    for rid in (65534, 65535, 69999):
+        one = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 3, 1, n_replicas=1, precision=32, seed=7, replica_offset=rid)
+        one.set_sweep_mode(3)
+        a1, _ = one.sweep(3, 2.0, 0.4)
+        assert a1[0] == acc[rid]
+        assert np.array_equal(one.get_state()[0], big.get_state(rid, 1)[0])
+    assert np.isfinite(big.energies()).all() and big.measure().shape == (R, 21)
