@@ -943,7 +943,8 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
             // CTAs per replica: up to SCMC_SWEEP_TILES site tiles per CTA (coupling table staged once per CTA), but never fewer
             // than ~8 waves of CTAs over the chip, so small replica counts (8-GPU shards) do not end in a long tail
             unsigned bpr = (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES;
-            const unsigned min_bpr = (unsigned)((6000 + B.rcount - 1) / B.rcount);
+            static const long min_blocks = getenv("SCMC_MIN_BLOCKS") ? atol(getenv("SCMC_MIN_BLOCKS")) : 6000;
+            const unsigned min_bpr = (unsigned)((min_blocks + B.rcount - 1) / B.rcount);
             bpr = std::min(tiles, std::max(bpr, min_bpr));
             const dim3 grid(A.colour_last > A.colour ? 1u : bpr, (unsigned)B.rcount);
             if (A.inj_xi) {
