@@ -96,6 +96,11 @@ int32_t scmc_sweep_async(scmc_t* h, int64_t n_sweeps, int32_t hits, uint64_t see
  * bit-identical chains; the two families differ by rounding.  Auto picks the family from the model alone (never from the replica
  * count), so sharding replicas over GPUs cannot change a chain.  batch = replicas per batch for the streaming path (0 = all). */
 int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch);
+/* Replica lanes of the streaming kernels: 0 = auto (two lanes whenever a call is a chain of several launches), 1 = everything on
+ * the handle's stream, 2 = the replicas of a call are split over two internal side streams that fork from / join into the
+ * handle's stream, so the tail of one lane's colour pass is filled by the other lane's next pass.  Replicas never interact:
+ * chains are bit-identical for every setting (no reference counterpart -- the reference runs one chain per process). */
+int32_t scmc_set_lanes(scmc_t* h, int32_t lanes);
 
 /* ---- observables (measure!, ObservablesGeneric.jl:32-46; getMagnetization, Observables.jl:16-18) -------------------- */
 /* obs [R][SCMC_NOBS]; E is re-summed from the configuration */

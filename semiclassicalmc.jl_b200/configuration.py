@@ -119,6 +119,10 @@ class Configuration:
         """0 auto | 1 streaming T-gather | 2 resident T-gather | 3 streaming psi-gather | 4 resident psi-gather (include/scmc.h)."""
         _lib.check(self._lib.scmc_set_sweep_mode(self._h, mode, batch))
 
+    def set_lanes(self, lanes=0):
+        """0 auto | 1 one stream | 2 two replica lanes on side streams (streaming kernels; chains unchanged)."""
+        _lib.check(self._lib.scmc_set_lanes(self._h, lanes))
+
     def sweep(self, n_sweeps, beta, sigma, hits=2, want_counts=True):
         """n_sweeps colour-ordered sweeps of every replica (the 2N-update loops, MonteCarlo.jl:40-44)."""
         beta = np.broadcast_to(np.asarray(beta, dtype=np.float64), (self.n_replicas,)).copy()

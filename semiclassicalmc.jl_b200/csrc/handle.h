@@ -82,6 +82,11 @@ struct scmc_handle {
         int cta_col_off[16][scmc::MAXC + 1] = {{0}};   // local offsets of the colour classes inside a chunk
     } res;
     int64_t batch = 0;
+    // replica lanes of the streaming path: the replicas of a call are split over side streams so that the tail of one lane's
+    // colour pass overlaps with the other lane's next pass (colour passes of different replicas are independent)
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+    int32_t lanes = 0;                           // 0 = auto, 1 = single stream, 2 = two lanes
     size_t esz() const { return prec == 64 ? 8 : 4; }
 };
 

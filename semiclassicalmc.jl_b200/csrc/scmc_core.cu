@@ -923,9 +923,9 @@ int32_t ensure_T(scmc_handle* h) {
     });
 }
 
-static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
+static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A, cudaStream_t stream, int lanes = 1) {
     const bool psi = !A.inj_xi && uses_psi_gather(h);
-    if (!psi) SCMC_TRY(ensure_T(h));
+    if (!psi && stream == h->stream) SCMC_TRY(ensure_T(h));      // lanes: the caller refreshed T on h->stream before forking
     return dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
@@ -941,14 +941,16 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
             B.Jqt = h->fused_density ? h->d_Jqt : nullptr;
             const unsigned tiles = grid_for(nc, SCMC_SWEEP_THREADS);
             // CTAs per replica: up to SCMC_SWEEP_TILES site tiles per CTA (coupling table staged once per CTA), but never fewer
-            // than ~8 waves of CTAs over the chip, so small replica counts (8-GPU shards) do not end in a long tail
+            // than a few waves of CTAs over the chip, so small replica counts (8-GPU shards) do not end in a long tail.
+            // Measured on B200 (profiles/README.md): 6000 CTAs per launch on one stream, 1500 per lane with two lanes.
             unsigned bpr = (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES;
-            static const long min_blocks = getenv("SCMC_MIN_BLOCKS") ? atol(getenv("SCMC_MIN_BLOCKS")) : 6000;
+            static const long min_blocks_env = getenv("SCMC_MIN_BLOCKS") ? atol(getenv("SCMC_MIN_BLOCKS")) : 0;
+            const long min_blocks = min_blocks_env ? min_blocks_env / lanes : (lanes == 2 ? 1500 : 6000);
             const unsigned min_bpr = (unsigned)((min_blocks + B.rcount - 1) / B.rcount);
             bpr = std::min(tiles, std::max(bpr, min_bpr));
             const dim3 grid(A.colour_last > A.colour ? 1u : bpr, (unsigned)B.rcount);
             if (A.inj_xi) {
-                k_sweep_colour<R, GEN, ONS, NL, true><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+                k_sweep_colour<R, GEN, ONS, NL, true><<<grid, SCMC_SWEEP_THREADS, 0, stream>>>(M, B);
             } else if (psi) {
                 if constexpr (NL == 1) {
                     bool launched = false;
@@ -956,11 +958,11 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
                         if (h->z <= ASYNC_Z && h->async_pipeline) {
                             const size_t smem = (size_t)(h->z + 1) * (GenOps<GEN>::D / 2) * SCMC_SWEEP_THREADS * sizeof(float4);
                             SCMC_CK(cudaFuncSetAttribute(k_sweep_colour_psi_async<GEN, ONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                            k_sweep_colour_psi_async<GEN, ONS><<<grid, SCMC_SWEEP_THREADS, smem, h->stream>>>(M, B);
+                            k_sweep_colour_psi_async<GEN, ONS><<<grid, SCMC_SWEEP_THREADS, smem, stream>>>(M, B);
                             launched = true;
                         }
                     }
-                    if (!launched) k_sweep_colour_psi<R, GEN, ONS><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+                    if (!launched) k_sweep_colour_psi<R, GEN, ONS><<<grid, SCMC_SWEEP_THREADS, 0, stream>>>(M, B);
                 }
                 h->T_stale = true;
             } else if constexpr (std::is_same<R, float>::value && NL == 1) {
@@ -970,12 +972,12 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A) {
                     SCMC_CK(cudaFuncSetAttribute(k_sweep_colour_async<GEN, ONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
                     const unsigned tiles2 = grid_for(nc, SCMC_ASYNC_THREADS);
                     const dim3 g2(A.colour_last > A.colour ? 1u : (tiles2 + SCMC_ASYNC_TILES - 1) / SCMC_ASYNC_TILES, (unsigned)B.rcount);
-                    k_sweep_colour_async<GEN, ONS><<<g2, SCMC_ASYNC_THREADS, smem, h->stream>>>(M, B);
+                    k_sweep_colour_async<GEN, ONS><<<g2, SCMC_ASYNC_THREADS, smem, stream>>>(M, B);
                 } else {
-                    k_sweep_colour<R, GEN, ONS, NL, false><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+                    k_sweep_colour<R, GEN, ONS, NL, false><<<grid, SCMC_SWEEP_THREADS, 0, stream>>>(M, B);
                 }
             } else {
-                k_sweep_colour<R, GEN, ONS, NL, false><<<grid, SCMC_SWEEP_THREADS, 0, h->stream>>>(M, B);
+                k_sweep_colour<R, GEN, ONS, NL, false><<<grid, SCMC_SWEEP_THREADS, 0, stream>>>(M, B);
             }
             h->launches++;
         }
@@ -1006,22 +1008,51 @@ int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t s
         if (want_resident && !psi && h->res.eligible) { SCMC_TRY(ensure_T(h)); return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active, false); }
     }
     const int64_t batch = h->batch > 0 ? std::min<int64_t>(h->batch, h->R) : h->R;
+    if (!uses_psi_gather(h)) SCMC_TRY(ensure_T(h));      // on h->stream, before any lane forks
     for (int64_t r0 = 0; r0 < h->R; r0 += batch) {
         const int64_t rc = std::min<int64_t>(batch, h->R - r0);
         // trailing colour classes that are small (seam repairs) are visited by one block per replica in a single launch
         int first_small = h->n_col;
         while (first_small > 0 && h->col_off[first_small] - h->col_off[first_small - 1] <= 2 * SCMC_SWEEP_THREADS) first_small--;      // tiny lattices: the whole sweep is ONE launch
         if (first_small == h->n_col - 1) first_small = h->n_col;      // a single small class gains nothing
-        for (int64_t s = 0; s < n_sweeps; s++)
-            for (int c = 0; c < h->n_col; c++) {
+        // two replica lanes on side streams when a call is a chain of several dependent launches: every launch ends in a tail
+        // of partially filled SMs, which the other lane's launches fill (replicas never interact)
+        static const int lanes_env = getenv("SCMC_LANES") ? atoi(getenv("SCMC_LANES")) : 0;
+        int lanes = h->lanes ? h->lanes : (lanes_env ? lanes_env : 2);
+        const int64_t n_launch = n_sweeps * (first_small < h->n_col ? first_small + 1 : h->n_col);
+        if (rc < 2 || n_launch < 2 || !h->lane_stream[0]) lanes = 1;
+        cudaStream_t st[2] = {h->stream, h->stream};
+        int64_t lane_r0[2] = {r0, r0}, lane_rc[2] = {rc, 0};
+        if (lanes == 2) {
+            lane_rc[0] = rc / 2; lane_r0[1] = r0 + lane_rc[0]; lane_rc[1] = rc - lane_rc[0];
+            SCMC_CK(cudaEventRecord(h->ev_fork, h->stream));
+            for (int l = 0; l < 2; l++) {
+                st[l] = h->lane_stream[l];
+                SCMC_CK(cudaStreamWaitEvent(st[l], h->ev_fork, 0));
+            }
+        }
+        int32_t status = SCMC_OK;
+        for (int64_t s = 0; s < n_sweeps && status == SCMC_OK; s++)
+            for (int c = 0; c < h->n_col && status == SCMC_OK; c++) {
                 SweepArgs A{};
-                A.colour = c; A.colour_last = c; A.hits = hits; A.r0 = r0; A.rcount = rc;
+                A.colour = c; A.colour_last = c; A.hits = hits;
                 if (c >= first_small) { A.colour_last = h->n_col - 1; }
                 A.visit0 = (sweep_counter + (uint64_t)s) * (uint64_t)hits; A.seed = seed; A.roff = h->roff;
                 A.beta = h->beta; A.sigma = h->sigma; A.active = active; A.acc = h->acc;
-                SCMC_TRY(launch_colour_pass(h, A));
+                for (int l = 0; l < lanes && status == SCMC_OK; l++) {
+                    A.r0 = lane_r0[l]; A.rcount = lane_rc[l];
+                    status = launch_colour_pass(h, A, st[l], lanes);
+                }
                 if (A.colour_last > c) c = A.colour_last;
             }
+        if (lanes == 2) {                                 // join even after a failed launch: h->stream must not run ahead of the lanes
+            for (int l = 0; l < 2; l++) {
+                cudaError_t e = cudaEventRecord(h->ev_join[l], st[l]);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->ev_join[l], 0);
+                if (e != cudaSuccess && status == SCMC_OK) status = cuda_fail(e, "lane join", __FILE__, __LINE__);
+            }
+        }
+        SCMC_TRY(status);
     }
     return SCMC_OK;
 }
@@ -1271,6 +1302,12 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     C(cudaMemset(h->acc, 0, h->R * sizeof(unsigned long long)));
     C(cudaMemset(h->active, 1, h->R));
     if (ce != cudaSuccess) { scmc_destroy(h); return cuda_fail(ce, "scmc_create upload", __FILE__, __LINE__); }
+    for (int l = 0; l < 2; l++) {
+        C(cudaStreamCreateWithFlags(&h->lane_stream[l], cudaStreamNonBlocking));
+        C(cudaEventCreateWithFlags(&h->ev_join[l], cudaEventDisableTiming));
+    }
+    C(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    if (ce != cudaSuccess) { scmc_destroy(h); return cuda_fail(ce, "scmc_create lanes", __FILE__, __LINE__); }
     plan_resident(h, owner_of_perm);     // neighbour codes, launch geometry, eligibility of the replica-resident kernel
     *out = h;
     return SCMC_OK;
@@ -1282,6 +1319,11 @@ int32_t scmc_destroy(scmc_t* h) {
     void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16, h->d_cls_site, h->d_cls_nbr};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (int l = 0; l < 2; l++) {
+        if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
+        if (h->ev_join[l]) cudaEventDestroy(h->ev_join[l]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
     return SCMC_OK;
 }
@@ -1289,6 +1331,13 @@ int32_t scmc_destroy(scmc_t* h) {
 int32_t scmc_set_stream(scmc_t* h, void* s) {
     SCMC_ARG(h, "null handle");
     h->stream = (cudaStream_t)s;
+    return SCMC_OK;
+}
+
+int32_t scmc_set_lanes(scmc_t* h, int32_t lanes) {
+    SCMC_ARG(h, "null handle");
+    SCMC_ARG(lanes >= 0 && lanes <= 2, "scmc_set_lanes: lanes must be 0 (auto), 1 or 2");
+    h->lanes = lanes;
     return SCMC_OK;
 }
 
@@ -1503,7 +1552,7 @@ int32_t scmc_sweep_deterministic(scmc_t* h, int32_t hits, const double* beta, co
         A.colour = c; A.colour_last = c; A.hits = hits; A.r0 = 0; A.rcount = h->R; A.visit0 = 0; A.seed = 0; A.roff = h->roff;
         A.beta = h->beta; A.sigma = h->sigma; A.active = nullptr; A.acc = h->acc;
         A.inj_xi = dxi; A.inj_u = du; A.out_acc = dacc; A.out_dE = ddE;
-        st = launch_colour_pass(h, A);
+        st = launch_colour_pass(h, A, h->stream);
     }
     if (st == SCMC_OK) {
         fail(cudaMemcpyAsync(accept, dacc, n, cudaMemcpyDeviceToHost, h->stream));

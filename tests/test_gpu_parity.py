@@ -392,6 +392,7 @@ def test_more_replicas_than_the_grid_y_limit(scmc):
     R = 70000
     big = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 3, 1, n_replicas=R, precision=32, seed=7)
     big.set_sweep_mode(3)
+    big.set_lanes(1)            # one stream: all 70 000 replicas in one chunked launch sequence
     acc, att = big.sweep(3, 2.0, 0.4)
     assert np.all(att == 3 * 2 * 9) and acc.min() > 0
     for rid in (65534, 65535, 69999):
@@ -401,3 +402,28 @@ def test_more_replicas_than_the_grid_y_limit(scmc):
         assert a1[0] == acc[rid]
         assert np.array_equal(one.get_state()[0], big.get_state(rid, 1)[0])
     assert np.isfinite(big.energies()).all() and big.measure().shape == (R, 21)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode, n, labels", [(3, 1, 1), (1, 1, 1), (1, 2, 3)])
+def test_replica_lanes_do_not_change_chains(scmc, mode, n, labels):
+    """Two replica lanes on side streams (scmc_set_lanes) against everything on the handle's stream: same accepted counts, same
+    states, for both streaming kernel families and an odd replica count; work queued on the handle's stream afterwards sees the
+    joined result."""
+    def mk():
+        if labels == 1:
+            c = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 12, n, n_replicas=37, precision=32, seed=11)
+        else:
+            c = scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.1, 0.5], 12, n, n_replicas=37, precision=32, seed=11)
+        c.set_sweep_mode(mode)
+        return c
+    a, b = mk(), mk()
+    a.set_lanes(1); b.set_lanes(2)
+    beta = np.linspace(0.5, 20.0, 37)
+    for _ in range(3):
+        acc_a, _ = a.sweep(5, beta, 0.5)
+        acc_b, _ = b.sweep(5, beta, 0.5)
+        assert np.array_equal(acc_a, acc_b)
+        assert np.array_equal(a.energies(), b.energies())
+    assert np.array_equal(a.get_state(), b.get_state())
+    assert b.info()["launches"] > a.info()["launches"]
