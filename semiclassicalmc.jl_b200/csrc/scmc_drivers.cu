@@ -358,15 +358,25 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
     // Device-side driver: when every replica lives in ONE CTA of the psi-family resident kernel, the whole schedule (beta ramp, sigma
     // adaptation, measurement rows) runs inside the persistent kernel, up to 512 sweeps per launch; chains are identical to the
     // host-driven path below, measurement rows agree to rounding (energies re-summed from the resident states).
-    const bool device_side = uses_psi_gather(h) && h->res.eligible_psi && h->res.cs == 1 && (h->sweep_mode == 0 || h->sweep_mode == 4) &&
-                             !out->therm_energy;
+    const bool device_side = uses_psi_gather(h) && h->res.eligible_psi && h->res.cs == 1 && (h->sweep_mode == 0 || h->sweep_mode == 4);
     // ---- thermalisation (MonteCarlo.jl:38-66)
     int64_t n_log = 0;
     if (device_side) {
+        // energy log entries (one per sigma-adaptation point) are written by the kernel into one device table, copied out at the end
+        const int64_t log_base = (int64_t)p->sweep0 / rate + 1;       // g / rate of the first entry
+        const int64_t n_log_total = std::max<int64_t>(0, p->n_therm / rate - (int64_t)p->sweep0 / rate);
+        DevBuf dlog;
+        if (out->therm_energy && n_log_total > 0) SCMC_CK(dlog.alloc((size_t)n_log_total * R * 8));
         for (int64_t sweep = (int64_t)p->sweep0 + 1; sweep <= p->n_therm;) {
             const int64_t chunk = std::min<int64_t>(512, p->n_therm - sweep + 1);
-            SCMC_TRY(launch_resident_run(h, 1, chunk, p->hits, p->seed, dT.as<double>(), dTi.as<double>(), n_anneal, rate, sweep, 0, nullptr));
+            SCMC_TRY(launch_resident_run(h, 1, chunk, p->hits, p->seed, dT.as<double>(), dTi.as<double>(), n_anneal, rate, sweep, log_base,
+                                         dlog.p ? dlog.as<double>() : nullptr));
             sweep += chunk;
+        }
+        if (dlog.p) {
+            SCMC_CK(cudaMemcpyAsync(out->therm_energy, dlog.p, (size_t)n_log_total * R * 8, cudaMemcpyDeviceToHost, h->stream));
+            SCMC_CK(cudaStreamSynchronize(h->stream));
+            n_log = n_log_total;
         }
     }
     for (int64_t sweep = (int64_t)p->sweep0 + 1; !device_side && sweep <= p->n_therm; sweep++) {

@@ -348,10 +348,13 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                         const double ratio = run_acc / A.att_window;
                         sigma = (R)fmin((double)sigma * 0.5 / (1.0 - ratio), 60.0);
                         run_acc = 0.0;
-                    } else {                                       // measure! (ObservablesGeneric.jl:32-46) straight from the resident states
-                        float eacc = 0.f, macc[NG];
+                    }
+                    // E and sum_i T_i straight from the resident states (measure!, ObservablesGeneric.jl:32-46; the thermalisation
+                    // energy log, MonteCarlo.jl:48-49): run == 2 writes a measure! row, run == 1 logs E/N before sigma is adapted
+                    if (run == 2 || A.rows != nullptr) {
+                        double eacc = 0.0, macc[NG];      // FP64 partial sums (a thread owns only a few sites)
 #pragma unroll
-                        for (int t = 0; t < NG; t++) macc[t] = 0.f;
+                        for (int t = 0; t < NG; t++) macc[t] = 0.0;
                         for (int q = tid; q < n_own; q += nth) {
                             R re[D], im[D], h[NG], P[NP];
                             load_psi<R, D>(sPsi + q, (size_t)cap, re, im);
@@ -384,24 +387,24 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
 #pragma unroll
                                     for (int t = 0; t < NG; t++) e = fma(Tsq[t], M.cp.K[t], e);
                                 }
-                                eacc += (float)e;
+                                eacc += (double)e;
 #pragma unroll
-                                for (int t = 0; t < NG; t++) macc[t] += (float)T[t];
+                                for (int t = 0; t < NG; t++) macc[t] += (double)T[t];
                             } else if constexpr (NP == NG) {
                                 field_from_sums_smem<1>(sJt, (const R(*)[NG])P, h);           // h = Hq
-                                eacc += 0.5f * (float)GenOps<GEN>::energy_from_state(re, im, h);
+                                eacc += 0.5 * (double)GenOps<GEN>::energy_from_state(re, im, h);
                                 R Pown[NP];
 #pragma unroll
                                 for (int t = 0; t < NP; t++) Pown[t] = R(0);
                                 GenOps<GEN>::density_acc(re, im, Pown);
 #pragma unroll
-                                for (int t = 0; t < NG; t++) macc[t] += (float)Pown[t];
+                                for (int t = 0; t < NG; t++) macc[t] += (double)Pown[t];
                             }
                         }
                         const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
                         for (int t = 0; t <= NG; t++) {
-                            double v = t < NG ? (double)macc[t < NG ? t : 0] : (double)eacc;
+                            double v = t < NG ? macc[t < NG ? t : 0] : eacc;
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                             if (lane == 0) s_red[warp][t] = v;
@@ -417,16 +420,21 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                             if (fused) GenOps<GEN>::expect_from_density(tot, Tsum);           // magnetisation is linear in the density sums
                             else for (int t = 0; t < NG; t++) Tsum[t] = tot[t];
                             const double E = tot[NG] + A.e_const, invN = 1.0 / (double)M.N;
-                            double* row = A.rows + ((size_t)(g / A.rate - A.row_base) * A.nrep + r) * SCMC_NOBS;
-                            double m[NG];
-                            for (int t = 0; t < NG; t++) m[t] = Tsum[t] * invN;
-                            row[0] = E * invN;
-                            row[1] = (E * invN) * (E * invN);
-                            row[2] = sqrt(m[4] * m[4] + m[8] * m[8] + m[12] * m[12]);
-                            row[3] = sqrt(m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
-                            row[4] = sqrt(m[5] * m[5] + m[6] * m[6] + m[7] * m[7] + m[9] * m[9] + m[10] * m[10] + m[11] * m[11] + m[13] * m[13] +
-                                          m[14] * m[14] + m[15] * m[15]);
-                            for (int t = 0; t < NG; t++) row[5 + t] = m[t];
+                            const size_t slot = (size_t)(g / A.rate - A.row_base) * A.nrep + r;
+                            if (run == 1) {
+                                A.rows[slot] = E * invN;
+                            } else {
+                                double* row = A.rows + slot * SCMC_NOBS;
+                                double m[NG];
+                                for (int t = 0; t < NG; t++) m[t] = Tsum[t] * invN;
+                                row[0] = E * invN;
+                                row[1] = (E * invN) * (E * invN);
+                                row[2] = sqrt(m[4] * m[4] + m[8] * m[8] + m[12] * m[12]);
+                                row[3] = sqrt(m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
+                                row[4] = sqrt(m[5] * m[5] + m[6] * m[6] + m[7] * m[7] + m[9] * m[9] + m[10] * m[10] + m[11] * m[11] + m[13] * m[13] +
+                                              m[14] * m[14] + m[15] * m[15]);
+                                for (int t = 0; t < NG; t++) row[5 + t] = m[t];
+                            }
                         }
                         __syncthreads();
                     }

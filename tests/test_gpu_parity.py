@@ -373,13 +373,18 @@ def test_device_side_run_equals_host_driven_schedule(scmc, precision):
     ra = scmc.run_(a, None, Ts, 2.0, 230, 345, measurement_rate=10)
     b = mk()                                   # auto: single-CTA resident psi kernel, device-side schedule
     assert b.info()["resident_psi"] and b.info()["cluster"] == 1
+    l0 = b.info()["launches"]
     rb = scmc.run_(b, None, Ts, 2.0, 230, 345, measurement_rate=10)
+    assert b.info()["launches"] - l0 <= 6      # 575 sweeps in a handful of persistent launches: the schedule really ran on the device
+    assert a.info()["launches"] > 100
     assert ra["rows"] == rb["rows"] == 34
+    assert ra["therm_energy"].shape == rb["therm_energy"].shape == (23, R)
     assert np.array_equal(ra["sigma"], rb["sigma"]) and np.array_equal(ra["acc_rate"], rb["acc_rate"])
     assert np.array_equal(a.get_state(), b.get_state())
     tol = 1e-10 if precision == 64 else 2e-5
     assert np.allclose(ra["series"], rb["series"], rtol=tol, atol=tol)
     assert np.allclose(ra["mean"], rb["mean"], rtol=tol, atol=tol)
+    assert np.allclose(ra["therm_energy"], rb["therm_energy"], rtol=tol, atol=tol)     # E/N logged at the sigma-adaptation points
     # a resumed run (current_sweep) continues both paths identically
     ra2 = scmc.run_(a, None, Ts, 2.0, 230, 500, measurement_rate=10, current_sweep=575, σ=ra["sigma"])
     rb2 = scmc.run_(b, None, Ts, 2.0, 230, 500, measurement_rate=10, current_sweep=575, σ=rb["sigma"])
