@@ -68,6 +68,8 @@ struct scmc_handle {
     unsigned long long* acc = nullptr;           // [R] accepted-update counters
     uint8_t* active = nullptr;                   // [R] replica still running (annealing) -- nullptr semantics handled by callers
     double* obs = nullptr;                       // [R][SCMC_NOBS] scratch rows
+    double* d_meas_partial = nullptr;            // [R][parts][17] per-CTA partial sums of the psi-family measurement
+    size_t meas_partial_bytes = 0;
     void* pinned = nullptr;                      // pinned host staging for the beta / sigma tables
     int64_t bytes = 0, launches = 0;
     int32_t sweep_mode = 0;                      // 0 auto, 1 streaming T-gather, 2 resident T-gather, 3 streaming psi-gather, 4 resident psi-gather
@@ -94,7 +96,7 @@ namespace scmc {
 // implemented in scmc_core.cu
 int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma);
 int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active);
-int32_t launch_measure(scmc_handle* h, double* d_rows /* device [R][SCMC_NOBS] */);
+int32_t launch_measure(scmc_handle* h, double* d_rows /* device [R][SCMC_NOBS] or null */, double* d_Etot = nullptr /* device [R] or null */);
 int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes);
 int32_t ensure_T(scmc_handle* h);      // recompute the cached T (Tsq) planes from psi if a psi-gather sweep left them stale
 bool uses_psi_gather(const scmc_handle* h);

@@ -46,6 +46,14 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #define SCMC_SWEEP_THREADS 128
 #define SCMC_SWEEP_BLOCKS 5
 #endif
+// resident CTAs per SM the FP64 instantiations are compiled for: at 5 (96 registers) they spill 0.4-2.4 KB per thread.  Measured on
+// B200 (C5 lattice, 2048 replicas, FP64): T-gather 0.92 / 1.10 / 1.21e10 updates/s at 5 / 4 / 3 CTAs, psi-gather 1.39 / 1.60 / 1.45e10
+#ifndef SCMC_SWEEP_BLOCKS_F64
+#define SCMC_SWEEP_BLOCKS_F64 3
+#endif
+#ifndef SCMC_SWEEP_PSI_BLOCKS_F64
+#define SCMC_SWEEP_PSI_BLOCKS_F64 4
+#endif
 #ifndef SCMC_HIT_UNROLL2
 #define SCMC_HIT_UNROLL2 0
 #endif
@@ -159,7 +167,7 @@ __device__ __forceinline__ void prefetch_site(const DevModel<R, NL>& M, int64_t 
 // grid = (blocks per replica, replicas of the batch); a block walks over tiles of blockDim.x sites of its replica so that the
 // coupling table (global -> shared, coalesced) is staged once per block.  INJECT = deterministic test mode (host-supplied randoms).
 template <class R, int GEN, bool ONSITE, int NL, bool INJECT>
-__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep_colour(const __grid_constant__ DevModel<R, NL> M, const SweepArgs A) {
+__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEEP_BLOCKS_F64 : SCMC_SWEEP_BLOCKS) k_sweep_colour(const __grid_constant__ DevModel<R, NL> M, const SweepArgs A) {
     constexpr int D = GenOps<GEN>::D;
     const int64_t r = A.r0 + blockIdx.y;
     __shared__ __align__(16) R sJt[NL * NG * NG];
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
 // FMAs and maps once per visit.  Nothing but psi is read or written: DRAM traffic per visit drops from ~272 B to ~150 B and
 // the T planes become a lazily refreshed cache (ensure_T).  Rounding differs from the T-gather kernels at the 1-ulp level.
 template <class R, int GEN, bool ONSITE>
-__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep_colour_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A) {
+__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEEP_PSI_BLOCKS_F64 : SCMC_SWEEP_BLOCKS) k_sweep_colour_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A) {
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
     const int64_t r = A.r0 + blockIdx.y;
     __shared__ __align__(16) R sJt[NG * NG];
@@ -719,6 +727,134 @@ __global__ void __launch_bounds__(256) k_measure(const __grid_constant__ DevMode
     }
 }
 
+// psi-family measurement: E and sum_i T_i straight from the states, with the gather / density-sum / mat-vec arithmetic of
+// k_sweep_colour_psi (no T planes are read, so no refresh after psi-gather sweeps).  grid = (CTAs per replica, replicas); every CTA
+// leaves NG + 1 FP64 partial sums, k_measure_finish adds them in a fixed order (deterministic) and writes the measure! row.
+// On the fused path (16 density entries, no on-site term) the partial sums are density sums; T = C . P is applied once at the end.
+#define SCMC_MEASURE_THREADS 128
+template <class R, int GEN, bool ONSITE>
+__global__ void __launch_bounds__(SCMC_MEASURE_THREADS, sizeof(R) == 8 ? 3 : 5) k_measure_psi(const __grid_constant__ DevModel<R, 1> M, const void* Jt_, const void* Jqt_, double* partial) {
+    constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
+    const int64_t r = blockIdx.y;
+    __shared__ __align__(16) R sJt[NG * NG];
+    __shared__ double red[SCMC_MEASURE_THREADS / 32][NG + 1];
+    const bool fused = !ONSITE && NP == NG && Jqt_ != nullptr;
+    for (int t = threadIdx.x; t < NG * NG; t += blockDim.x) sJt[t] = ((const R*)(fused ? Jqt_ : Jt_))[t];
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const int64_t rbase = r * M.Ns;
+    unsigned long long Pq[NPV];
+#pragma unroll
+    for (int v = 0; v < NPV; v++) {
+        Pq[v] = (unsigned long long)(M.psi + rbase + v * ps);
+        asm volatile("" : "+l"(Pq[v]));
+    }
+    const unsigned stride = (unsigned)M.N;
+    __syncthreads();
+    // per-thread partial sums: the energy in FP64, the 16 magnetisation sums in the handle's precision (a thread adds at most a few
+    // dozen values of magnitude <= 1; everything after that is FP64)
+    double eacc = 0.0;
+    R macc[NG];
+#pragma unroll
+    for (int t = 0; t < NG; t++) macc[t] = R(0);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < M.N; p += gridDim.x * blockDim.x) {
+        asm volatile("" ::: "memory");      // keeps the 64 coupling-table LDS.128 inside the loop (hoisted, they spill to local memory)
+        R re[D], im[D], h[NG], P[NP];
+        load_psi<R, D>(M.psi + rbase + p, ps, re, im);
+#pragma unroll
+        for (int t = 0; t < NP; t++) P[t] = R(0);
+        const int32_t* nb = M.nbr + p;
+#pragma unroll 2
+        for (int k = 0; k < M.z; k += 3) {
+            unsigned j[3];
+#pragma unroll
+            for (int t = 0; t < 3; t++) j[t] = (unsigned)nb[(unsigned)(k + t) * stride];
+            vec4<R> v[3][NPV];
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int q = 0; q < NPV; q++) v[t][q] = *reinterpret_cast<const vec4<R>*>(Pq[q] + (unsigned long long)j[t] * sizeof(vec4<R>));
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                R nr[D], ni[D];
+#pragma unroll
+                for (int q = 0; q < NPV; q++) { nr[2 * q] = v[t][q].x; ni[2 * q] = v[t][q].y; nr[2 * q + 1] = v[t][q].z; ni[2 * q + 1] = v[t][q].w; }
+                GenOps<GEN>::density_acc(nr, ni, P);
+            }
+        }
+        if (!fused) {
+            R S[1][NG], T[NG];
+            GenOps<GEN>::expect_from_density(P, S[0]);
+            field_from_sums_smem<1>(sJt, S, h);
+            GenOps<GEN>::expect(re, im, T);
+            R e = R(0);
+#pragma unroll
+            for (int t = 0; t < NG; t++) e = fma(T[t], h[t], e);
+            e *= R(0.5);
+            if (ONSITE) {
+                R Tsq[NG];
+                GenOps<GEN>::expect_sq(re, im, Tsq);
+#pragma unroll
+                for (int t = 0; t < NG; t++) e = fma(Tsq[t], M.cp.K[t], e);
+            }
+            eacc += (double)e;
+#pragma unroll
+            for (int t = 0; t < NG; t++) macc[t] += T[t];
+        } else if constexpr (NP == NG) {
+            field_from_sums_smem<1>(sJt, (const R(*)[NG])P, h);           // h = Hq
+            eacc += 0.5 * (double)GenOps<GEN>::energy_from_state(re, im, h);
+            R Pown[NP];
+#pragma unroll
+            for (int t = 0; t < NP; t++) Pown[t] = R(0);
+            GenOps<GEN>::density_acc(re, im, Pown);
+#pragma unroll
+            for (int t = 0; t < NG; t++) macc[t] += Pown[t];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t <= NG; t++) {
+        double v = t < NG ? (double)macc[t < NG ? t : 0] : eacc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x <= NG) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w][threadIdx.x];
+        partial[((size_t)r * gridDim.x + blockIdx.x) * (NG + 1) + threadIdx.x] = v;
+    }
+}
+
+template <int GEN>
+__global__ void __launch_bounds__(128) k_measure_finish(int64_t nrep, int nparts, int fused, int64_t N, double e_const, const double* partial, double* rows, double* Etot) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrep) return;
+    double tot[NG + 1], Tsum[NG];
+    for (int t = 0; t <= NG; t++) tot[t] = 0.0;
+    for (int b = 0; b < nparts; b++)
+        for (int t = 0; t <= NG; t++) tot[t] += partial[((size_t)r * nparts + b) * (NG + 1) + t];
+    if (fused) {
+        if constexpr (GenOps<GEN>::NDENS == NG) GenOps<GEN>::expect_from_density(tot, Tsum);
+    } else {
+        for (int t = 0; t < NG; t++) Tsum[t] = tot[t];
+    }
+    const double E = tot[NG] + e_const, invN = 1.0 / (double)N;
+    if (Etot) Etot[r] = E;
+    if (rows) {
+        double* row = rows + r * SCMC_NOBS;
+        double m[NG];
+        for (int a = 0; a < NG; a++) m[a] = Tsum[a] * invN;
+        row[0] = E * invN;
+        row[1] = (E * invN) * (E * invN);
+        row[2] = sqrt(m[4] * m[4] + m[8] * m[8] + m[12] * m[12]);
+        row[3] = sqrt(m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
+        row[4] = sqrt(m[5] * m[5] + m[6] * m[6] + m[7] * m[7] + m[9] * m[9] + m[10] * m[10] + m[11] * m[11] + m[13] * m[13] +
+                      m[14] * m[14] + m[15] * m[15]);
+        for (int a = 0; a < NG; a++) row[5 + a] = m[a];
+    }
+}
+
 template <class R, int NL>
 __global__ void __launch_bounds__(256) k_local_field(const __grid_constant__ DevModel<R, NL> M, int64_t r, double* out) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1057,14 +1193,42 @@ int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t s
     return SCMC_OK;
 }
 
-int32_t launch_measure(scmc_handle* h, double* d_rows) {
-    SCMC_TRY(ensure_T(h));
+int32_t launch_measure(scmc_handle* h, double* d_rows, double* d_Etot) {
+    const bool psi = uses_psi_gather(h);
+    if (!psi) SCMC_TRY(ensure_T(h));
     return dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
         constexpr bool ONS = decltype(ons)::value != 0;
         auto M = make_model<R, NL>(h);
-        k_measure<R, GEN, ONS, NL><<<(unsigned)h->R, 256, 0, h->stream>>>(M, h->e_const, d_rows, nullptr);
+        if constexpr (NL == 1) {
+            if (psi) {
+                // CTAs per replica: SCMC_SWEEP_TILES site tiles each, at most 64, and enough CTAs over all replicas to fill the chip
+                const int64_t tiles = (h->N + SCMC_MEASURE_THREADS - 1) / SCMC_MEASURE_THREADS;
+                int64_t parts = std::min<int64_t>(64, (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES);
+                parts = std::min<int64_t>(tiles, std::max<int64_t>(parts, std::min<int64_t>(64, (2000 + h->R - 1) / h->R)));
+                const size_t need = (size_t)h->R * parts * (NG + 1) * sizeof(double);
+                if (need > h->meas_partial_bytes) {
+                    if (h->d_meas_partial) { SCMC_CK(cudaStreamSynchronize(h->stream)); SCMC_CK(cudaFree(h->d_meas_partial)); h->d_meas_partial = nullptr; h->meas_partial_bytes = 0; }
+                    SCMC_CK(cudaMalloc(&h->d_meas_partial, need));
+                    h->meas_partial_bytes = need;
+                }
+                const bool fused = h->fused_density && !ONS && GenOps<GEN>::NDENS == NG;
+                for (int64_t y0 = 0; y0 < h->R; y0 += 65535) {      // gridDim.y limit
+                    const int64_t yc = std::min<int64_t>(65535, h->R - y0);
+                    auto My = M;
+                    My.psi = M.psi + y0 * M.Ns;      // replica window: blockIdx.y counts from y0
+                    k_measure_psi<R, GEN, ONS><<<dim3((unsigned)parts, (unsigned)yc), SCMC_MEASURE_THREADS, 0, h->stream>>>(
+                        My, h->d_Jt, fused ? h->d_Jqt : nullptr, h->d_meas_partial + (size_t)y0 * parts * (NG + 1));
+                    h->launches++;
+                }
+                k_measure_finish<GEN><<<grid_for(h->R, 128), 128, 0, h->stream>>>(h->R, (int)parts, fused ? 1 : 0, h->N, h->e_const, h->d_meas_partial, d_rows, d_Etot);
+                h->launches++;
+                SCMC_CK(cudaGetLastError());
+                return SCMC_OK;
+            }
+        }
+        k_measure<R, GEN, ONS, NL><<<(unsigned)h->R, 256, 0, h->stream>>>(M, h->e_const, d_rows, d_Etot);
         h->launches++;
         SCMC_CK(cudaGetLastError());
         return SCMC_OK;
@@ -1316,7 +1480,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
 int32_t scmc_destroy(scmc_t* h) {
     if (!h) return SCMC_OK;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16, h->d_cls_site, h->d_cls_nbr};
+    void* ptrs[] = {h->d_meas_partial, h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16, h->d_cls_site, h->d_cls_nbr};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h->pinned) cudaFreeHost(h->pinned);
     for (int l = 0; l < 2; l++) {
@@ -1448,19 +1612,9 @@ int32_t scmc_get_T(scmc_t* h, int64_t r, double* T, double* Tsq) {
 int32_t scmc_energy(scmc_t* h, double* E) {
     SCMC_ARG(h && E, "null argument");
     SCMC_CK(cudaSetDevice(h->device));
-    SCMC_TRY(ensure_T(h));
     double* dE = nullptr;
     SCMC_CK(cudaMalloc(&dE, h->R * 8));
-    int32_t st = dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
-        using R = decltype(rt);
-        constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
-        constexpr bool ONS = decltype(ons)::value != 0;
-        auto M = make_model<R, NL>(h);
-        k_measure<R, GEN, ONS, NL><<<(unsigned)h->R, 256, 0, h->stream>>>(M, h->e_const, nullptr, dE);
-        h->launches++;
-        SCMC_CK(cudaGetLastError());
-        return SCMC_OK;
-    });
+    int32_t st = launch_measure(h, nullptr, dE);
     if (st == SCMC_OK) {
         cudaMemcpyAsync(E, dE, h->R * 8, cudaMemcpyDeviceToHost, h->stream);
         cudaError_t e = cudaStreamSynchronize(h->stream);

@@ -314,7 +314,9 @@ def test_device_side_annealing_equals_host_driven_loop(scmc, precision):
     ra = scmc.runAnnealing_(a, 2.0, **kw)
     b = mk()                                       # auto: psi family, single-CTA resident kernel, device-side controller
     assert b.info()["resident_psi"] and b.info()["cluster"] == 1
+    l0 = b.info()["launches"]
     rb = scmc.runAnnealing_(b, 2.0, **kw)
+    assert b.info()["launches"] - l0 <= 12 and a.info()["launches"] > 500      # the controller really ran inside the persistent kernel
     assert np.array_equal(ra["sweeps"], rb["sweeps"]) and ra["sweeps"].min() > 50
     assert np.array_equal(ra["beta"], rb["beta"]) and np.array_equal(ra["sigma"], rb["sigma"])
     assert np.array_equal(a.get_state(), b.get_state())
