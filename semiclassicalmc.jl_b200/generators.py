@@ -130,9 +130,7 @@ def _emit_hloc(fname, g, gsq):
 
 
 def _density_terms(g):
-    """(j, k, part) entries of P_jk = conj(psi_j) psi_k (j <= k) that any generator uses, in a fixed order.
-    With 16 entries (d = 4: fillings 1 and 3) the order is by flip class j ^ k (0: diagonal, 1: valley flip, 2: spin flip, 3: both),
-    four entries per class, so that couplings which conserve both flips are block-diagonal in 4x4 blocks of the density basis."""
+    """(j, k, part) entries of P_jk = conj(psi_j) psi_k (j <= k) that any generator uses, in a fixed order."""
     gre, gim = _quantise(g)
     d = g.shape[1]
     used = []
@@ -146,8 +144,6 @@ def _density_terms(g):
                     used.append((j, k, "r"))
                 if np.any(gim[:, j, k] != 0):
                     used.append((j, k, "i"))
-    if d == 4 and len(used) == 16:
-        used.sort(key=lambda t: (t[0] ^ t[1], t[0], t[1], t[2] == "i"))
     return used
 
 
