@@ -181,6 +181,31 @@ __device__ __forceinline__ void field_from_sums_smem(const double* sJt, const do
             for (int a = 0; a < NG; a++) h[a] = fma(sJt[(l * NG + b) * NG + a], S[l][b], h[a]);
 }
 
+// One label's share of field_from_sums_smem: h += J_l . S with the sum S of that label in 16 registers.  Called for l = 0, 1, ... with the
+// accumulator carried along, it issues exactly the FMA sequence of field_from_sums_smem<NL> (same order => same bits).
+__device__ __forceinline__ void field_accumulate_smem(const float* sJt_l, const float* S, unsigned long long* hp) {
+#pragma unroll
+    for (int b = 0; b < NG; b++) {
+        unsigned long long sb;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(sb) : "f"(S[b]));
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const float4 j4 = *reinterpret_cast<const float4*>(sJt_l + b * NG + 4 * q);
+            unsigned long long j01, j23;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(j01) : "f"(j4.x), "f"(j4.y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(j23) : "f"(j4.z), "f"(j4.w));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(hp[2 * q]) : "l"(j01), "l"(sb));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(hp[2 * q + 1]) : "l"(j23), "l"(sb));
+        }
+    }
+}
+__device__ __forceinline__ void field_accumulate_smem(const double* sJt_l, const double* S, double* h) {
+#pragma unroll
+    for (int b = 0; b < NG; b++)
+#pragma unroll
+        for (int a = 0; a < NG; a++) h[a] = fma(sJt_l[b * NG + a], S[b], h[a]);
+}
+
 // ------------------------------------------------------------------------------------------------ one Metropolis hit
 // e_loc = T.h (+ K.Tsq) is the part of the energy that depends on the visited site; dE = e_loc(psi') - e_loc(psi)
 // (getEnergyDifference!, Configuration.jl:278-298, with the neighbour mat-vecs hoisted into h).

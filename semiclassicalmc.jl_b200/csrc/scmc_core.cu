@@ -90,6 +90,8 @@ struct SweepArgs {
     const double *inj_xi, *inj_u;
     uint8_t* out_acc;
     double* out_dE;
+    int32_t lab_major;            // several labels: label l owns neighbour slots [lab_off[l], lab_off[l+1]) at every site
+    int32_t lab_off[MAXL + 1];
 };
 
 // S_l = sum of T_j over the neighbours with label l.  The neighbour table is padded to a multiple of 3 slots; padding slots
@@ -148,6 +150,59 @@ __device__ __forceinline__ void neighbour_sums(const DevModel<R, NL>& M, int64_t
     }
 }
 
+// Local field of a several-label model with site-independent slot ranges per label: one label at a time, its neighbour sum in 16
+// registers (not in a run-time indexed S[NL][16], which the compiler places in local memory: profiles/README.md), fed straight into that
+// label's mat-vec.  Loads, additions and FMAs are those of neighbour_sums + field_from_sums_smem in the same order.
+template <class R, int NL>
+__device__ __forceinline__ void field_label_major(const DevModel<R, NL>& M, const SweepArgs& A, const R* sJt, int64_t rbase, size_t ps, int p, R* h) {
+    const int32_t* nb = M.nbr + p;
+    unsigned long long Tq[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        Tq[q] = (unsigned long long)(M.T + rbase + q * ps);
+        asm volatile("" : "+l"(Tq[q]));
+    }
+    const unsigned stride = (unsigned)M.N;
+    constexpr bool F32 = sizeof(R) == 4;
+    unsigned long long hp[NG / 2];
+    if (F32) {
+#pragma unroll
+        for (int i = 0; i < NG / 2; i++) hp[i] = 0ull;
+    } else {
+#pragma unroll
+        for (int a = 0; a < NG; a++) h[a] = R(0);
+    }
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+        R S[NG];
+#pragma unroll
+        for (int a = 0; a < NG; a++) S[a] = R(0);
+        const int k1 = A.lab_off[l + 1];
+        for (int k = A.lab_off[l]; k < k1; k += 3) {
+            unsigned j[3];
+#pragma unroll
+            for (int t = 0; t < 3; t++) j[t] = (k + t < k1) ? (unsigned)nb[(unsigned)(k + t) * stride] : stride;      // past the label's range: zero site
+            vec4<R> v[3][4];
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) v[t][q] = *reinterpret_cast<const vec4<R>*>(Tq[q] + (unsigned long long)j[t] * sizeof(vec4<R>));
+#pragma unroll
+            for (int t = 0; t < 3; t++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    S[4 * q] += v[t][q].x; S[4 * q + 1] += v[t][q].y; S[4 * q + 2] += v[t][q].z; S[4 * q + 3] += v[t][q].w;
+                }
+        }
+        if constexpr (F32) field_accumulate_smem((const float*)sJt + l * NG * NG, (const float*)S, hp);
+        else field_accumulate_smem((const double*)sJt + l * NG * NG, (const double*)S, (double*)h);
+    }
+    if constexpr (F32) {
+#pragma unroll
+        for (int i = 0; i < NG / 2; i++) asm("mov.b64 {%0, %1}, %2;" : "=f"(h[2 * i]), "=f"(h[2 * i + 1]) : "l"(hp[i]));
+    }
+}
+
 // Software prefetch of everything the NEXT site tile of this thread will read (psi planes, neighbour T planes) into L2:
 // no registers are held across the hit loop, and the DRAM round trip of the next tile overlaps with the current tile's hits.
 template <class R, int NL, int D>
@@ -197,7 +252,9 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
         R re[D], im[D], T[NG], Tsq[NG], h[NG];
         load_psi<R, D>(M.psi + rbase + p, ps, re, im);
         const int site = M.orig[p];
-        {
+        if (NL > 1 && A.lab_major) {
+            field_label_major<R, NL>(M, A, sJt, rbase, ps, p, h);
+        } else {
             R S[NL][NG];
             neighbour_sums<R, NL>(M, rbase, ps, p, S);
 #if SCMC_ABLATE == 3
@@ -1075,6 +1132,8 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A, cudaStream
             B.r0 = A.r0 + y0; B.rcount = std::min<int64_t>(65535, A.rcount - y0);
             B.Jt = h->d_Jt;
             B.Jqt = h->fused_density ? h->d_Jqt : nullptr;
+            B.lab_major = h->label_major ? 1 : 0;
+            memcpy(B.lab_off, h->lab_off, sizeof B.lab_off);
             const unsigned tiles = grid_for(nc, SCMC_SWEEP_THREADS);
             // CTAs per replica: up to SCMC_SWEEP_TILES site tiles per CTA (coupling table staged once per CTA), but never fewer
             // than a few waves of CTAs over the chip, so small replica counts (8-GPU shards) do not end in a long tail.
@@ -1393,12 +1452,31 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__); }
     std::vector<int32_t> nb((size_t)h->z * N, (int32_t)N);
     std::vector<int8_t> lb((size_t)h->z * N, 0);
-    for (int64_t p = 0; p < N; p++)
-        for (int k = 0; k < z_max; k++) {
-            const int32_t j = nbr_site[(int64_t)h->orig[p] * z_max + k];
-            nb[(size_t)k * N + p] = j >= 0 ? h->perm[j] : (int32_t)N;
-            lb[(size_t)k * N + p] = j >= 0 ? (int8_t)nbr_label[(int64_t)h->orig[p] * z_max + k] : 0;
+    // slots of a site are stably sorted by label (bonds that do not exist last): the order of the bonds inside a label, and with it every
+    // per-label neighbour sum, is the caller's; with one label this is the caller's order
+    std::vector<int64_t> per_label((size_t)n_labels, -1);
+    h->label_major = n_labels > 1 && !(getenv("SCMC_LABEL_MAJOR") && atoi(getenv("SCMC_LABEL_MAJOR")) == 0);
+    std::vector<int> order(z_max);
+    for (int64_t p = 0; p < N; p++) {
+        const int64_t i = h->orig[p];
+        auto key = [&](int k) { return nbr_site[i * z_max + k] >= 0 ? (int)nbr_label[i * z_max + k] : n_labels; };
+        for (int k = 0; k < z_max; k++) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+        std::vector<int64_t> cnt((size_t)n_labels, 0);
+        for (int s = 0; s < z_max; s++) {
+            const int k = order[s];
+            const int32_t j = nbr_site[i * z_max + k];
+            nb[(size_t)s * N + p] = j >= 0 ? h->perm[j] : (int32_t)N;
+            lb[(size_t)s * N + p] = j >= 0 ? (int8_t)nbr_label[i * z_max + k] : 0;
+            if (j >= 0) cnt[nbr_label[i * z_max + k]]++;
         }
+        for (int l = 0; l < n_labels; l++) {
+            if (per_label[l] < 0) per_label[l] = cnt[l];
+            else if (per_label[l] != cnt[l]) h->label_major = false;      // bond counts per label differ between sites: per-thread labels
+        }
+    }
+    h->lab_off[0] = 0;
+    for (int l = 0; l < MAXL; l++) h->lab_off[l + 1] = h->lab_off[l] + (l < n_labels ? (int32_t)std::max<int64_t>(per_label[l], 0) : 0);
     const size_t plane = (size_t)h->R * h->Ns * 4 * h->esz();
     int32_t st = SCMC_OK;
     auto A = [&](void** p, size_t bytes) { if (st == SCMC_OK) st = dev_alloc(h, p, bytes); };
