@@ -51,6 +51,9 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #ifndef SCMC_SWEEP_BLOCKS_F64
 #define SCMC_SWEEP_BLOCKS_F64 3
 #endif
+#ifndef SCMC_SWEEP_BLOCKS_NL
+#define SCMC_SWEEP_BLOCKS_NL SCMC_SWEEP_BLOCKS      // FP32 instantiations with several coupling labels
+#endif
 #ifndef SCMC_SWEEP_PSI_BLOCKS_F64
 #define SCMC_SWEEP_PSI_BLOCKS_F64 4
 #endif
@@ -222,7 +225,7 @@ __device__ __forceinline__ void prefetch_site(const DevModel<R, NL>& M, int64_t 
 // grid = (blocks per replica, replicas of the batch); a block walks over tiles of blockDim.x sites of its replica so that the
 // coupling table (global -> shared, coalesced) is staged once per block.  INJECT = deterministic test mode (host-supplied randoms).
 template <class R, int GEN, bool ONSITE, int NL, bool INJECT>
-__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEEP_BLOCKS_F64 : SCMC_SWEEP_BLOCKS) k_sweep_colour(const __grid_constant__ DevModel<R, NL> M, const SweepArgs A) {
+__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEEP_BLOCKS_F64 : (NL > 1 ? SCMC_SWEEP_BLOCKS_NL : SCMC_SWEEP_BLOCKS)) k_sweep_colour(const __grid_constant__ DevModel<R, NL> M, const SweepArgs A) {
     constexpr int D = GenOps<GEN>::D;
     const int64_t r = A.r0 + blockIdx.y;
     __shared__ __align__(16) R sJt[NL * NG * NG];
