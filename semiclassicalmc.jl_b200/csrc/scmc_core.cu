@@ -727,18 +727,31 @@ __global__ void __launch_bounds__(SCMC_ASYNC_THREADS, SCMC_ASYNC_BLOCKS) k_sweep
 // Energy + magnetisation of every replica; one CTA per replica; FP64 accumulation.
 // row = [E/N, (E/N)^2, |m_sigma|, |m_tau|, |m_sigmatau|, m[16]]  (measure!, ObservablesGeneric.jl:32-46); Etot[r] = E.
 template <class R, int GEN, bool ONSITE, int NL>
-__global__ void __launch_bounds__(256) k_measure(const __grid_constant__ DevModel<R, NL> M, double e_const, double* rows, double* Etot) {
+__global__ void __launch_bounds__(256) k_measure(const __grid_constant__ DevModel<R, NL> M, double e_const, double* rows, double* Etot, const SweepArgs A) {
     const int64_t r = blockIdx.x;
     const size_t ps = (size_t)M.nrep * M.Ns;
     const int64_t rbase = r * M.Ns;
+    // several labels with site-independent slot ranges: the label-major gather of the sweep kernel (couplings staged in shared memory)
+    __shared__ __align__(16) R sJt[NL > 1 ? NL * NG * NG : 4];
+    const bool lab_major = NL > 1 && A.lab_major;
+    if (lab_major) {
+        for (int t = threadIdx.x; t < NL * NG * NG; t += blockDim.x) sJt[t] = ((const R*)A.Jt)[t];
+        __syncthreads();
+    }
     double acc[NG + 1];
 #pragma unroll
     for (int a = 0; a <= NG; a++) acc[a] = 0.0;
     for (int p = threadIdx.x; p < M.N; p += blockDim.x) {
-        R T[NG], h[NG], S[NL][NG];
+        asm volatile("" ::: "memory");      // keeps the coupling-table loads inside the loop (hoisted, they spill: see k_measure_psi)
+        R T[NG], h[NG];
         load_T<R>(M.T + rbase + p, ps, T);
-        neighbour_sums<R, NL>(M, rbase, ps, p, S);
-        field_from_sums<R, NL>(M.cp, S, h);
+        if (lab_major) {
+            field_label_major<R, NL>(M, A, sJt, rbase, ps, p, h);
+        } else {
+            R S[NL][NG];
+            neighbour_sums<R, NL>(M, rbase, ps, p, S);
+            field_from_sums<R, NL>(M.cp, S, h);
+        }
         R e = R(0);
 #pragma unroll
         for (int a = 0; a < NG; a++) e = fma(T[a], h[a], e);
@@ -1290,7 +1303,10 @@ int32_t launch_measure(scmc_handle* h, double* d_rows, double* d_Etot) {
                 return SCMC_OK;
             }
         }
-        k_measure<R, GEN, ONS, NL><<<(unsigned)h->R, 256, 0, h->stream>>>(M, h->e_const, d_rows, d_Etot);
+        SweepArgs MA{};
+        MA.Jt = h->d_Jt; MA.lab_major = h->label_major ? 1 : 0;
+        memcpy(MA.lab_off, h->lab_off, sizeof MA.lab_off);
+        k_measure<R, GEN, ONS, NL><<<(unsigned)h->R, 256, 0, h->stream>>>(M, h->e_const, d_rows, d_Etot, MA);
         h->launches++;
         SCMC_CK(cudaGetLastError());
         return SCMC_OK;

@@ -441,7 +441,8 @@ def test_replica_lanes_do_not_change_chains(scmc, mode, n, labels):
 def test_label_major_field_is_bit_identical(scmc, monkeypatch, n, precision):
     """Several labels with the same number of bonds per label at every site (TG/h-BN): the label-major gather (one label at a time, sum in
     registers) against the per-thread-label gather of the same build (SCMC_LABEL_MAJOR=0): same loads, additions and FMAs in the same
-    order, so energies, acceptance counts and states must agree bit for bit."""
+    order, so acceptance counts, local fields and states must agree bit for bit.  Energies come from k_measure, whose mat-vec differs between
+    the two paths (couplings from shared memory with packed FMAs vs from the constant bank), so they agree to rounding only."""
     def mk(flag):
         monkeypatch.setenv("SCMC_LABEL_MAJOR", flag)
         c = scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.1, 0.5], 12, n, n_replicas=16, precision=precision, seed=99)
@@ -449,7 +450,8 @@ def test_label_major_field_is_bit_identical(scmc, monkeypatch, n, precision):
         return c
     a, b = mk("0"), mk("1")
     assert np.array_equal(a.get_state(), b.get_state())
-    assert np.array_equal(a.energies(), b.energies())
+    etol = 1e-12 if precision == 64 else 2e-6
+    assert np.allclose(a.energies(), b.energies(), rtol=etol, atol=0)
     assert np.array_equal(a.local_field(3), b.local_field(3))
     beta = np.linspace(0.5, 10.0, 16)
     for _ in range(3):
@@ -457,4 +459,5 @@ def test_label_major_field_is_bit_identical(scmc, monkeypatch, n, precision):
         acc_b, _ = b.sweep(4, beta, 0.4)
         assert np.array_equal(acc_a, acc_b)
     assert np.array_equal(a.get_state(), b.get_state())
-    assert np.array_equal(a.energies(), b.energies())
+    assert np.allclose(a.energies(), b.energies(), rtol=etol, atol=0)
+    assert np.allclose(a.measure(), b.measure(), rtol=10 * etol, atol=10 * etol)
