@@ -79,6 +79,7 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #ifndef SCMC_SWEEP_TILES
 #define SCMC_SWEEP_TILES 16     // site tiles (of SCMC_SWEEP_THREADS sites) a block walks over
 #endif
+#define SCMC_MEASURE_THREADS 128
 struct SweepArgs {
     int32_t colour, colour_last, hits;   // classes [colour, colour_last] are visited in order by ONE block per replica when colour_last > colour
     int64_t r0, rcount;        // replica batch [r0, r0 + rcount)
@@ -724,24 +725,29 @@ __global__ void __launch_bounds__(SCMC_ASYNC_THREADS, SCMC_ASYNC_BLOCKS) k_sweep
     if ((tid & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
 }
 
-// Energy + magnetisation of every replica; one CTA per replica; FP64 accumulation.
-// row = [E/N, (E/N)^2, |m_sigma|, |m_tau|, |m_sigmatau|, m[16]]  (measure!, ObservablesGeneric.jl:32-46); Etot[r] = E.
+// Energy + magnetisation of every replica from the cached T (Tsq) planes (T-gather family).  grid = (CTAs per replica, replicas);
+// every CTA leaves NG + 1 FP64 partial sums, k_measure_finish adds them in a fixed order (deterministic) and writes
+// row = [E/N, (E/N)^2, |m_sigma|, |m_tau|, |m_sigmatau|, m[16]]  (measure!, ObservablesGeneric.jl:32-46) and Etot[r] = E.
 template <class R, int GEN, bool ONSITE, int NL>
-__global__ void __launch_bounds__(256) k_measure(const __grid_constant__ DevModel<R, NL> M, double e_const, double* rows, double* Etot, const SweepArgs A) {
-    const int64_t r = blockIdx.x;
+__global__ void __launch_bounds__(SCMC_MEASURE_THREADS, sizeof(R) == 8 ? 2 : 4) k_measure(const __grid_constant__ DevModel<R, NL> M, double* partial, const SweepArgs A) {
+    const int64_t r = blockIdx.y;
     const size_t ps = (size_t)M.nrep * M.Ns;
     const int64_t rbase = r * M.Ns;
     // several labels with site-independent slot ranges: the label-major gather of the sweep kernel (couplings staged in shared memory)
     __shared__ __align__(16) R sJt[NL > 1 ? NL * NG * NG : 4];
+    __shared__ double red[SCMC_MEASURE_THREADS / 32][NG + 1];
     const bool lab_major = NL > 1 && A.lab_major;
     if (lab_major) {
         for (int t = threadIdx.x; t < NL * NG * NG; t += blockDim.x) sJt[t] = ((const R*)A.Jt)[t];
         __syncthreads();
     }
-    double acc[NG + 1];
+    // per-thread partial sums: the energy in FP64, the 16 magnetisation sums in the handle's precision (a thread adds at most a few
+    // dozen values of magnitude <= d; everything after that is FP64)
+    double eacc = 0.0;
+    R macc[NG];
 #pragma unroll
-    for (int a = 0; a <= NG; a++) acc[a] = 0.0;
-    for (int p = threadIdx.x; p < M.N; p += blockDim.x) {
+    for (int a = 0; a < NG; a++) macc[a] = R(0);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < M.N; p += gridDim.x * blockDim.x) {
         asm volatile("" ::: "memory");      // keeps the coupling-table loads inside the loop (hoisted, they spill: see k_measure_psi)
         R T[NG], h[NG];
         load_T<R>(M.T + rbase + p, ps, T);
@@ -762,41 +768,23 @@ __global__ void __launch_bounds__(256) k_measure(const __grid_constant__ DevMode
 #pragma unroll
             for (int a = 0; a < NG; a++) e = fma(Tsq[a], M.cp.K[a], e);
         }
-        acc[NG] += (double)e;
+        eacc += (double)e;
 #pragma unroll
-        for (int a = 0; a < NG; a++) acc[a] += (double)T[a];
+        for (int a = 0; a < NG; a++) macc[a] += T[a];
     }
-    __shared__ double red[8][NG + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int a = 0; a <= NG; a++) {
-        double v = acc[a];
+    for (int t = 0; t <= NG; t++) {
+        double v = t < NG ? (double)macc[t < NG ? t : 0] : eacc;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) red[warp][a] = v;
+        if (lane == 0) red[warp][t] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot[NG + 1];
-        for (int a = 0; a <= NG; a++) {
-            double v = 0.0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w][a];
-            tot[a] = v;
-        }
-        const double E = tot[NG] + e_const, invN = 1.0 / (double)M.N;
-        if (Etot) Etot[r] = E;
-        if (rows) {
-            double* row = rows + r * SCMC_NOBS;
-            double m[NG];
-            for (int a = 0; a < NG; a++) m[a] = tot[a] * invN;
-            row[0] = E * invN;
-            row[1] = (E * invN) * (E * invN);
-            row[2] = sqrt(m[4] * m[4] + m[8] * m[8] + m[12] * m[12]);
-            row[3] = sqrt(m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
-            row[4] = sqrt(m[5] * m[5] + m[6] * m[6] + m[7] * m[7] + m[9] * m[9] + m[10] * m[10] + m[11] * m[11] + m[13] * m[13] +
-                          m[14] * m[14] + m[15] * m[15]);
-            for (int a = 0; a < NG; a++) row[5 + a] = m[a];
-        }
+    if (threadIdx.x <= NG) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) v += red[w][threadIdx.x];
+        partial[((size_t)r * gridDim.x + blockIdx.x) * (NG + 1) + threadIdx.x] = v;
     }
 }
 
@@ -804,7 +792,6 @@ __global__ void __launch_bounds__(256) k_measure(const __grid_constant__ DevMode
 // k_sweep_colour_psi (no T planes are read, so no refresh after psi-gather sweeps).  grid = (CTAs per replica, replicas); every CTA
 // leaves NG + 1 FP64 partial sums, k_measure_finish adds them in a fixed order (deterministic) and writes the measure! row.
 // On the fused path (16 density entries, no on-site term) the partial sums are density sums; T = C . P is applied once at the end.
-#define SCMC_MEASURE_THREADS 128
 template <class R, int GEN, bool ONSITE>
 __global__ void __launch_bounds__(SCMC_MEASURE_THREADS, sizeof(R) == 8 ? 3 : 5) k_measure_psi(const __grid_constant__ DevModel<R, 1> M, const void* Jt_, const void* Jqt_, double* partial) {
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
@@ -1271,42 +1258,47 @@ int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t s
 int32_t launch_measure(scmc_handle* h, double* d_rows, double* d_Etot) {
     const bool psi = uses_psi_gather(h);
     if (!psi) SCMC_TRY(ensure_T(h));
+    // CTAs per replica: SCMC_SWEEP_TILES site tiles each, at most 64, and enough CTAs over all replicas to fill the chip
+    const int64_t tiles = (h->N + SCMC_MEASURE_THREADS - 1) / SCMC_MEASURE_THREADS;
+    int64_t parts = std::min<int64_t>(64, (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES);
+    parts = std::min<int64_t>(tiles, std::max<int64_t>(parts, std::min<int64_t>(64, (2000 + h->R - 1) / h->R)));
+    const size_t need = (size_t)h->R * parts * (NG + 1) * sizeof(double);
+    if (need > h->meas_partial_bytes) {
+        if (h->d_meas_partial) { SCMC_CK(cudaStreamSynchronize(h->stream)); SCMC_CK(cudaFree(h->d_meas_partial)); h->d_meas_partial = nullptr; h->meas_partial_bytes = 0; }
+        SCMC_CK(cudaMalloc(&h->d_meas_partial, need));
+        h->meas_partial_bytes = need;
+    }
     return dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
         constexpr bool ONS = decltype(ons)::value != 0;
         auto M = make_model<R, NL>(h);
-        if constexpr (NL == 1) {
-            if (psi) {
-                // CTAs per replica: SCMC_SWEEP_TILES site tiles each, at most 64, and enough CTAs over all replicas to fill the chip
-                const int64_t tiles = (h->N + SCMC_MEASURE_THREADS - 1) / SCMC_MEASURE_THREADS;
-                int64_t parts = std::min<int64_t>(64, (tiles + SCMC_SWEEP_TILES - 1) / SCMC_SWEEP_TILES);
-                parts = std::min<int64_t>(tiles, std::max<int64_t>(parts, std::min<int64_t>(64, (2000 + h->R - 1) / h->R)));
-                const size_t need = (size_t)h->R * parts * (NG + 1) * sizeof(double);
-                if (need > h->meas_partial_bytes) {
-                    if (h->d_meas_partial) { SCMC_CK(cudaStreamSynchronize(h->stream)); SCMC_CK(cudaFree(h->d_meas_partial)); h->d_meas_partial = nullptr; h->meas_partial_bytes = 0; }
-                    SCMC_CK(cudaMalloc(&h->d_meas_partial, need));
-                    h->meas_partial_bytes = need;
+        bool fused = false;
+        for (int64_t y0 = 0; y0 < h->R; y0 += 65535) {      // gridDim.y limit
+            const int64_t yc = std::min<int64_t>(65535, h->R - y0);
+            auto My = M;                                     // replica window: blockIdx.y counts from y0
+            My.psi = M.psi + y0 * M.Ns;
+            My.T = M.T + y0 * M.Ns;
+            if (M.Tsq) My.Tsq = M.Tsq + y0 * M.Ns;
+            double* part = h->d_meas_partial + (size_t)y0 * parts * (NG + 1);
+            const dim3 grid((unsigned)parts, (unsigned)yc);
+            bool launched = false;
+            if constexpr (NL == 1) {
+                if (psi) {
+                    fused = h->fused_density && !ONS && GenOps<GEN>::NDENS == NG;
+                    k_measure_psi<R, GEN, ONS><<<grid, SCMC_MEASURE_THREADS, 0, h->stream>>>(My, h->d_Jt, fused ? h->d_Jqt : nullptr, part);
+                    launched = true;
                 }
-                const bool fused = h->fused_density && !ONS && GenOps<GEN>::NDENS == NG;
-                for (int64_t y0 = 0; y0 < h->R; y0 += 65535) {      // gridDim.y limit
-                    const int64_t yc = std::min<int64_t>(65535, h->R - y0);
-                    auto My = M;
-                    My.psi = M.psi + y0 * M.Ns;      // replica window: blockIdx.y counts from y0
-                    k_measure_psi<R, GEN, ONS><<<dim3((unsigned)parts, (unsigned)yc), SCMC_MEASURE_THREADS, 0, h->stream>>>(
-                        My, h->d_Jt, fused ? h->d_Jqt : nullptr, h->d_meas_partial + (size_t)y0 * parts * (NG + 1));
-                    h->launches++;
-                }
-                k_measure_finish<GEN><<<grid_for(h->R, 128), 128, 0, h->stream>>>(h->R, (int)parts, fused ? 1 : 0, h->N, h->e_const, h->d_meas_partial, d_rows, d_Etot);
-                h->launches++;
-                SCMC_CK(cudaGetLastError());
-                return SCMC_OK;
             }
+            if (!launched) {
+                SweepArgs MA{};
+                MA.Jt = h->d_Jt; MA.lab_major = h->label_major ? 1 : 0;
+                memcpy(MA.lab_off, h->lab_off, sizeof MA.lab_off);
+                k_measure<R, GEN, ONS, NL><<<grid, SCMC_MEASURE_THREADS, 0, h->stream>>>(My, part, MA);
+            }
+            h->launches++;
         }
-        SweepArgs MA{};
-        MA.Jt = h->d_Jt; MA.lab_major = h->label_major ? 1 : 0;
-        memcpy(MA.lab_off, h->lab_off, sizeof MA.lab_off);
-        k_measure<R, GEN, ONS, NL><<<(unsigned)h->R, 256, 0, h->stream>>>(M, h->e_const, d_rows, d_Etot, MA);
+        k_measure_finish<GEN><<<grid_for(h->R, 128), 128, 0, h->stream>>>(h->R, (int)parts, fused ? 1 : 0, h->N, h->e_const, h->d_meas_partial, d_rows, d_Etot);
         h->launches++;
         SCMC_CK(cudaGetLastError());
         return SCMC_OK;
