@@ -1438,7 +1438,9 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
         const bool psi_family = n_labels == 1 && (d == 4 || h->onsite);
         const size_t per_site = (psi_family ? 4 * w * (d / 2) : 4 * w * (4 + d / 2 + (h->onsite ? 4 : 0))) + 2 * (size_t)h->z + (n_labels > 1 ? (size_t)h->z : 0);
         int cs = 0;
+        const int cs_min = getenv("SCMC_CLUSTER_MIN") ? atoi(getenv("SCMC_CLUSTER_MIN")) : 1;      // experiments: larger clusters than needed
         for (int c : {1, 2, 4, 8}) {
+            if (c < cs_min) continue;
             const int64_t n_own = (N + c - 1) / c;
             const size_t cap = (size_t)(n_own + 1 + 7) / 8 * 8;
             if (cap * per_site + (size_t)MAXL * 256 * w + 1024 <= (size_t)226 * 1024 && n_own + 1 <= 8191 && N >= c) { cs = c; break; }
