@@ -355,10 +355,10 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
         SCMC_CK(cudaGetLastError());
         return SCMC_OK;
     };
-    // Device-side driver: when every replica lives in ONE CTA of the psi-family resident kernel, the whole schedule (beta ramp, sigma
-    // adaptation, measurement rows) runs inside the persistent kernel, up to 512 sweeps per launch; chains are identical to the
+    // Device-side driver: when every replica lives in one CTA or one cluster of the psi-family resident kernel, the whole schedule (beta ramp,
+    // sigma adaptation, measurement rows) runs inside the persistent kernel, up to 512 sweeps per launch; chains are identical to the
     // host-driven path below, measurement rows agree to rounding (energies re-summed from the resident states).
-    const bool device_side = uses_psi_gather(h) && h->res.eligible_psi && h->res.cs == 1 && (h->sweep_mode == 0 || h->sweep_mode == 4);
+    const bool device_side = uses_psi_gather(h) && h->res.eligible_psi && h->res.cs >= 1 && (h->sweep_mode == 0 || h->sweep_mode == 4);
     // ---- thermalisation (MonteCarlo.jl:38-66)
     int64_t n_log = 0;
     if (device_side) {

@@ -212,6 +212,14 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
 // psi-gather family (same arithmetic as k_sweep_colour_psi, bit-identical chains): only psi lives in shared memory
 // (d/2 x 16 B per site instead of psi + T), neighbours are read as states through DSMEM and enter through density-matrix sums.
 // C5 (128 x 128, FP32): 16384 x (32 + 12) B = 704 KB -> cluster of 4 CTAs x 177 KB, all 148 SMs busy.
+// FP64 value of another CTA of the cluster (or of this CTA when CLUSTER is false) at shared address `addr`
+template <bool CLUSTER> __device__ __forceinline__ double ld_f64(uint32_t addr) {
+    double v;
+    if (CLUSTER) asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
 template <class R, int GEN, bool ONSITE, bool CLUSTER>
 __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__ DevModel<R, 1> M, const __grid_constant__ ResidentArgs A) {
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
@@ -223,6 +231,7 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
     uint16_t* sNbr = reinterpret_cast<uint16_t*>(sJt + NG * NG);  // [z][nmax]
     __shared__ unsigned s_acc;
     __shared__ double s_red[16][NG + 1];                          // measurement reduction (one row per warp)
+    __shared__ double s_xchg[NG + 1];                             // this CTA's partial sums, read by the other CTAs of the cluster (run modes)
     unsigned rank = 0, cluster_id = blockIdx.x;
     if (CLUSTER) {
         rank = cg::this_cluster().block_rank();
@@ -256,8 +265,8 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
         double an_acc = anneal ? (double)A.acc[r] : 0.0;
         bool an_still = true;
         // run! schedule of this replica
-        const int run = CLUSTER ? 0 : A.run_mode;
-        double run_acc = run ? (double)A.acc[r] : 0.0;
+        const int run = A.run_mode;                            // clusters: acceptance counts and measurement sums are reduced through DSMEM
+        double run_acc = (run && rank == 0) ? (double)A.acc[r] : 0.0;      // this CTA's share of the window's accepted updates (rank 0 carries the count over from the previous launch)
         const double run_T = run == 1 ? A.run_T[r] : 1.0, run_Ti = run == 1 ? A.run_Ti[r] : 1.0;
         if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
         unsigned nacc = 0;
@@ -345,7 +354,15 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                 if (tid == 0) s_acc = 0;
                 if (g % A.rate == 0) {
                     if (run == 1) {                                // sigma <- min(sigma * 0.5 / (1 - R), 60)  (MonteCarlo.jl:50-53)
-                        const double ratio = run_acc / A.att_window;
+                        double acc_all = run_acc;
+                        if (CLUSTER) {                              // accepted updates of the whole replica: every CTA adds the shares in rank order
+                            if (tid == 0) s_xchg[0] = run_acc;
+                            cg::this_cluster().sync();
+                            acc_all = 0.0;
+                            for (int b = 0; b < A.cs; b++) acc_all += ld_f64<CLUSTER>(map_to_rank(smem_u32(&s_xchg[0]), (uint32_t)b));
+                            cg::this_cluster().sync();
+                        }
+                        const double ratio = acc_all / A.att_window;
                         sigma = (R)fmin((double)sigma * 0.5 / (1.0 - ratio), 60.0);
                         run_acc = 0.0;
                     }
@@ -362,11 +379,12 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                             for (int t = 0; t < NP; t++) P[t] = R(0);
                             for (int k = 0; k < M.z; k++) {
                                 const unsigned code = sNbr[k * nmax + q];
-                                const uint32_t addr = sPsi_u32 + (code & 0x1FFFu) * (uint32_t)sizeof(V);
+                                uint32_t addr = sPsi_u32 + (code & 0x1FFFu) * (uint32_t)sizeof(V);
+                                if (CLUSTER) addr = map_to_rank(addr, code >> 13);
                                 R nr[D], ni[D];
 #pragma unroll
                                 for (int v = 0; v < NPV; v++) {
-                                    const V w4 = ld_v4<false>(addr + v * plane_bytes, R(0));
+                                    const V w4 = ld_v4<CLUSTER>(addr + v * plane_bytes, R(0));
                                     nr[2 * v] = w4.x; ni[2 * v] = w4.y; nr[2 * v + 1] = w4.z; ni[2 * v + 1] = w4.w;
                                 }
                                 GenOps<GEN>::density_acc(nr, ni, P);
@@ -410,11 +428,23 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                             if (lane == 0) s_red[warp][t] = v;
                         }
                         __syncthreads();
-                        if (tid == 0) {
+                        if (CLUSTER) {
+                            if (tid <= NG) {
+                                double v = 0.0;
+                                for (int w = 0; w < (nth >> 5); w++) v += s_red[w][tid];
+                                s_xchg[tid] = v;
+                            }
+                            cg::this_cluster().sync();
+                        }
+                        if (tid == 0 && rank == 0) {
                             double tot[NG + 1], Tsum[NG];
                             for (int t = 0; t <= NG; t++) {
                                 double v = 0.0;
-                                for (int w = 0; w < (nth >> 5); w++) v += s_red[w][t];
+                                if (CLUSTER) {
+                                    for (int b = 0; b < A.cs; b++) v += ld_f64<CLUSTER>(map_to_rank(smem_u32(&s_xchg[t]), (uint32_t)b));
+                                } else {
+                                    for (int w = 0; w < (nth >> 5); w++) v += s_red[w][t];
+                                }
                                 tot[t] = v;
                             }
                             if (fused) GenOps<GEN>::expect_from_density(tot, Tsum);           // magnetisation is linear in the density sums
@@ -436,7 +466,7 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                                 for (int t = 0; t < NG; t++) row[5 + t] = m[t];
                             }
                         }
-                        __syncthreads();
+                        if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
                     }
                 }
             } else if (!anneal) {
@@ -470,9 +500,17 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
             for (int v = 0; v < NPV; v++) M.psi[gbase + q + v * ps] = sPsi[v * cap + q];
         }
         if (run) {
-            if (tid == 0) {
+            double acc_all = run_acc;
+            if (CLUSTER) {
+                if (tid == 0) s_xchg[0] = run_acc;
+                cg::this_cluster().sync();
+                acc_all = 0.0;
+                for (int b = 0; b < A.cs; b++) acc_all += ld_f64<CLUSTER>(map_to_rank(smem_u32(&s_xchg[0]), (uint32_t)b));
+                cg::this_cluster().sync();
+            }
+            if (tid == 0 && rank == 0) {
                 ((R*)A.sigma)[r] = sigma;
-                A.acc[r] = (unsigned long long)run_acc;
+                A.acc[r] = (unsigned long long)acc_all;
             }
             __syncthreads();
             continue;
@@ -727,9 +765,17 @@ int32_t launch_resident_run(scmc_handle* h, int mode, int64_t chunk, int32_t hit
             A.run_mode = mode; A.run_T = d_T; A.run_Ti = d_Ti; A.n_anneal = n_anneal; A.rate = rate; A.sweep_first = sweep_first; A.row_base = row_base;
             A.att_window = (double)hits * (double)h->N * (double)rate; A.e_const = h->e_const; A.rows = d_rows;
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)A.n_clusters); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem_psi; cfg.stream = h->stream;
-            cfg.attrs = nullptr; cfg.numAttrs = 0;
-            SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, false>, M, A));
+            cfg.gridDim = dim3((unsigned)(A.n_clusters * P.cs)); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem_psi; cfg.stream = h->stream;
+            cudaLaunchAttribute at[1];
+            cfg.attrs = at; cfg.numAttrs = 0;
+            if (P.cs > 1) {      // several CTAs per replica: acceptance counts and measurement sums are reduced through DSMEM inside the kernel
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = P.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.numAttrs = 1;
+                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, true>, M, A));
+            } else {
+                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, false>, M, A));
+            }
             h->launches++;
             return SCMC_OK;
         }

@@ -461,3 +461,37 @@ def test_label_major_field_is_bit_identical(scmc, monkeypatch, n, precision):
     assert np.array_equal(a.get_state(), b.get_state())
     assert np.allclose(a.energies(), b.energies(), rtol=etol, atol=0)
     assert np.allclose(a.measure(), b.measure(), rtol=10 * etol, atol=10 * etol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L, cmin, precision", [(12, 2, 32), (12, 4, 32), (12, 2, 64), (96, 1, 32)])
+def test_device_side_run_in_clusters_equals_host_driven_schedule(scmc, monkeypatch, L, cmin, precision):
+    """run! inside the persistent kernel when a replica spans a cluster of CTAs (acceptance counts and measurement sums reduced through
+    distributed shared memory) vs the host-driven schedule on the streaming kernel: identical chains, adapted sigma and acceptance rates;
+    measurement rows and the thermalisation energy log equal to rounding.  L = 12 forces a larger cluster than the lattice needs
+    (SCMC_CLUSTER_MIN), L = 96 needs a cluster of 2 by size."""
+    R = 6 if L == 12 else 3
+    n_th, n_me = (120, 150) if L == 12 else (30, 40)
+    Ts = np.geomspace(0.05, 1.5, R)
+    def mk(c):
+        monkeypatch.setenv("SCMC_CLUSTER_MIN", str(c))
+        return scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], L, 1, n_replicas=R, precision=precision, seed=1357)
+    a = mk(1); a.set_sweep_mode(3)              # streaming psi-gather kernel, host-driven schedule
+    ra = scmc.run_(a, None, Ts, 2.0, n_th, n_me, measurement_rate=10)
+    b = mk(cmin)
+    assert b.info()["resident_psi"] and b.info()["cluster"] >= max(2, cmin)
+    l0 = b.info()["launches"]
+    rb = scmc.run_(b, None, Ts, 2.0, n_th, n_me, measurement_rate=10)
+    assert b.info()["launches"] - l0 <= 6      # the schedule ran inside the persistent cluster kernel
+    assert ra["rows"] == rb["rows"] == (n_th + n_me) // 10 - n_th // 10
+    assert np.array_equal(ra["sigma"], rb["sigma"]) and np.array_equal(ra["acc_rate"], rb["acc_rate"])
+    assert np.array_equal(a.get_state(), b.get_state())
+    tol = 1e-10 if precision == 64 else 2e-5
+    assert np.allclose(ra["series"], rb["series"], rtol=tol, atol=tol)
+    assert np.allclose(ra["mean"], rb["mean"], rtol=tol, atol=tol)
+    assert np.allclose(ra["therm_energy"], rb["therm_energy"], rtol=tol, atol=tol)
+    # resumed run: the window's accepted count is carried over between launches by rank 0 only
+    ra2 = scmc.run_(a, None, Ts, 2.0, n_th, n_me + 55, measurement_rate=10, current_sweep=n_th + n_me, σ=ra["sigma"])
+    rb2 = scmc.run_(b, None, Ts, 2.0, n_th, n_me + 55, measurement_rate=10, current_sweep=n_th + n_me, σ=rb["sigma"])
+    assert ra2["rows"] == rb2["rows"] and np.array_equal(a.get_state(), b.get_state())
+    assert np.array_equal(ra2["acc_rate"], rb2["acc_rate"])
