@@ -489,7 +489,7 @@ int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results*
     const int check_every = 16;
     // Device-side driver: when every replica lives in ONE CTA of the psi-family resident kernel, the whole cooling loop
     // (acceptance window, beta / sigma updates, stop flag) runs inside the persistent kernel, `chunk` sweeps per launch.
-    const bool device_side = uses_psi_gather(h) && h->res.eligible_psi && h->res.cs == 1 && (h->sweep_mode == 0 || h->sweep_mode == 4) && p->N_max > 1;
+    const bool device_side = uses_psi_gather(h) && h->res.eligible_psi && h->res.cs >= 1 && (h->sweep_mode == 0 || h->sweep_mode == 4) && p->N_max > 1;
     if (device_side) {
         const int64_t n_total = p->N_max - 1;
         for (int64_t launched = 0; launched < n_total && n_active > 0;) {

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
         R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
         R nbeta = neg_beta_scaled(beta);
         // annealing state of this replica (all threads keep identical copies; the controller is deterministic)
-        const bool anneal = !CLUSTER && A.anneal != 0;
+        const bool anneal = A.anneal != 0;                     // clusters: the sweep's accepted count is reduced through DSMEM, every CTA takes the same decision
         int64_t an_done = anneal ? A.sweeps_done[r] : 0, an_sat = anneal ? A.sweeps_at_T[r] : 0;
         double an_acc = anneal ? (double)A.acc[r] : 0.0;
         bool an_still = true;
@@ -476,7 +476,15 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                 const unsigned wt = __reduce_add_sync(0xffffffffu, sweep_acc);
                 if ((tid & 31) == 0 && wt) atomicAdd(&s_acc, wt);
                 __syncthreads();
-                an_acc += (double)s_acc;
+                double sweep_all = (double)s_acc;
+                if (CLUSTER) {                                      // accepted updates of the whole replica in this sweep, added in rank order
+                    if (tid == 0) s_xchg[0] = (double)s_acc;
+                    cg::this_cluster().sync();
+                    sweep_all = 0.0;
+                    for (int b = 0; b < A.cs; b++) sweep_all += ld_f64<CLUSTER>(map_to_rank(smem_u32(&s_xchg[0]), (uint32_t)b));
+                    cg::this_cluster().sync();
+                }
+                an_acc += sweep_all;
                 __syncthreads();
                 if (tid == 0) s_acc = 0;
                 an_sat++; an_done++;
@@ -516,7 +524,7 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
             continue;
         }
         if (anneal) {
-            if (tid == 0) {
+            if (tid == 0 && rank == 0) {
                 ((R*)A.beta)[r] = beta; ((R*)A.sigma)[r] = sigma;
                 A.acc[r] = (unsigned long long)an_acc;
                 A.sweeps_at_T[r] = an_sat; A.sweeps_done[r] = an_done;
@@ -732,9 +740,17 @@ int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint
             A.sigma_min = sigma_min; A.n_per_T = n_per_T; A.n_total = n_total; A.sweeps_at_T = d_sweeps_at_T; A.sweeps_done = d_sweeps_done;
             A.active_rw = h->active; A.n_active = d_n_active;
             cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)A.n_clusters); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem_psi; cfg.stream = h->stream;
-            cfg.attrs = nullptr; cfg.numAttrs = 0;
-            SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, false>, M, A));
+            cfg.gridDim = dim3((unsigned)(A.n_clusters * P.cs)); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem_psi; cfg.stream = h->stream;
+            cudaLaunchAttribute at[1];
+            cfg.attrs = at; cfg.numAttrs = 0;
+            if (P.cs > 1) {
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = P.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.numAttrs = 1;
+                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, true>, M, A));
+            } else {
+                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, false>, M, A));
+            }
             h->launches++;
             return SCMC_OK;
         }

@@ -495,3 +495,27 @@ def test_device_side_run_in_clusters_equals_host_driven_schedule(scmc, monkeypat
     rb2 = scmc.run_(b, None, Ts, 2.0, n_th, n_me + 55, measurement_rate=10, current_sweep=n_th + n_me, σ=rb["sigma"])
     assert ra2["rows"] == rb2["rows"] and np.array_equal(a.get_state(), b.get_state())
     assert np.array_equal(ra2["acc_rate"], rb2["acc_rate"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cmin, precision", [(2, 32), (4, 32), (2, 64)])
+def test_device_side_annealing_in_clusters_equals_host_driven_loop(scmc, monkeypatch, cmin, precision):
+    """runAnnealing!'s cooling loop inside the persistent kernel when a replica spans a cluster of CTAs (the sweep's accepted count is
+    reduced through distributed shared memory every sweep) vs the loop driven from the host one sweep at a time: identical sweep counts,
+    final beta and sigma, and bit-identical states for every replica."""
+    def mk(c):
+        monkeypatch.setenv("SCMC_CLUSTER_MIN", str(c))
+        return scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 12, 1, n_replicas=10, precision=precision, seed=4321)
+    kw = dict(T_fac=0.9, N_max=700, N_o=0, N_per_T=20, min_acc_per_site=3, min_accrate=0.02, σ_min=0.05)
+    a = mk(1); a.set_sweep_mode(3)                 # streaming psi-gather kernel, host-driven controller
+    ra = scmc.runAnnealing_(a, 2.0, **kw)
+    b = mk(cmin)
+    assert b.info()["resident_psi"] and b.info()["cluster"] == cmin
+    l0 = b.info()["launches"]
+    rb = scmc.runAnnealing_(b, 2.0, **kw)
+    assert b.info()["launches"] - l0 <= 12         # the controller ran inside the persistent cluster kernel
+    assert np.array_equal(ra["sweeps"], rb["sweeps"]) and ra["sweeps"].min() > 50
+    assert np.array_equal(ra["beta"], rb["beta"]) and np.array_equal(ra["sigma"], rb["sigma"])
+    assert np.array_equal(a.get_state(), b.get_state())
+    etol = 1e-12 if precision == 64 else 2e-6
+    assert np.allclose(ra["E"], rb["E"], rtol=etol, atol=0)
