@@ -1201,7 +1201,11 @@ int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t s
         // passes are small (launch-bound) or many sweeps run per call; the streaming kernel wins for big batches of large lattices.
         const bool psi = uses_psi_gather(h);
         const int64_t work_per_pass = h->R * h->N / std::max(1, h->n_col);
-        const bool want_resident = h->res.cs >= 1 && h->res.cs <= 2 && (n_sweeps >= 4 || work_per_pass < 300000);
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+        // clusters of up to 2 CTAs, or larger ones when all of them are on the chip at once (few replicas: scmc_create grew the cluster to fill it)
+        const bool cluster_ok = h->res.cs >= 1 && (h->res.cs <= 2 || h->R * h->res.cs <= n_sm);
+        const bool want_resident = cluster_ok && (n_sweeps >= 4 || work_per_pass < 300000);
         if (want_resident && psi && h->res.eligible_psi) return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active, true);
         if (want_resident && !psi && h->res.eligible) { SCMC_TRY(ensure_T(h)); return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active, false); }
     }
@@ -1444,6 +1448,15 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
             const int64_t n_own = (N + c - 1) / c;
             const size_t cap = (size_t)(n_own + 1 + 7) / 8 * 8;
             if (cap * per_site + (size_t)MAXL * 256 * w + 1024 <= (size_t)226 * 1024 && n_own + 1 <= 8191 && N >= c) { cs = c; break; }
+        }
+        // Few replicas (psi family, whose run! and annealing drivers work inside clusters): grow the cluster while all clusters still fit
+        // on the chip in one wave and a CTA keeps >= 512 sites.  Measured (profiles/README.md, cluster size for few replicas): full run! of
+        // 48x48 x 64 replicas 47.5 -> 23.9 ms at cluster 2, x 16 replicas 38.2 -> 16.5 ms at cluster 4; a 72-site lattice loses 35 % in clusters
+        // and a full chip (148 replicas) loses 12-27 %.  Chains do not depend on the cluster size.
+        if (cs >= 1 && psi_family && !(getenv("SCMC_CLUSTER_FILL") && atoi(getenv("SCMC_CLUSTER_FILL")) == 0)) {
+            int n_sm = 148;
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+            while (cs < 8 && n_replicas * (int64_t)(2 * cs) <= n_sm && N / (2 * cs) >= 512) cs *= 2;
         }
         const int64_t n_nom = cs ? (N + cs - 1) / cs : N;
         int32_t at = 0;
