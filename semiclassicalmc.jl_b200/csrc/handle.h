@@ -72,6 +72,11 @@ struct scmc_handle {
     unsigned long long* acc = nullptr;           // [R] accepted-update counters
     uint8_t* active = nullptr;                   // [R] replica still running (annealing) -- nullptr semantics handled by callers
     double* obs = nullptr;                       // [R][SCMC_NOBS] scratch rows
+    // grow-only device scratch of the API calls (every call that uses it synchronises the stream before it returns, so a slot is free again
+    // at the next call).  cudaMalloc / cudaFree per call cost 0.3-1 ms each on a B200 box and now and then 10-300 ms (profiles/README.md).
+    static constexpr int N_SCRATCH = 8;
+    void* scratch[N_SCRATCH] = {nullptr};
+    size_t scratch_bytes[N_SCRATCH] = {0};
     double* d_meas_partial = nullptr;            // [R][parts][17] per-CTA partial sums of the psi-family measurement
     size_t meas_partial_bytes = 0;
     void* pinned = nullptr;                      // pinned host staging for the beta / sigma tables
@@ -104,6 +109,10 @@ int32_t launch_measure(scmc_handle* h, double* d_rows /* device [R][SCMC_NOBS] o
 int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes);
 int32_t ensure_T(scmc_handle* h);      // recompute the cached T (Tsq) planes from psi if a psi-gather sweep left them stale
 bool uses_psi_gather(const scmc_handle* h);
+// device scratch slot of at least `bytes` bytes (kept in the handle, grown on demand); scratch_trim frees slots above 64 MB after a call
+cudaError_t scratch_get(scmc_handle* h, int slot, size_t bytes, void** p);
+void scratch_trim(scmc_handle* h);
+bool resident_preferred(const scmc_handle* h);      // the auto policy's cluster predicate: clusters of <= 2 CTAs, or all clusters on the chip at once
 int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint64_t seed, double att_per_sweep, double min_accepted,
                                double beta_fac, double min_accrate, double sigma_min, int64_t n_per_T, int64_t n_total,
                                int64_t* d_sweeps_at_T, int64_t* d_sweeps_done, int* d_n_active);

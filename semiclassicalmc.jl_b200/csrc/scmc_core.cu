@@ -1104,6 +1104,44 @@ bool uses_psi_gather(const scmc_handle* h) {
     return h->n_labels == 1 && (h->d == 4 || h->onsite) && !h->res_family_T;      // measured: d = 6 without on-site term is on par / slightly faster with T-gather
 }
 
+// Where the replica-resident kernel is the better one (measured, profiles/README.md): clusters of up to 2 CTAs, or larger ones when all of
+// them are on the chip at once (few replicas: scmc_create grew the cluster to fill it).  Many replicas in clusters of 4 or 8 (C5; TG/h-BN
+// 48x48 x 1024: resident 735 us against streaming 360 us per sweep) belong to the streaming kernels -- for plain sweeps and for the
+// device-side run! / annealing drivers alike.
+cudaError_t scratch_get(scmc_handle* h, int slot, size_t bytes, void** p) {
+    if (bytes == 0) bytes = 16;
+    if (h->scratch_bytes[slot] < bytes) {
+        if (h->scratch[slot]) {
+            cudaError_t e = cudaStreamSynchronize(h->stream);
+            if (e != cudaSuccess) return e;
+            cudaFree(h->scratch[slot]);
+            h->scratch[slot] = nullptr; h->scratch_bytes[slot] = 0;
+        }
+        cudaError_t e = cudaMalloc(&h->scratch[slot], bytes);
+        if (e != cudaSuccess) { h->scratch[slot] = nullptr; return e; }
+        h->scratch_bytes[slot] = bytes;
+        h->bytes += 0;      // scratch is not part of the model footprint reported by scmc_info
+    }
+    *p = h->scratch[slot];
+    return cudaSuccess;
+}
+
+void scratch_trim(scmc_handle* h) {
+    for (int i = 0; i < scmc_handle::N_SCRATCH; i++)
+        if (h->scratch[i] && h->scratch_bytes[i] > ((size_t)64 << 20)) {
+            cudaStreamSynchronize(h->stream);
+            cudaFree(h->scratch[i]);
+            h->scratch[i] = nullptr; h->scratch_bytes[i] = 0;
+        }
+}
+
+bool resident_preferred(const scmc_handle* h) {
+    if (h->res.cs < 1) return false;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
+    return h->res.cs <= 2 || h->R * h->res.cs <= n_sm;
+}
+
 int32_t ensure_T(scmc_handle* h) {
     if (!h->T_stale) return SCMC_OK;
     h->T_stale = false;
@@ -1201,11 +1239,7 @@ int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t s
         // passes are small (launch-bound) or many sweeps run per call; the streaming kernel wins for big batches of large lattices.
         const bool psi = uses_psi_gather(h);
         const int64_t work_per_pass = h->R * h->N / std::max(1, h->n_col);
-        int n_sm = 148;
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
-        // clusters of up to 2 CTAs, or larger ones when all of them are on the chip at once (few replicas: scmc_create grew the cluster to fill it)
-        const bool cluster_ok = h->res.cs >= 1 && (h->res.cs <= 2 || h->R * h->res.cs <= n_sm);
-        const bool want_resident = cluster_ok && (n_sweeps >= 4 || work_per_pass < 300000);
+        const bool want_resident = resident_preferred(h) && (n_sweeps >= 4 || work_per_pass < 300000);
         if (want_resident && psi && h->res.eligible_psi) return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active, true);
         if (want_resident && !psi && h->res.eligible) { SCMC_TRY(ensure_T(h)); return launch_resident(h, n_sweeps, hits, seed, sweep_counter, active, false); }
     }
@@ -1449,11 +1483,11 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
             const size_t cap = (size_t)(n_own + 1 + 7) / 8 * 8;
             if (cap * per_site + (size_t)MAXL * 256 * w + 1024 <= (size_t)226 * 1024 && n_own + 1 <= 8191 && N >= c) { cs = c; break; }
         }
-        // Few replicas (psi family, whose run! and annealing drivers work inside clusters): grow the cluster while all clusters still fit
+        // Few replicas (the run! and annealing drivers of both families work inside clusters): grow the cluster while all clusters still fit
         // on the chip in one wave and a CTA keeps >= 512 sites.  Measured (profiles/README.md, cluster size for few replicas): full run! of
         // 48x48 x 64 replicas 47.5 -> 23.9 ms at cluster 2, x 16 replicas 38.2 -> 16.5 ms at cluster 4; a 72-site lattice loses 35 % in clusters
         // and a full chip (148 replicas) loses 12-27 %.  Chains do not depend on the cluster size.
-        if (cs >= 1 && psi_family && !(getenv("SCMC_CLUSTER_FILL") && atoi(getenv("SCMC_CLUSTER_FILL")) == 0)) {
+        if (cs >= 1 && !(getenv("SCMC_CLUSTER_FILL") && atoi(getenv("SCMC_CLUSTER_FILL")) == 0)) {
             int n_sm = 148;
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
             while (cs < 8 && n_replicas * (int64_t)(2 * cs) <= n_sm && N / (2 * cs) >= 512) cs *= 2;
@@ -1586,6 +1620,7 @@ int32_t scmc_destroy(scmc_t* h) {
     cudaSetDevice(h->device);
     void* ptrs[] = {h->d_meas_partial, h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16, h->d_cls_site, h->d_cls_nbr};
     for (void* p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < scmc_handle::N_SCRATCH; i++) if (h->scratch[i]) cudaFree(h->scratch[i]);
     if (h->pinned) cudaFreeHost(h->pinned);
     for (int l = 0; l < 2; l++) {
         if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
@@ -1717,14 +1752,13 @@ int32_t scmc_energy(scmc_t* h, double* E) {
     SCMC_ARG(h && E, "null argument");
     SCMC_CK(cudaSetDevice(h->device));
     double* dE = nullptr;
-    SCMC_CK(cudaMalloc(&dE, h->R * 8));
+    SCMC_CK(scratch_get(h, 7, h->R * 8, (void**)&dE));
     int32_t st = launch_measure(h, nullptr, dE);
     if (st == SCMC_OK) {
         cudaMemcpyAsync(E, dE, h->R * 8, cudaMemcpyDeviceToHost, h->stream);
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) st = cuda_fail(e, "energy sync", __FILE__, __LINE__);
     }
-    cudaFree(dE);
     return st;
 }
 

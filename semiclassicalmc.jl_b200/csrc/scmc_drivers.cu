@@ -310,10 +310,13 @@ static int32_t dispatch_d(const scmc_handle* h, F&& f) {
 }
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
-struct DevBuf {   // RAII device scratch
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+// Device scratch of one API call: a slot of the handle's grow-only pool (no cudaMalloc / cudaFree per call); the last DevBuf of a call
+// trims oversized slots when it goes out of scope.
+struct DevBuf {
+    scmc_handle* h; int slot; void* p = nullptr;
+    DevBuf(scmc_handle* h_, int slot_) : h(h_), slot(slot_) {}
+    ~DevBuf() { if (p && h->scratch_bytes[slot] > ((size_t)64 << 20)) scratch_trim(h); }
+    cudaError_t alloc(size_t bytes) { return scratch_get(h, slot, bytes, &p); }
     template <class T> T* as() { return (T*)p; }
 };
 
@@ -333,7 +336,7 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
     const int64_t total = p->n_therm + p->n_measure;
     const int64_t meas_start = std::max<int64_t>(p->n_therm + 1, (int64_t)p->sweep0 + 1);
     const int64_t rows_total = total >= meas_start ? total / rate - (meas_start - 1) / rate : 0;
-    DevBuf dT, dTi, dser;
+    DevBuf dT(h, 0), dTi(h, 1), dser(h, 2);
     SCMC_CK(dT.alloc(R * 8)); SCMC_CK(dTi.alloc(R * 8));
     SCMC_CK(cudaMemcpyAsync(dT.p, p->T, R * 8, cudaMemcpyHostToDevice, h->stream));
     SCMC_CK(cudaMemcpyAsync(dTi.p, p->T_i, R * 8, cudaMemcpyHostToDevice, h->stream));
@@ -358,14 +361,15 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
     // Device-side driver: when every replica lives in one CTA or one cluster of the psi-family resident kernel, the whole schedule (beta ramp,
     // sigma adaptation, measurement rows) runs inside the persistent kernel, up to 512 sweeps per launch; chains are identical to the
     // host-driven path below, measurement rows agree to rounding (energies re-summed from the resident states).
-    const bool device_side = uses_psi_gather(h) && h->res.eligible_psi && h->res.cs >= 1 && (h->sweep_mode == 0 || h->sweep_mode == 4);
+    const bool psi_fam = uses_psi_gather(h);
+    const bool device_side = (psi_fam ? h->res.eligible_psi : h->res.eligible) && (resident_preferred(h) || h->sweep_mode != 0) && (h->sweep_mode == 0 || h->sweep_mode == (psi_fam ? 4 : 2));
     // ---- thermalisation (MonteCarlo.jl:38-66)
     int64_t n_log = 0;
     if (device_side) {
         // energy log entries (one per sigma-adaptation point) are written by the kernel into one device table, copied out at the end
         const int64_t log_base = (int64_t)p->sweep0 / rate + 1;       // g / rate of the first entry
         const int64_t n_log_total = std::max<int64_t>(0, p->n_therm / rate - (int64_t)p->sweep0 / rate);
-        DevBuf dlog;
+        DevBuf dlog(h, 3);
         if (out->therm_energy && n_log_total > 0) SCMC_CK(dlog.alloc((size_t)n_log_total * R * 8));
         for (int64_t sweep = (int64_t)p->sweep0 + 1; sweep <= p->n_therm;) {
             const int64_t chunk = std::min<int64_t>(512, p->n_therm - sweep + 1);
@@ -477,7 +481,7 @@ int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results*
     std::vector<double> b0(R, 1.0 / p->T_i), s0(R, p->sigma0);
     SCMC_TRY(upload_scalars(h, b0.data(), s0.data()));
     SCMC_CK(cudaStreamSynchronize(h->stream));
-    DevBuf dsat, ddone, dnact;
+    DevBuf dsat(h, 0), ddone(h, 1), dnact(h, 2);
     SCMC_CK(dsat.alloc(R * 8)); SCMC_CK(ddone.alloc(R * 8)); SCMC_CK(dnact.alloc(sizeof(int)));
     SCMC_CK(cudaMemsetAsync(dsat.p, 0, R * 8, h->stream));
     SCMC_CK(cudaMemsetAsync(ddone.p, 0, R * 8, h->stream));
@@ -489,7 +493,8 @@ int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results*
     const int check_every = 16;
     // Device-side driver: when every replica lives in ONE CTA of the psi-family resident kernel, the whole cooling loop
     // (acceptance window, beta / sigma updates, stop flag) runs inside the persistent kernel, `chunk` sweeps per launch.
-    const bool device_side = uses_psi_gather(h) && h->res.eligible_psi && h->res.cs >= 1 && (h->sweep_mode == 0 || h->sweep_mode == 4) && p->N_max > 1;
+    const bool psi_fam = uses_psi_gather(h);
+    const bool device_side = (psi_fam ? h->res.eligible_psi : h->res.eligible) && (resident_preferred(h) || h->sweep_mode != 0) && (h->sweep_mode == 0 || h->sweep_mode == (psi_fam ? 4 : 2)) && p->N_max > 1;
     if (device_side) {
         const int64_t n_total = p->N_max - 1;
         for (int64_t launched = 0; launched < n_total && n_active > 0;) {
@@ -571,7 +576,7 @@ int32_t scmc_structure_factor(scmc_t* h, const double* ks, const double* pos, in
     std::vector<double> ppos((size_t)h->N * dim);
     for (int64_t q = 0; q < h->N; q++)
         for (int x = 0; x < dim; x++) ppos[(size_t)q * dim + x] = pos[(size_t)h->orig[q] * dim + x];
-    DevBuf dk, dp, dout;
+    DevBuf dk(h, 0), dp(h, 1), dout(h, 2);
     SCMC_CK(dk.alloc((size_t)nk * dim * 8)); SCMC_CK(dp.alloc(ppos.size() * 8));
     const size_t out_bytes = (size_t)h->R * 16 * nk * 8;
     SCMC_CK(dout.alloc(out_bytes));
@@ -597,7 +602,7 @@ int32_t scmc_correlations(scmc_t* h, int64_t r, const int32_t* project, int64_t 
     for (int64_t t = 0; t < h->N * h->N; t++) SCMC_ARG(project[t] >= 0 && project[t] < n_rs, "scmc_correlations: project index out of range");
     SCMC_CK(cudaSetDevice(h->device));
     SCMC_TRY(ensure_T(h));
-    DevBuf dproj, dperm, dC;
+    DevBuf dproj(h, 0), dperm(h, 1), dC(h, 2);
     SCMC_CK(dproj.alloc((size_t)h->N * h->N * 4)); SCMC_CK(dperm.alloc(h->N * 4)); SCMC_CK(dC.alloc((size_t)16 * n_rs * 8));
     SCMC_CK(cudaMemcpyAsync(dproj.p, project, (size_t)h->N * h->N * 4, cudaMemcpyHostToDevice, h->stream));
     SCMC_CK(cudaMemcpyAsync(dperm.p, h->perm.data(), h->N * 4, cudaMemcpyHostToDevice, h->stream));
@@ -623,7 +628,7 @@ int32_t scmc_sublattice_magnetization(scmc_t* h, const int32_t* site_label, int3
         lp[q] = site_label[h->orig[q]];
         SCMC_ARG(lp[q] >= 0 && lp[q] < n_sub, "scmc_sublattice_magnetization: label out of range");
     }
-    DevBuf dl, dout;
+    DevBuf dl(h, 0), dout(h, 1);
     const size_t ob = (size_t)h->R * n_sub * 16 * 8;
     SCMC_CK(dl.alloc(h->N * 4)); SCMC_CK(dout.alloc(ob));
     SCMC_CK(cudaMemcpyAsync(dl.p, lp.data(), h->N * 4, cudaMemcpyHostToDevice, h->stream));
@@ -647,7 +652,7 @@ int32_t scmc_chirality(scmc_t* h, const int32_t* tri, double* out) {
             SCMC_ARG(j >= 0 && j < h->N, "scmc_chirality: site index out of range");
             tp[(size_t)q * 4 + m] = h->perm[j];
         }
-    DevBuf dt, dout;
+    DevBuf dt(h, 0), dout(h, 1);
     SCMC_CK(dt.alloc(tp.size() * 4)); SCMC_CK(dout.alloc((size_t)h->R * 3 * 8));
     SCMC_CK(cudaMemcpyAsync(dt.p, tp.data(), tp.size() * 4, cudaMemcpyHostToDevice, h->stream));
     if (h->prec == 64) k_chirality<double><<<(unsigned)h->R, 256, 0, h->stream>>>((const double4*)h->T, (int)h->N, (int)h->Ns, h->R, dt.as<int32_t>(), dout.as<double>());

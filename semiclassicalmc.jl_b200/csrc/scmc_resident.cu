@@ -71,7 +71,29 @@ template <bool CLUSTER> __device__ __forceinline__ double4 ld_v4(uint32_t addr, 
     return v;
 }
 
-// One replica at a time per cluster; grid = n_clusters * cs CTAs, persistent over replicas.
+// FP64 value of another CTA of the cluster (or of this CTA when CLUSTER is false) at shared address `addr`
+template <bool CLUSTER> __device__ __forceinline__ double ld_f64(uint32_t addr) {
+    double v;
+    if (CLUSTER) asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// Sum of one FP64 value per CTA over the cluster, added in rank order in every CTA (identical result everywhere, deterministic).
+// `slot` is a __shared__ double of this CTA; two cluster barriers.  Without a cluster: the value itself.
+template <bool CLUSTER> __device__ __forceinline__ double cluster_sum(double x, double* slot, int cs, int tid) {
+    if (!CLUSTER) return x;
+    if (tid == 0) *slot = x;
+    cg::this_cluster().sync();
+    double v = 0.0;
+    for (int b = 0; b < cs; b++) v += ld_f64<CLUSTER>(map_to_rank(smem_u32(slot), (uint32_t)b));
+    cg::this_cluster().sync();
+    return v;
+}
+
+// One replica at a time per cluster; grid = n_clusters * cs CTAs, persistent over replicas.  T-gather family: psi, T (Tsq) of the replica
+// live in (distributed) shared memory.  Besides plain sweeps the kernel runs the device-side schedules of k_resident_psi: runAnnealing!'s
+// cooling loop (A.anneal) and run! (A.run_mode 1 = thermalisation chunk, 2 = measurement chunk), with the same control flow and formulas.
 template <class R, int GEN, bool ONSITE, int NL, bool CLUSTER>
 __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ DevModel<R, NL> M, const __grid_constant__ ResidentArgs A) {
     constexpr int D = GenOps<GEN>::D;
@@ -86,6 +108,8 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
     uint16_t* sNbr = reinterpret_cast<uint16_t*>(sJt + NL * NG * NG);        // [z][nmax]
     int8_t* sLab = reinterpret_cast<int8_t*>(sNbr + (size_t)M.z * nmax);     // [z][nmax] (NL > 1 only)
     __shared__ unsigned s_acc;
+    __shared__ double s_red[16][NG + 1];                          // measurement reduction (one row per warp)
+    __shared__ double s_xchg[NG + 1];                             // this CTA's partial sums, read by the other CTAs of the cluster
 
     unsigned rank = 0, cluster_id = blockIdx.x;
     if (CLUSTER) {
@@ -112,6 +136,34 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
     const uint32_t sT_u32 = smem_u32(sT);
     const uint32_t plane_bytes = (uint32_t)cap * (uint32_t)sizeof(V);
 
+    // local field of my site q from the neighbours' T vectors in (distributed) shared memory: h = sum_l J_l sum_{j in l} T_j
+    auto field_at = [&](int q, R* h) {
+        R S[NL][NG];
+#pragma unroll
+        for (int l = 0; l < NL; l++)
+#pragma unroll
+            for (int a = 0; a < NG; a++) S[l][a] = R(0);
+#pragma unroll 3
+        for (int k = 0; k < M.z; k++) {
+            const unsigned code = sNbr[k * nmax + q];
+            const int l = NL == 1 ? 0 : sLab[k * nmax + q];
+            uint32_t addr = sT_u32 + (code & 0x1FFFu) * (uint32_t)sizeof(V);
+            if (CLUSTER) addr = map_to_rank(addr, code >> 13);
+            V v[4];
+#pragma unroll
+            for (int p4 = 0; p4 < 4; p4++) v[p4] = ld_v4<CLUSTER>(addr + p4 * plane_bytes, R(0));
+#pragma unroll
+            for (int ll = 0; ll < NL; ll++)
+                if (NL == 1 || l == ll) {
+#pragma unroll
+                    for (int p4 = 0; p4 < 4; p4++) {
+                        S[ll][4 * p4] += v[p4].x; S[ll][4 * p4 + 1] += v[p4].y; S[ll][4 * p4 + 2] += v[p4].z; S[ll][4 * p4 + 3] += v[p4].w;
+                    }
+                }
+        }
+        field_from_sums_smem<NL>(sJt, S, h);
+    };
+
     for (int64_t r = cluster_id; r < A.nrep; r += A.n_clusters) {
         if (A.active != nullptr && !A.active[r]) continue;          // uniform over the cluster
         const int64_t gbase = r * M.Ns + my_off;
@@ -126,12 +178,32 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
                 for (int v = 0; v < 4; v++) sTsq[v * cap + q] = M.Tsq[gbase + q + v * ps];
             }
         }
-        const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
-        const R nbeta = neg_beta_scaled(beta);
+        R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+        R nbeta = neg_beta_scaled(beta);
+        // annealing state of this replica (every thread of every CTA keeps identical copies; the controller is deterministic)
+        const bool anneal = A.anneal != 0;
+        int64_t an_done = anneal ? A.sweeps_done[r] : 0, an_sat = anneal ? A.sweeps_at_T[r] : 0;
+        double an_acc = anneal ? (double)A.acc[r] : 0.0;
+        bool an_still = true;
+        // run! schedule of this replica; run_acc is this CTA's share of the window's accepted updates (rank 0 carries the count over)
+        const int run = A.run_mode;
+        double run_acc = (run && rank == 0) ? (double)A.acc[r] : 0.0;
+        const double run_T = run == 1 ? A.run_T[r] : 1.0, run_Ti = run == 1 ? A.run_Ti[r] : 1.0;
         if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
         unsigned nacc = 0;
-        for (int sweep = 0; sweep < A.n_sweeps; sweep++) {
-            const uint64_t visit_base = A.visit0 + (uint64_t)sweep * (uint64_t)A.hits;
+        for (int sweep = 0; sweep < A.n_sweeps && an_still; sweep++) {
+            if (anneal && an_done >= A.n_total) break;
+            const int64_t g = A.sweep_first + sweep;               // 1-based global sweep index (run modes)
+            if (run == 1) {                                        // geometric ramp T_i -> T over the first n_anneal sweeps (MonteCarlo.jl:24-27)
+                double t = run_T;
+                if (g <= A.n_anneal && A.n_anneal > 1) t = run_Ti * pow(run_T / run_Ti, (double)(g - 1) / (double)(A.n_anneal - 1));
+                beta = (R)(1.0 / t);
+                nbeta = neg_beta_scaled(beta);
+            }
+            const uint64_t visit_base = anneal ? (uint64_t)an_done * (uint64_t)A.hits
+                                        : run  ? (uint64_t)(g - 1) * (uint64_t)A.hits
+                                               : A.visit0 + (uint64_t)sweep * (uint64_t)A.hits;
+            unsigned sweep_acc = 0;
             for (int c = 0; c < M.n_col; c++) {
                 const int c0 = A.cta_col_off[rank][c], cnt = A.cta_col_off[rank][c + 1] - c0;
                 for (int s = tid; s < cnt; s += nth) {
@@ -141,32 +213,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
                     load_T<R>(sT + q, (size_t)cap, T);
                     if (ONSITE) load_T<R>(sTsq + q, (size_t)cap, Tsq);
                     const int site = M.orig[my_off + q];
-                    {
-                        R S[NL][NG];
-#pragma unroll
-                        for (int l = 0; l < NL; l++)
-#pragma unroll
-                            for (int a = 0; a < NG; a++) S[l][a] = R(0);
-#pragma unroll 3
-                        for (int k = 0; k < M.z; k++) {
-                            const unsigned code = sNbr[k * nmax + q];
-                            const int l = NL == 1 ? 0 : sLab[k * nmax + q];
-                            uint32_t addr = sT_u32 + (code & 0x1FFFu) * (uint32_t)sizeof(V);
-                            if (CLUSTER) addr = map_to_rank(addr, code >> 13);
-                            V v[4];
-#pragma unroll
-                            for (int p4 = 0; p4 < 4; p4++) v[p4] = ld_v4<CLUSTER>(addr + p4 * plane_bytes, R(0));
-#pragma unroll
-                            for (int ll = 0; ll < NL; ll++)
-                                if (NL == 1 || l == ll) {
-#pragma unroll
-                                    for (int p4 = 0; p4 < 4; p4++) {
-                                        S[ll][4 * p4] += v[p4].x; S[ll][4 * p4 + 1] += v[p4].y; S[ll][4 * p4 + 2] += v[p4].z; S[ll][4 * p4 + 3] += v[p4].w;
-                                    }
-                                }
-                        }
-                        field_from_sums_smem<NL>(sJt, S, h);
-                    }
+                    field_at(q, h);
                     R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
                     unsigned mine = 0;
                     for (int hit = 0; hit < A.hits; hit++) {
@@ -179,13 +226,117 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
                         store_T<R>(sT + q, (size_t)cap, T);
                         if (ONSITE) store_T<R>(sTsq + q, (size_t)cap, Tsq);
                     }
-                    nacc += mine;
+                    sweep_acc += mine;
                 }
                 // all CTAs finish the colour class before anyone reads its T vectors (release/acquire at cluster scope)
                 if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
             }
+            if (!run && !anneal) { nacc += sweep_acc; continue; }
+            // ---- schedules: accepted updates of this sweep in my CTA
+            {
+                const unsigned wt = __reduce_add_sync(0xffffffffu, sweep_acc);
+                if ((tid & 31) == 0 && wt) atomicAdd(&s_acc, wt);
+                __syncthreads();
+            }
+            const double mine_sweep = (double)s_acc;
+            __syncthreads();
+            if (tid == 0) s_acc = 0;
+            if (run) {
+                run_acc += mine_sweep;
+                if (g % A.rate == 0) {
+                    if (run == 1) {                                // sigma <- min(sigma * 0.5 / (1 - R), 60)  (MonteCarlo.jl:50-53)
+                        const double acc_all = cluster_sum<CLUSTER>(run_acc, &s_xchg[0], A.cs, tid);
+                        const double ratio = acc_all / A.att_window;
+                        sigma = (R)fmin((double)sigma * 0.5 / (1.0 - ratio), 60.0);
+                        run_acc = 0.0;
+                    }
+                    // E and sum_i T_i from the resident T (Tsq) vectors (measure!, ObservablesGeneric.jl:32-46; thermalisation energy log,
+                    // MonteCarlo.jl:48-49): run == 2 writes a measure! row, run == 1 logs E/N
+                    if (run == 2 || A.rows != nullptr) {
+                        double eacc = 0.0, macc[NG];
+#pragma unroll
+                        for (int t = 0; t < NG; t++) macc[t] = 0.0;
+                        for (int q = tid; q < n_own; q += nth) {
+                            R T[NG], h[NG];
+                            load_T<R>(sT + q, (size_t)cap, T);
+                            field_at(q, h);
+                            R e = R(0);
+#pragma unroll
+                            for (int t = 0; t < NG; t++) e = fma(T[t], h[t], e);
+                            e *= R(0.5);
+                            if (ONSITE) {
+                                R Tsq[NG];
+                                load_T<R>(sTsq + q, (size_t)cap, Tsq);
+#pragma unroll
+                                for (int t = 0; t < NG; t++) e = fma(Tsq[t], M.cp.K[t], e);
+                            }
+                            eacc += (double)e;
+#pragma unroll
+                            for (int t = 0; t < NG; t++) macc[t] += (double)T[t];
+                        }
+                        const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+                        for (int t = 0; t <= NG; t++) {
+                            double v = t < NG ? macc[t < NG ? t : 0] : eacc;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                            if (lane == 0) s_red[warp][t] = v;
+                        }
+                        __syncthreads();
+                        if (tid <= NG) {
+                            double v = 0.0;
+                            for (int w = 0; w < (nth >> 5); w++) v += s_red[w][tid];
+                            s_xchg[tid] = v;
+                        }
+                        if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
+                        if (tid == 0 && rank == 0) {
+                            double tot[NG + 1];
+                            for (int t = 0; t <= NG; t++) {
+                                double v = 0.0;
+                                for (int b = 0; b < (CLUSTER ? A.cs : 1); b++) v += ld_f64<CLUSTER>(CLUSTER ? map_to_rank(smem_u32(&s_xchg[t]), (uint32_t)b) : smem_u32(&s_xchg[t]));
+                                tot[t] = v;
+                            }
+                            const double E = tot[NG] + A.e_const, invN = 1.0 / (double)M.N;
+                            const size_t slot = (size_t)(g / A.rate - A.row_base) * A.nrep + r;
+                            if (run == 1) {
+                                A.rows[slot] = E * invN;
+                            } else {
+                                double* row = A.rows + slot * SCMC_NOBS;
+                                double m[NG];
+                                for (int t = 0; t < NG; t++) m[t] = tot[t] * invN;
+                                row[0] = E * invN;
+                                row[1] = (E * invN) * (E * invN);
+                                row[2] = sqrt(m[4] * m[4] + m[8] * m[8] + m[12] * m[12]);
+                                row[3] = sqrt(m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
+                                row[4] = sqrt(m[5] * m[5] + m[6] * m[6] + m[7] * m[7] + m[9] * m[9] + m[10] * m[10] + m[11] * m[11] + m[13] * m[13] +
+                                              m[14] * m[14] + m[15] * m[15]);
+                                for (int t = 0; t < NG; t++) row[5 + t] = m[t];
+                            }
+                        }
+                        // nobody overwrites T vectors or the exchange slots before every CTA is done reading them
+                        if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
+                    }
+                }
+            } else {
+                // accepted updates of this sweep over the whole replica, then the cooling rule (MonteCarlo.jl:151-203)
+                an_acc += cluster_sum<CLUSTER>(mine_sweep, &s_xchg[0], A.cs, tid);
+                an_sat++; an_done++;
+                const bool last = an_done >= A.n_total;
+                if (!(an_acc < A.min_accepted && an_sat < A.n_per_T && !last)) {
+                    const double ratio = an_acc / (A.att_per_sweep * (double)an_sat);
+                    if (ratio > A.min_accrate) {
+                        beta = (R)((double)beta * A.beta_fac);
+                        sigma = (R)fmax(fmin((double)sigma * 0.5 / (1.0 - ratio), 60.0), A.sigma_min);
+                        nbeta = neg_beta_scaled(beta);
+                        an_acc = 0.0; an_sat = 0;
+                    } else {
+                        an_still = false;
+                    }
+                }
+                __syncthreads();
+            }
         }
-        // ---- store my strip (state out) and the acceptance count
+        // ---- store my strip (state out)
         for (int q = tid; q < n_own; q += nth) {
 #pragma unroll
             for (int v = 0; v < NPV; v++) M.psi[gbase + q + v * ps] = sPsi[v * cap + q];
@@ -195,6 +346,27 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
 #pragma unroll
                 for (int v = 0; v < 4; v++) M.Tsq[gbase + q + v * ps] = sTsq[v * cap + q];
             }
+        }
+        if (run) {
+            const double acc_all = cluster_sum<CLUSTER>(run_acc, &s_xchg[0], A.cs, tid);
+            if (tid == 0 && rank == 0) {
+                ((R*)A.sigma)[r] = sigma;
+                A.acc[r] = (unsigned long long)acc_all;
+            }
+            __syncthreads();
+            continue;
+        }
+        if (anneal) {
+            if (tid == 0 && rank == 0) {
+                ((R*)A.beta)[r] = beta; ((R*)A.sigma)[r] = sigma;
+                A.acc[r] = (unsigned long long)an_acc;
+                A.sweeps_at_T[r] = an_sat; A.sweeps_done[r] = an_done;
+                const bool running = an_still && an_done < A.n_total;
+                A.active_rw[r] = an_still ? 1 : 0;
+                if (running) atomicAdd(A.n_active, 1);
+            }
+            __syncthreads();
+            continue;
         }
         const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
         if ((tid & 31) == 0 && tot) atomicAdd(&s_acc, tot);
@@ -212,14 +384,6 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
 // psi-gather family (same arithmetic as k_sweep_colour_psi, bit-identical chains): only psi lives in shared memory
 // (d/2 x 16 B per site instead of psi + T), neighbours are read as states through DSMEM and enter through density-matrix sums.
 // C5 (128 x 128, FP32): 16384 x (32 + 12) B = 704 KB -> cluster of 4 CTAs x 177 KB, all 148 SMs busy.
-// FP64 value of another CTA of the cluster (or of this CTA when CLUSTER is false) at shared address `addr`
-template <bool CLUSTER> __device__ __forceinline__ double ld_f64(uint32_t addr) {
-    double v;
-    if (CLUSTER) asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
-}
-
 template <class R, int GEN, bool ONSITE, bool CLUSTER>
 __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__ DevModel<R, 1> M, const __grid_constant__ ResidentArgs A) {
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
@@ -714,18 +878,48 @@ int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t
 }
 
 
+// Launch of the persistent kernel of one arithmetic family with a filled ResidentArgs (cluster attribute when a replica spans several CTAs)
+template <class R, int GEN, bool ONS, int NL>
+static int32_t launch_family_kernel(scmc_handle* h, const DevModel<R, NL>& M, ResidentArgs& A, bool psi) {
+    auto& P = h->res;
+    A.n_clusters = (int32_t)std::min<int64_t>(h->R, psi ? P.max_clusters_psi : P.max_clusters);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(A.n_clusters * P.cs)); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = psi ? P.smem_psi : P.smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    cfg.attrs = at; cfg.numAttrs = 0;
+    if (P.cs > 1) {
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = P.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.numAttrs = 1;
+    }
+    if (psi) {
+        if constexpr (NL == 1) {
+            if (P.cs > 1) SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, true>, M, A));
+            else SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, false>, M, A));
+        } else {
+            return SCMC_ERR_UNSUPPORTED;
+        }
+    } else {
+        if (P.cs > 1) SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident<R, GEN, ONS, NL, true>, M, A));
+        else SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident<R, GEN, ONS, NL, false>, M, A));
+    }
+    h->launches++;
+    return SCMC_OK;
+}
+
 // Device-side cooling loop for single-CTA psi-family replicas: up to `chunk` sweeps per launch, controller inside the kernel.
 // Returns through *n_active how many replicas are still cooling and have budget left.
 int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint64_t seed, double att_per_sweep, double min_accepted,
                                double beta_fac, double min_accrate, double sigma_min, int64_t n_per_T, int64_t n_total,
                                int64_t* d_sweeps_at_T, int64_t* d_sweeps_done, int* d_n_active) {
     auto& P = h->res;
-    h->T_stale = true;
+    const bool psi = uses_psi_gather(h);
+    if (psi) h->T_stale = true; else SCMC_TRY(ensure_T(h));      // the T-gather kernel keeps the T (Tsq) planes current
     return dispatch_r(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
         constexpr bool ONS = decltype(ons)::value != 0;
-        if constexpr (NL != 1) { return SCMC_ERR_UNSUPPORTED; } else {
+        {
             auto M = make_model_r<R, NL>(h);
             ResidentArgs A;
             memset(&A, 0, sizeof A);
@@ -734,40 +928,27 @@ int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint
             A.active = h->active; A.acc = h->acc; A.nbr16 = h->d_nbr16;
             memcpy(A.cta_off, P.cta_off, sizeof A.cta_off);
             memcpy(A.cta_col_off, P.cta_col_off, sizeof A.cta_col_off);
-            A.n_clusters = (int32_t)std::min<int64_t>(h->R, P.max_clusters_psi);
             A.n_sweeps = (int32_t)chunk; A.visit0 = 0;
             A.anneal = 1; A.att_per_sweep = att_per_sweep; A.min_accepted = min_accepted; A.beta_fac = beta_fac; A.min_accrate = min_accrate;
             A.sigma_min = sigma_min; A.n_per_T = n_per_T; A.n_total = n_total; A.sweeps_at_T = d_sweeps_at_T; A.sweeps_done = d_sweeps_done;
             A.active_rw = h->active; A.n_active = d_n_active;
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)(A.n_clusters * P.cs)); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem_psi; cfg.stream = h->stream;
-            cudaLaunchAttribute at[1];
-            cfg.attrs = at; cfg.numAttrs = 0;
-            if (P.cs > 1) {
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = P.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                cfg.numAttrs = 1;
-                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, true>, M, A));
-            } else {
-                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, false>, M, A));
-            }
-            h->launches++;
-            return SCMC_OK;
+            return launch_family_kernel<R, GEN, ONS, NL>(h, M, A, psi);
         }
     });
 }
 
 
-// One chunk of the device-side run! schedule (single-CTA psi-family replicas): mode 1 = thermalisation, 2 = measurement.
+// One chunk of the device-side run! schedule (either family, any cluster size): mode 1 = thermalisation, 2 = measurement.
 int32_t launch_resident_run(scmc_handle* h, int mode, int64_t chunk, int32_t hits, uint64_t seed, const double* d_T, const double* d_Ti,
                             int64_t n_anneal, int64_t rate, int64_t sweep_first, int64_t row_base, double* d_rows) {
     auto& P = h->res;
-    h->T_stale = true;
+    const bool psi = uses_psi_gather(h);
+    if (psi) h->T_stale = true; else SCMC_TRY(ensure_T(h));      // the T-gather kernel keeps the T (Tsq) planes current
     return dispatch_r(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
         constexpr bool ONS = decltype(ons)::value != 0;
-        if constexpr (NL != 1) { return SCMC_ERR_UNSUPPORTED; } else {
+        {
             auto M = make_model_r<R, NL>(h);
             ResidentArgs A;
             memset(&A, 0, sizeof A);
@@ -776,24 +957,10 @@ int32_t launch_resident_run(scmc_handle* h, int mode, int64_t chunk, int32_t hit
             A.active = nullptr; A.acc = h->acc; A.nbr16 = h->d_nbr16;
             memcpy(A.cta_off, P.cta_off, sizeof A.cta_off);
             memcpy(A.cta_col_off, P.cta_col_off, sizeof A.cta_col_off);
-            A.n_clusters = (int32_t)std::min<int64_t>(h->R, P.max_clusters_psi);
             A.n_sweeps = (int32_t)chunk;
             A.run_mode = mode; A.run_T = d_T; A.run_Ti = d_Ti; A.n_anneal = n_anneal; A.rate = rate; A.sweep_first = sweep_first; A.row_base = row_base;
             A.att_window = (double)hits * (double)h->N * (double)rate; A.e_const = h->e_const; A.rows = d_rows;
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3((unsigned)(A.n_clusters * P.cs)); cfg.blockDim = dim3(P.nthreads); cfg.dynamicSmemBytes = P.smem_psi; cfg.stream = h->stream;
-            cudaLaunchAttribute at[1];
-            cfg.attrs = at; cfg.numAttrs = 0;
-            if (P.cs > 1) {      // several CTAs per replica: acceptance counts and measurement sums are reduced through DSMEM inside the kernel
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = P.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                cfg.numAttrs = 1;
-                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, true>, M, A));
-            } else {
-                SCMC_CK(cudaLaunchKernelEx(&cfg, k_resident_psi<R, GEN, ONS, false>, M, A));
-            }
-            h->launches++;
-            return SCMC_OK;
+            return launch_family_kernel<R, GEN, ONS, NL>(h, M, A, psi);
         }
     });
 }

@@ -523,3 +523,72 @@ def test_device_side_annealing_in_clusters_equals_host_driven_loop(scmc, monkeyp
     assert np.array_equal(a.get_state(), b.get_state())
     etol = 1e-12 if precision == 64 else 2e-6
     assert np.allclose(ra["E"], rb["E"], rtol=etol, atol=0)
+
+
+def _t_family_model(scmc, kind, R, precision, seed):
+    if kind == "tghbn_n2":
+        return scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.1, 0.5], 12, 2, n_replicas=R, precision=precision, seed=seed)
+    if kind == "tghbn_n1":
+        return scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.1, 0.5], 12, 1, n_replicas=R, precision=precision, seed=seed)
+    if kind == "honey_n2":          # d = 6 without on-site term: T-gather family in auto mode
+        return scmc.initializeCfg("nearest-neighbor", "honeycomb", [np.eye(16)], 8, 2, n_replicas=R, precision=precision, seed=seed)
+    if kind == "tri_forced":        # psi-family model driven through the T-gather kernels (modes 1 / 2)
+        return scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 12, 1, n_replicas=R, precision=precision, seed=seed)
+    raise KeyError(kind)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind, cmin, precision", [("tghbn_n2", 1, 32), ("tghbn_n2", 2, 32), ("tghbn_n1", 1, 32), ("honey_n2", 1, 32), ("honey_n2", 2, 64),
+                                                   ("tri_forced", 1, 32), ("tghbn_n2", 1, 64)])
+def test_t_family_device_side_run_equals_host_driven_schedule(scmc, monkeypatch, kind, cmin, precision):
+    """run! inside the persistent T-gather kernel (one CTA or a cluster per replica) vs the host-driven schedule on the streaming T-gather
+    kernel: identical chains, adapted sigma and acceptance rates; measurement rows and the thermalisation log equal to rounding."""
+    R = 6
+    Ts = np.geomspace(0.05, 1.5, R)
+    def mk(c):
+        monkeypatch.setenv("SCMC_CLUSTER_MIN", str(c))
+        return _t_family_model(scmc, kind, R, precision, 2024)
+    a = mk(1); a.set_sweep_mode(1)              # streaming T-gather kernel, host-driven schedule
+    ra = scmc.run_(a, None, Ts, 2.0, 120, 150, measurement_rate=10)
+    b = mk(cmin)
+    if kind == "tri_forced": b.set_sweep_mode(2)
+    assert b.info()["resident"] and b.info()["cluster"] == cmin
+    l0 = b.info()["launches"]
+    rb = scmc.run_(b, None, Ts, 2.0, 120, 150, measurement_rate=10)
+    assert b.info()["launches"] - l0 <= 8      # the schedule ran inside the persistent kernel
+    assert a.info()["launches"] > 100
+    assert ra["rows"] == rb["rows"] == 15
+    assert np.array_equal(ra["sigma"], rb["sigma"]) and np.array_equal(ra["acc_rate"], rb["acc_rate"])
+    assert np.array_equal(a.get_state(), b.get_state())
+    assert np.array_equal(a.get_T(R - 1), b.get_T(R - 1))
+    tol = 1e-10 if precision == 64 else 2e-5
+    assert np.allclose(ra["series"], rb["series"], rtol=tol, atol=tol)
+    assert np.allclose(ra["mean"], rb["mean"], rtol=tol, atol=tol)
+    assert np.allclose(ra["therm_energy"], rb["therm_energy"], rtol=tol, atol=tol)
+    ra2 = scmc.run_(a, None, Ts, 2.0, 120, 205, measurement_rate=10, current_sweep=270, σ=ra["sigma"])
+    rb2 = scmc.run_(b, None, Ts, 2.0, 120, 205, measurement_rate=10, current_sweep=270, σ=rb["sigma"])
+    assert ra2["rows"] == rb2["rows"] and np.array_equal(a.get_state(), b.get_state())
+    assert np.array_equal(ra2["acc_rate"], rb2["acc_rate"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind, cmin, precision", [("tghbn_n2", 1, 32), ("tghbn_n2", 2, 32), ("honey_n2", 1, 64), ("tri_forced", 2, 32)])
+def test_t_family_device_side_annealing_equals_host_driven_loop(scmc, monkeypatch, kind, cmin, precision):
+    """runAnnealing!'s cooling loop inside the persistent T-gather kernel vs the loop driven from the host one sweep at a time."""
+    def mk(c):
+        monkeypatch.setenv("SCMC_CLUSTER_MIN", str(c))
+        return _t_family_model(scmc, kind, 8, precision, 777)
+    kw = dict(T_fac=0.9, N_max=500, N_o=0, N_per_T=20, min_acc_per_site=3, min_accrate=0.02, σ_min=0.05)
+    a = mk(1); a.set_sweep_mode(1)
+    ra = scmc.runAnnealing_(a, 2.0, **kw)
+    b = mk(cmin)
+    if kind == "tri_forced": b.set_sweep_mode(2)
+    assert b.info()["resident"] and b.info()["cluster"] == cmin
+    l0 = b.info()["launches"]
+    rb = scmc.runAnnealing_(b, 2.0, **kw)
+    assert b.info()["launches"] - l0 <= 12 and a.info()["launches"] > 300
+    assert np.array_equal(ra["sweeps"], rb["sweeps"]) and ra["sweeps"].min() > 50
+    assert np.array_equal(ra["beta"], rb["beta"]) and np.array_equal(ra["sigma"], rb["sigma"])
+    assert np.array_equal(a.get_state(), b.get_state())
+    etol = 1e-12 if precision == 64 else 2e-6
+    assert np.allclose(ra["E"], rb["E"], rtol=etol, atol=0)
