@@ -1104,10 +1104,11 @@ bool uses_psi_gather(const scmc_handle* h) {
     return h->n_labels == 1 && (h->d == 4 || h->onsite) && !h->res_family_T;      // measured: d = 6 without on-site term is on par / slightly faster with T-gather
 }
 
-// Where the replica-resident kernel is the better one (measured, profiles/README.md): clusters of up to 2 CTAs, or larger ones when all of
-// them are on the chip at once (few replicas: scmc_create grew the cluster to fill it).  Many replicas in clusters of 4 or 8 (C5; TG/h-BN
-// 48x48 x 1024: resident 735 us against streaming 360 us per sweep) belong to the streaming kernels -- for plain sweeps and for the
-// device-side run! / annealing drivers alike.
+// Where the replica-resident kernel is the better one (measured, profiles/README.md): clusters of up to 2 CTAs, or larger ones when they
+// need at most two waves over the chip (few replicas; run! of TG/h-BN 48x48 x 64 in clusters of 4 = 256 CTAs: 50 ms resident against 65 ms
+// streaming, x 128 = 512 CTAs: 100 against 81 ms; psi family 128x128 x 64: equal, x 148: 196 against 145 ms).  Many replicas in clusters of 4
+// or 8 (C5; TG/h-BN 48x48 x 1024: resident 735 us against streaming 360 us per sweep) belong to the streaming kernels -- for plain sweeps
+// and for the device-side run! / annealing drivers alike.
 cudaError_t scratch_get(scmc_handle* h, int slot, size_t bytes, void** p) {
     if (bytes == 0) bytes = 16;
     if (h->scratch_bytes[slot] < bytes) {
@@ -1139,7 +1140,7 @@ bool resident_preferred(const scmc_handle* h) {
     if (h->res.cs < 1) return false;
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device);
-    return h->res.cs <= 2 || h->R * h->res.cs <= n_sm;
+    return h->res.cs <= 2 || h->R * h->res.cs <= 2 * (int64_t)n_sm;
 }
 
 int32_t ensure_T(scmc_handle* h) {
