@@ -142,8 +142,10 @@ typedef struct {
 } scmc_run_results;
 /* run! (MonteCarlo.jl:3-108) for all replicas at once: 3/4 geometric ramp T_i -> T, sigma adaptation every measurement_rate
  * sweeps during thermalisation (min(sigma * 0.5 / (1 - R), 60)), then measurement sweeps with measure! every measurement_rate.
- * When every replica fits one CTA of the resident kernel the whole schedule runs on the device (<= 512 sweeps per launch);
- * otherwise controller kernels run between sweep launches.  Both give the same chains. */
+ * Where the replica-resident kernel is the preferred one (a replica in one CTA or one cluster of CTAs, few enough clusters: see
+ * scmc_set_sweep_mode and DESIGN.md section 4) the whole schedule runs inside that persistent kernel (<= 512 sweeps per launch,
+ * acceptance counts and measurement sums of a cluster reduced through distributed shared memory); otherwise controller kernels run
+ * between sweep launches.  Both give the same chains, adapted sigma and acceptance rates; rows agree to rounding. */
 int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_results* out);
 
 typedef struct {
@@ -160,7 +162,8 @@ typedef struct {
     int64_t* sweeps;            /* [R] annealing sweeps performed per replica */
 } scmc_anneal_results;
 /* cooling loop of runAnnealing! (MonteCarlo.jl:131-204), every replica with its own beta / sigma / stopping flag (device-side
- * inside the resident kernel when a replica fits one CTA, else one controller kernel per sweep; identical chains) */
+ * inside the resident kernel where that kernel is the preferred one, one CTA or one cluster per replica, else one controller kernel
+ * per sweep; identical chains) */
 int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results* out);
 /* optimisation sweeps (localOptimization!, MonteCarlo.jl:214-225, 289-329): colour-ordered; every site is moved to the
  * minimiser of its local energy <psi|H_loc|psi> (the fixed point of the reference's per-site gradient descent). E [R] or NULL. */
