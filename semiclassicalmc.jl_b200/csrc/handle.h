@@ -109,9 +109,9 @@ int32_t launch_measure(scmc_handle* h, double* d_rows /* device [R][SCMC_NOBS] o
 int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes);
 int32_t ensure_T(scmc_handle* h);      // recompute the cached T (Tsq) planes from psi if a psi-gather sweep left them stale
 bool uses_psi_gather(const scmc_handle* h);
-// device scratch slot of at least `bytes` bytes (kept in the handle, grown on demand); scratch_trim frees slots above 64 MB after a call
+// device scratch slot of at least `bytes` bytes (kept in the handle, grown on demand); a DevBuf above 64 MB releases its own slot when it goes out of scope
 cudaError_t scratch_get(scmc_handle* h, int slot, size_t bytes, void** p);
-void scratch_trim(scmc_handle* h);
+void scratch_release(scmc_handle* h, int slot);      // frees ONE slot (the caller is done with it and it is oversized)
 bool resident_preferred(const scmc_handle* h);      // the auto policy's cluster predicate: clusters of <= 2 CTAs, or all clusters on the chip at once
 int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint64_t seed, double att_per_sweep, double min_accepted,
                                double beta_fac, double min_accrate, double sigma_min, int64_t n_per_T, int64_t n_total,

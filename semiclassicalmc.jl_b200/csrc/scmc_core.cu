@@ -1127,13 +1127,11 @@ cudaError_t scratch_get(scmc_handle* h, int slot, size_t bytes, void** p) {
     return cudaSuccess;
 }
 
-void scratch_trim(scmc_handle* h) {
-    for (int i = 0; i < scmc_handle::N_SCRATCH; i++)
-        if (h->scratch[i] && h->scratch_bytes[i] > ((size_t)64 << 20)) {
-            cudaStreamSynchronize(h->stream);
-            cudaFree(h->scratch[i]);
-            h->scratch[i] = nullptr; h->scratch_bytes[i] = 0;
-        }
+void scratch_release(scmc_handle* h, int slot) {
+    if (!h->scratch[slot]) return;
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->scratch[slot]);
+    h->scratch[slot] = nullptr; h->scratch_bytes[slot] = 0;
 }
 
 bool resident_preferred(const scmc_handle* h) {

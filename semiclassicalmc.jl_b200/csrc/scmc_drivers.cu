@@ -310,12 +310,14 @@ static int32_t dispatch_d(const scmc_handle* h, F&& f) {
 }
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
-// Device scratch of one API call: a slot of the handle's grow-only pool (no cudaMalloc / cudaFree per call); the last DevBuf of a call
-// trims oversized slots when it goes out of scope.
+// Device scratch of one API call: a slot of the handle's grow-only pool (no cudaMalloc / cudaFree per call).  A buffer above 64 MB gives
+// ITS OWN slot back when it goes out of scope (never another buffer's: an inner-scope buffer may die while outer ones are still in use).
 struct DevBuf {
     scmc_handle* h; int slot; void* p = nullptr;
     DevBuf(scmc_handle* h_, int slot_) : h(h_), slot(slot_) {}
-    ~DevBuf() { if (p && h->scratch_bytes[slot] > ((size_t)64 << 20)) scratch_trim(h); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p && h->scratch_bytes[slot] > ((size_t)64 << 20)) scratch_release(h, slot); }
     cudaError_t alloc(size_t bytes) { return scratch_get(h, slot, bytes, &p); }
     template <class T> T* as() { return (T*)p; }
 };

@@ -592,3 +592,31 @@ def test_t_family_device_side_annealing_equals_host_driven_loop(scmc, monkeypatc
     assert np.array_equal(a.get_state(), b.get_state())
     etol = 1e-12 if precision == 64 else 2e-6
     assert np.allclose(ra["E"], rb["E"], rtol=etol, atol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["psi_tri48", "T_honey24"])
+def test_chip_filling_cluster_rule_does_not_change_chains(scmc, monkeypatch, kind):
+    """Few replicas: scmc_create grows the cluster beyond what the lattice needs so that idle SMs get work (SCMC_CLUSTER_FILL=0 switches the
+    rule off).  The cluster size is a layout choice: run!, annealing and plain sweeps must give identical chains with the rule on and off."""
+    def mk(fill, R):
+        monkeypatch.setenv("SCMC_CLUSTER_FILL", fill)
+        if kind == "psi_tri48":
+            return scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 48, 1, n_replicas=R, precision=32, seed=31)
+        return scmc.initializeCfg("nearest-neighbor", "honeycomb", [np.eye(16)], 24, 2, n_replicas=R, precision=32, seed=31)
+    R = 12
+    a, b = mk("0", R), mk("1", R)
+    assert a.info()["cluster"] == 1 and b.info()["cluster"] >= 2          # the rule triggers for this shape
+    Ts = np.geomspace(0.05, 1.5, R)
+    ra = scmc.run_(a, None, Ts, 2.0, 60, 60, measurement_rate=10)
+    rb = scmc.run_(b, None, Ts, 2.0, 60, 60, measurement_rate=10)
+    assert np.array_equal(ra["sigma"], rb["sigma"]) and np.array_equal(ra["acc_rate"], rb["acc_rate"])
+    assert np.array_equal(a.get_state(), b.get_state())
+    assert np.allclose(ra["mean"], rb["mean"], rtol=2e-5, atol=2e-5)
+    acc_a, _ = a.sweep(7, 1.0 / Ts, ra["sigma"]); acc_b, _ = b.sweep(7, 1.0 / Ts, rb["sigma"])
+    assert np.array_equal(acc_a, acc_b) and np.array_equal(a.get_state(), b.get_state())
+    a2, b2 = mk("0", R), mk("1", R)
+    kw = dict(T_fac=0.9, N_max=300, N_o=0, N_per_T=20, min_acc_per_site=3, min_accrate=0.02, σ_min=0.05)
+    qa, qb = scmc.runAnnealing_(a2, 2.0, **kw), scmc.runAnnealing_(b2, 2.0, **kw)
+    assert np.array_equal(qa["sweeps"], qb["sweeps"]) and np.array_equal(qa["beta"], qb["beta"]) and np.array_equal(qa["sigma"], qb["sigma"])
+    assert np.array_equal(a2.get_state(), b2.get_state())
