@@ -620,3 +620,23 @@ def test_chip_filling_cluster_rule_does_not_change_chains(scmc, monkeypatch, kin
     qa, qb = scmc.runAnnealing_(a2, 2.0, **kw), scmc.runAnnealing_(b2, 2.0, **kw)
     assert np.array_equal(qa["sweeps"], qb["sweeps"]) and np.array_equal(qa["beta"], qb["beta"]) and np.array_equal(qa["sigma"], qb["sigma"])
     assert np.array_equal(a2.get_state(), b2.get_state())
+
+
+@pytest.mark.gpu
+def test_oversized_scratch_buffers_of_run_are_independent(scmc):
+    """Thermalisation log and measurement rows both above the 64 MB threshold of the scratch pool (4096 replicas of a 3x3 lattice, a point
+    every sweep): the log buffer goes out of scope before the measurement phase and must release only its own slot.  Device-side schedule
+    against the host-driven one: same chains, rows and log equal to rounding."""
+    R = 4096
+    Ts = np.geomspace(0.1, 2.0, R)
+    mk = lambda: scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 3, 1, n_replicas=R, precision=32, seed=8)
+    a = mk(); a.set_sweep_mode(3)
+    ra = scmc.run_(a, None, Ts, 2.0, 2100, 100, measurement_rate=1)
+    b = mk()
+    rb = scmc.run_(b, None, Ts, 2.0, 2100, 100, measurement_rate=1)
+    assert ra["rows"] == rb["rows"] == 100 and ra["therm_energy"].shape == rb["therm_energy"].shape == (2100, R)
+    assert ra["therm_energy"].nbytes > (64 << 20) and ra["series"].nbytes > (64 << 20)
+    assert np.array_equal(a.get_state(), b.get_state()) and np.array_equal(ra["sigma"], rb["sigma"])
+    assert np.isfinite(rb["series"]).all() and np.isfinite(rb["therm_energy"]).all()
+    assert np.allclose(ra["series"], rb["series"], rtol=2e-5, atol=2e-5)
+    assert np.allclose(ra["therm_energy"], rb["therm_energy"], rtol=2e-5, atol=2e-5)
