@@ -108,6 +108,16 @@ int32_t scmc_measure(scmc_t* h, double* obs);
 /* S^a(k) = |sum_i T_i^a exp(i k.r_i)|^2 / n_rs for every replica: equals computeStructureFactorVec(getCorrelations(...))
  * (Observables.jl:22-41, 116-128) on the allowed momenta of the periodic cluster.  ks [nk][dim], pos [N][dim], out [R][16][nk]. */
 int32_t scmc_structure_factor(scmc_t* h, const double* ks, const double* pos, int32_t nk, int32_t dim, double n_rs, double* Sak);
+/* The same S^a(k) for allowed momenta of a two-dimensional periodic L1 x L2 cluster with n_basis sites per cell, as a separable DFT over the
+ * cell indices (O(N (L1 + L2)) for ALL momenta of a cell instead of O(N) per momentum): site i sits in cell (cell[i][0], cell[i][1]) with basis
+ * index basis[i]; momentum k = (m1' b1 + m2' b2) / L is requested as m = (m1' mod L1, m2' mod L2) together with its basis phases
+ * phase[k][b] = (cos, sin)(k . delta_b).  comp_mask = 0: output [R][16][nk] as scmc_structure_factor (computeStructureFactorVec,
+ * Observables.jl:116-128); comp_mask != 0: output [R][nk], summed over the components a whose bit a is set (computeStructureFactor with
+ * `components`, Observables.jl:101-113; the reference's default 1:15 is mask 0x7FFF) -- 16 times less data to copy back.  No direct
+ * reference counterpart for the algorithm: the reference evaluates these formulas on averaged O(N^2) correlations. */
+int32_t scmc_structure_factor_grid(scmc_t* h, int32_t L1, int32_t L2, int32_t n_basis, const int32_t* cell /* [N][2] */, const int32_t* basis /* [N] */,
+                                   int32_t nk, const int32_t* m /* [nk][2] */, const double* phase /* [nk][n_basis][2] */, double n_rs, uint32_t comp_mask,
+                                   double* Sak);
 /* getCorrelations (Observables.jl:22-41) of one replica for a caller-supplied project map [N][N] (0-based), C [16][n_rs] */
 int32_t scmc_correlations(scmc_t* h, int64_t replica, const int32_t* project, int64_t n_rs, double* C);
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "scmc_set_lanes": (C.c_int32, [C.c_void_p, C.c_int32]),
     "scmc_measure": (C.c_int32, [C.c_void_p, c_dp]),
     "scmc_structure_factor": (C.c_int32, [C.c_void_p, c_dp, c_dp, C.c_int32, C.c_int32, C.c_double, c_dp]),
+    "scmc_structure_factor_grid": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_ip, c_ip, C.c_int32, c_ip, c_dp, C.c_double, C.c_uint32, c_dp]),
     "scmc_correlations": (C.c_int32, [C.c_void_p, C.c_int64, c_ip, C.c_int64, c_dp]),
     "scmc_sublattice_magnetization": (C.c_int32, [C.c_void_p, c_ip, C.c_int32, c_dp]),
     "scmc_chirality": (C.c_int32, [C.c_void_p, c_ip, c_dp]),

@@ -185,6 +185,98 @@ __global__ void __launch_bounds__(128) k_structure_factor(const vec4<R>* __restr
         for (int a = 0; a < NG; a++) out[((size_t)r * NG + a) * nk + k] = (sr[a] * sr[a] + si[a] * si[a]) * inv_nrs;
 }
 
+// ---- structure factor on the allowed momenta of a periodic L1 x L2 cluster as a separable DFT over the cell indices -----------------
+// k = (m1 b1 + m2 b2) / L, r = n1 a1 + n2 a2 + delta_b  =>  k.r = 2 pi (m1 n1 / L1 + m2 n2 / L2) + k.delta_b, so for every basis site b
+// F_b^a(m1, m2) = sum_{n1, n2} T^a(n1, n2, b) w1^{m1 n1} w2^{m2 n2} gives all L1 L2 momenta of a cell in O(N (L1 + L2)) operations and
+// S^a(k) = |sum_b e^{i k.delta_b} F_b^a(m1 mod L1, m2 mod L2)|^2 / n_rs for any allowed k (momenta outside the first cell differ only in the
+// basis phases).  FP64 twiddles (host-computed tables) and accumulation, like k_structure_factor.
+// pass 1, rows: X[r][b][a][n2][m1] = sum_{n1} T^a(n1, n2, b) w1^{m1 n1};  grid (L2 * nb, replicas)
+template <class R>
+__global__ void __launch_bounds__(128) k_sf_dft_rows(const vec4<R>* __restrict__ Tpl, int Ns, int64_t nrep, int64_t r0, const int32_t* __restrict__ grid_site /* [nb][L1][L2] */,
+                                                     const double2* __restrict__ tw1, int L1, int L2, int nb, double2* __restrict__ X) {
+    extern __shared__ __align__(16) unsigned char sf_smem[];
+    double* sT = reinterpret_cast<double*>(sf_smem);                  // [L1][16]
+    double2* sw = reinterpret_cast<double2*>(sT + (size_t)L1 * NG);   // [L1]
+    const int n2 = blockIdx.x % L2, b = blockIdx.x / L2;
+    const int64_t r = r0 + blockIdx.y;
+    const size_t ps = (size_t)nrep * Ns;
+    const vec4<R>* base = Tpl + r * Ns;
+    for (int t = threadIdx.x; t < L1 * 4; t += blockDim.x) {
+        const int n1 = t >> 2, q = t & 3;
+        const vec4<R> v = base[(size_t)q * ps + grid_site[((size_t)b * L1 + n1) * L2 + n2]];
+        double* d = sT + (size_t)n1 * NG + 4 * q;
+        d[0] = (double)v.x; d[1] = (double)v.y; d[2] = (double)v.z; d[3] = (double)v.w;
+    }
+    for (int t = threadIdx.x; t < L1; t += blockDim.x) sw[t] = tw1[t];
+    __syncthreads();
+    for (int m1 = threadIdx.x; m1 < L1; m1 += blockDim.x) {
+        double sr[NG], si[NG];
+#pragma unroll
+        for (int a = 0; a < NG; a++) { sr[a] = 0.0; si[a] = 0.0; }
+        int idx = 0;
+        for (int n1 = 0; n1 < L1; n1++) {
+            const double2 w = sw[idx];
+            const double* t = sT + (size_t)n1 * NG;
+#pragma unroll
+            for (int a = 0; a < NG; a++) { sr[a] = fma(t[a], w.x, sr[a]); si[a] = fma(t[a], w.y, si[a]); }
+            idx += m1; if (idx >= L1) idx -= L1;
+        }
+#pragma unroll
+        for (int a = 0; a < NG; a++)
+            X[((((size_t)blockIdx.y * nb + b) * NG + a) * L2 + n2) * L1 + m1] = make_double2(sr[a], si[a]);
+    }
+}
+// pass 2, columns: F[r][b][a][m1][m2] = sum_{n2} X[r][b][a][n2][m1] w2^{m2 n2};  grid (ceil(L1 / 8), 16 * nb, replicas), tiles of 8 m1
+__global__ void __launch_bounds__(256) k_sf_dft_cols(const double2* __restrict__ X, const double2* __restrict__ tw2, int L1, int L2, int nb, double2* __restrict__ F) {
+    extern __shared__ __align__(16) unsigned char sf_smem[];
+    double2* sX = reinterpret_cast<double2*>(sf_smem);                // [L2][8]
+    double2* sw = sX + (size_t)L2 * 8;                                // [L2]
+    const int m1_0 = blockIdx.x * 8;
+    const size_t plane = ((size_t)blockIdx.z * nb * NG + blockIdx.y) * (size_t)L1 * L2;      // blockIdx.y = b * 16 + a
+    for (int t = threadIdx.x; t < L2 * 8; t += blockDim.x) {
+        const int n2 = t >> 3, j = t & 7;
+        sX[t] = (m1_0 + j < L1) ? X[plane + (size_t)n2 * L1 + m1_0 + j] : make_double2(0.0, 0.0);
+    }
+    for (int t = threadIdx.x; t < L2; t += blockDim.x) sw[t] = tw2[t];
+    __syncthreads();
+    for (int t = threadIdx.x; t < L2 * 8; t += blockDim.x) {
+        const int m2 = t >> 3, j = t & 7;
+        if (m1_0 + j >= L1) continue;
+        double yr = 0.0, yi = 0.0;
+        int idx = 0;
+        for (int n2 = 0; n2 < L2; n2++) {
+            const double2 w = sw[idx], x = sX[n2 * 8 + j];
+            yr = fma(x.x, w.x, yr); yr = fma(-x.y, w.y, yr);
+            yi = fma(x.x, w.y, yi); yi = fma(x.y, w.x, yi);
+            idx += m2; if (idx >= L2) idx -= L2;
+        }
+        F[plane + (size_t)(m1_0 + j) * L2 + m2] = make_double2(yr, yi);
+    }
+}
+// S^a(k) for the requested momenta: out[r][a][k] = |sum_b phase[k][b] F[r][b][a][m1_k][m2_k]|^2 / n_rs;  grid (ceil(nk / 128), replicas)
+// comp_mask != 0: out[r][k] = sum over the components a with bit a set (computeStructureFactor, Observables.jl:101-113)
+__global__ void __launch_bounds__(128) k_sf_combine(const double2* __restrict__ F, const int32_t* __restrict__ m, const double2* __restrict__ phase, int nk, int L1, int L2, int nb,
+                                                    double inv_nrs, int64_t r0, uint32_t comp_mask, double* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nk) return;
+    const int m1 = m[2 * k], m2 = m[2 * k + 1];
+    const size_t at = (size_t)m1 * L2 + m2, plane = (size_t)L1 * L2;
+    double total = 0.0;
+    for (int a = 0; a < NG; a++) {
+        if (comp_mask && !((comp_mask >> a) & 1u)) continue;
+        double sr = 0.0, si = 0.0;
+        for (int b = 0; b < nb; b++) {
+            const double2 f = F[(((size_t)blockIdx.y * nb + b) * NG + a) * plane + at], ph = phase[(size_t)k * nb + b];
+            sr += f.x * ph.x - f.y * ph.y;
+            si += f.x * ph.y + f.y * ph.x;
+        }
+        const double v = (sr * sr + si * si) * inv_nrs;
+        if (comp_mask) total += v;
+        else out[((size_t)(r0 + blockIdx.y) * NG + a) * nk + k] = v;
+    }
+    if (comp_mask) out[(size_t)(r0 + blockIdx.y) * nk + k] = total;
+}
+
 // C[a][project[i][j]] += T_i^a T_j^a  (Observables.jl:22-41); project given in the caller's site order
 template <class R>
 __global__ void __launch_bounds__(256) k_correlations(const vec4<R>* __restrict__ Tpl, int N, int Ns, int64_t nrep, int64_t r, const int32_t* __restrict__ perm,
@@ -592,6 +684,64 @@ int32_t scmc_structure_factor(scmc_t* h, const double* ks, const double* pos, in
         k_structure_factor<float><<<grid, 128, 0, h->stream>>>((const float4*)h->T, (int)h->N, (int)h->Ns, h->R, dk.as<double>(), dp.as<double>(), nk, dim, 1.0 / n_rs, dout.as<double>());
     h->launches++;
     SCMC_CK(cudaGetLastError());
+    SCMC_CK(cudaMemcpyAsync(Sak, dout.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    return SCMC_OK;
+}
+
+int32_t scmc_structure_factor_grid(scmc_t* h, int32_t L1, int32_t L2, int32_t n_basis, const int32_t* cell, const int32_t* basis, int32_t nk, const int32_t* m,
+                                   const double* phase, double n_rs, uint32_t comp_mask, double* Sak) {
+    SCMC_ARG(h && cell && basis && m && phase && Sak, "null argument");
+    SCMC_ARG(L1 >= 1 && L2 >= 1 && n_basis >= 1 && nk >= 1 && n_rs > 0, "scmc_structure_factor_grid: bad sizes");
+    SCMC_ARG((int64_t)L1 * L2 * n_basis == h->N, "scmc_structure_factor_grid: L1 * L2 * n_basis must equal the number of sites");
+    SCMC_ARG(comp_mask <= 0xFFFFu, "scmc_structure_factor_grid: component mask has bits above 15");
+    SCMC_ARG(L1 <= 4096 && L2 <= 4096, "scmc_structure_factor_grid: linear size above 4096 not supported");
+    std::vector<int32_t> gs((size_t)h->N, -1);
+    for (int64_t i = 0; i < h->N; i++) {
+        const int32_t n1 = cell[2 * i], n2 = cell[2 * i + 1], b = basis[i];
+        SCMC_ARG(n1 >= 0 && n1 < L1 && n2 >= 0 && n2 < L2 && b >= 0 && b < n_basis, "scmc_structure_factor_grid: cell / basis index out of range");
+        int32_t& slot = gs[((size_t)b * L1 + n1) * L2 + n2];
+        SCMC_ARG(slot < 0, "scmc_structure_factor_grid: two sites share a (cell, basis) index");
+        slot = h->perm[i];
+    }
+    for (int32_t k = 0; k < nk; k++) SCMC_ARG(m[2 * k] >= 0 && m[2 * k] < L1 && m[2 * k + 1] >= 0 && m[2 * k + 1] < L2, "scmc_structure_factor_grid: momentum index out of range");
+    SCMC_CK(cudaSetDevice(h->device));
+    SCMC_TRY(ensure_T(h));
+    std::vector<double> tw((size_t)2 * (L1 + L2));
+    for (int j = 0; j < L1; j++) { tw[2 * j] = std::cos(2.0 * M_PI * j / L1); tw[2 * j + 1] = std::sin(2.0 * M_PI * j / L1); }
+    for (int j = 0; j < L2; j++) { tw[2 * (L1 + j)] = std::cos(2.0 * M_PI * j / L2); tw[2 * (L1 + j) + 1] = std::sin(2.0 * M_PI * j / L2); }
+    // replicas are processed in batches so that the two FP64 complex work arrays stay below ~1 GiB each
+    const size_t per_rep = (size_t)n_basis * 16 * L1 * L2 * sizeof(double2);
+    const int64_t rb = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(h->R, 65535), (int64_t)(((size_t)1 << 30) / per_rep)));
+    DevBuf dgs(h, 0), dtw(h, 1), dX(h, 2), dF(h, 3), dm(h, 4), dph(h, 5), dout(h, 6);
+    SCMC_CK(dgs.alloc(gs.size() * 4)); SCMC_CK(dtw.alloc(tw.size() * 8)); SCMC_CK(dX.alloc(per_rep * rb)); SCMC_CK(dF.alloc(per_rep * rb));
+    SCMC_CK(dm.alloc((size_t)nk * 2 * 4)); SCMC_CK(dph.alloc((size_t)nk * n_basis * 16));
+    const size_t out_bytes = (size_t)h->R * (comp_mask ? 1 : 16) * nk * 8;
+    SCMC_CK(dout.alloc(out_bytes));
+    SCMC_CK(cudaMemcpyAsync(dgs.p, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    SCMC_CK(cudaMemcpyAsync(dtw.p, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    SCMC_CK(cudaMemcpyAsync(dm.p, m, (size_t)nk * 2 * 4, cudaMemcpyHostToDevice, h->stream));
+    SCMC_CK(cudaMemcpyAsync(dph.p, phase, (size_t)nk * n_basis * 16, cudaMemcpyHostToDevice, h->stream));
+    const double2* tw1 = dtw.as<double2>(); const double2* tw2 = tw1 + L1;
+    const size_t smem1 = (size_t)L1 * 16 * 8 + (size_t)L1 * 16, smem2 = (size_t)L2 * 8 * 16 + (size_t)L2 * 16;
+    SCMC_ARG(smem1 <= 200 * 1024 && smem2 <= 200 * 1024, "scmc_structure_factor_grid: linear size too large for the shared-memory tiles");
+    if (smem1 > 48 * 1024) {
+        SCMC_CK(cudaFuncSetAttribute(k_sf_dft_rows<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        SCMC_CK(cudaFuncSetAttribute(k_sf_dft_rows<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    }
+    if (smem2 > 48 * 1024) SCMC_CK(cudaFuncSetAttribute(k_sf_dft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    for (int64_t r0 = 0; r0 < h->R; r0 += rb) {
+        const int64_t rc = std::min<int64_t>(rb, h->R - r0);
+        const dim3 g1((unsigned)(L2 * n_basis), (unsigned)rc);
+        if (h->prec == 64) k_sf_dft_rows<double><<<g1, 128, smem1, h->stream>>>((const double4*)h->T, (int)h->Ns, h->R, r0, dgs.as<int32_t>(), tw1, L1, L2, n_basis, dX.as<double2>());
+        else k_sf_dft_rows<float><<<g1, 128, smem1, h->stream>>>((const float4*)h->T, (int)h->Ns, h->R, r0, dgs.as<int32_t>(), tw1, L1, L2, n_basis, dX.as<double2>());
+        const dim3 g2((unsigned)((L1 + 7) / 8), (unsigned)(16 * n_basis), (unsigned)rc);
+        k_sf_dft_cols<<<g2, 256, smem2, h->stream>>>(dX.as<double2>(), tw2, L1, L2, n_basis, dF.as<double2>());
+        const dim3 g3(grid_for(nk, 128), (unsigned)rc);
+        k_sf_combine<<<g3, 128, 0, h->stream>>>(dF.as<double2>(), dm.as<int32_t>(), dph.as<double2>(), nk, L1, L2, n_basis, 1.0 / n_rs, r0, comp_mask, dout.as<double>());
+        h->launches += 3;
+        SCMC_CK(cudaGetLastError());
+    }
     SCMC_CK(cudaMemcpyAsync(Sak, dout.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
     SCMC_CK(cudaStreamSynchronize(h->stream));
     return SCMC_OK;

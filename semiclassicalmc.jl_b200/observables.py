@@ -71,10 +71,61 @@ def computeStructureFactor(correlation, rs, ks, components=None):
     return computeStructureFactorVec(correlation, rs, ks)[comps].sum(axis=0)
 
 
-def structureFactor(cfg, ks):
-    """Device path: S^a(k) = |sum_i T_i^a e^{ik.r_i}|^2 / |rs| for every replica, [R, 16, nk]; equals
-    computeStructureFactorVec(getCorrelations(cfg, getProject(cfg)), getRs(cfg), ks) on allowed momenta."""
+def _allowed_momentum_indices(cfg, ks):
+    """Integer coordinates m' of ks in the reciprocal basis of the L-supercell (k = sum_i m'_i b_i / L) when every k is an allowed momentum
+    of the periodic cluster (two-dimensional lattices), else None."""
+    lat = cfg.lattice
+    if lat.cells.shape[1] != 2 or ks.shape[1] != 2:
+        return None
+    A = np.stack(lat.unitcell.lattice_vectors) * lat.L            # supercell vectors L a_i
+    mf = ks @ A.T / (2 * np.pi)
+    mi = np.rint(mf)
+    if not np.allclose(mf, mi, atol=1e-6):
+        return None
+    return mi.astype(np.int64)
+
+
+def structureFactorSum(cfg, ks, components=None):
+    """S(k) summed over `components` (0-based; default 0..14 = the reference's 1:15) for every replica, [R, nk]: the device
+    counterpart of computeStructureFactor (Observables.jl:101-113).  Allowed momenta of a 2-D periodic cluster are summed on the device
+    (16 times less data to copy back than structureFactor); other momenta go through structureFactor."""
+    comps = list(range(15)) if components is None else [int(c) for c in components]
     ks = _lib.f64(ks)
+    mi = _allowed_momentum_indices(cfg, ks)
+    if mi is None or len(set(comps)) != len(comps):
+        return structureFactor(cfg, ks)[:, comps, :].sum(axis=1)
+    mask = 0
+    for c in comps:
+        mask |= 1 << c
+    return _structure_factor_grid(cfg, ks, mi, mask)
+
+
+def _structure_factor_grid(cfg, ks, mi, mask):
+    lat = cfg.lattice
+    L, nb = lat.L, len(cfg.basis)
+    m = np.ascontiguousarray(np.mod(mi, L), dtype=np.int32)
+    delta = np.stack(cfg.basis).astype(float)                 # basis offsets delta_b
+    ang = ks @ delta.T                                        # [nk, nb]
+    phase = np.ascontiguousarray(np.stack([np.cos(ang), np.sin(ang)], axis=-1))
+    cell = np.ascontiguousarray(lat.cells, dtype=np.int32)
+    basis = np.ascontiguousarray(lat.basis_labels - 1, dtype=np.int32)
+    out = np.empty((cfg.n_replicas, ks.shape[0]) if mask else (cfg.n_replicas, 16, ks.shape[0]))
+    _lib.check(cfg._lib.scmc_structure_factor_grid(cfg._h, L, L, nb, _lib.iptr(cell), _lib.iptr(basis), ks.shape[0], _lib.iptr(m), _lib.dptr(phase),
+                                                   float(nb * cfg.nSites), mask, _lib.dptr(out)))
+    return out
+
+
+def structureFactor(cfg, ks, method="auto"):
+    """Device path: S^a(k) = |sum_i T_i^a e^{ik.r_i}|^2 / |rs| for every replica, [R, 16, nk]; equals
+    computeStructureFactorVec(getCorrelations(cfg, getProject(cfg)), getRs(cfg), ks) on allowed momenta.
+    method "auto": allowed momenta of a 2-D periodic cluster go through the separable DFT over the cell indices (scmc_structure_factor_grid:
+    all momenta of a cell at once), anything else through the direct O(N) sum per momentum; "direct" / "grid" force one of them."""
+    ks = _lib.f64(ks)
+    mi = _allowed_momentum_indices(cfg, ks) if method in ("auto", "grid") else None
+    if method == "grid" and mi is None:
+        raise ValueError("structureFactor(method='grid'): the momenta are not all allowed momenta of a 2-D periodic cluster")
+    if mi is not None:
+        return _structure_factor_grid(cfg, ks, mi, 0)
     pos = _lib.f64(cfg.positions)
     out = np.zeros((cfg.n_replicas, 16, ks.shape[0]))
     _lib.check(cfg._lib.scmc_structure_factor(cfg._h, _lib.dptr(ks), _lib.dptr(pos), ks.shape[0], ks.shape[1],

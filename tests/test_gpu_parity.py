@@ -640,3 +640,32 @@ def test_oversized_scratch_buffers_of_run_are_independent(scmc):
     assert np.isfinite(rb["series"]).all() and np.isfinite(rb["therm_energy"]).all()
     assert np.allclose(ra["series"], rb["series"], rtol=2e-5, atol=2e-5)
     assert np.allclose(ra["therm_energy"], rb["therm_energy"], rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lattice, L, n, precision", [("triangular", 12, 1, 32), ("honeycomb", 8, 2, 32), ("honeycomb", 6, 1, 64), ("square", 7, 1, 64)])
+def test_structure_factor_grid_equals_direct_sum(scmc, lattice, L, n, precision):
+    """S^a(k) on the allowed momenta of the periodic cluster through the separable DFT over the cell indices (scmc_structure_factor_grid)
+    against the direct sum over sites per momentum (scmc_structure_factor): same FP64 accumulation of the same T values.  The box reaches
+    beyond the first reciprocal cell, where the basis phases of a two-site cell matter; non-allowed momenta fall back to the direct sum."""
+    R = 3
+    J = [np.eye(16)] if n == 2 else [random_symmetric_J(4)]
+    cfg = scmc.initializeCfg("nearest-neighbor", lattice, J, L, n, n_replicas=R, precision=precision, seed=17)
+    cfg.sweep(3, np.array([0.5, 2.0, 8.0]), np.full(R, 0.4))
+    ks = scmc.getKsInBox(lattice, L, [5 * np.pi, 5 * np.pi], [0.3, -0.2])
+    assert len(ks) > L * L                                   # more momenta than one reciprocal cell holds
+    direct = scmc.structureFactor(cfg, ks, method="direct")
+    grid = scmc.structureFactor(cfg, ks, method="grid")
+    auto = scmc.structureFactor(cfg, ks)
+    scale = np.abs(direct).max()
+    assert scale > 1e-3 and np.allclose(grid, direct, rtol=1e-9, atol=1e-10 * scale)
+    assert np.array_equal(auto, grid)
+    # component sums on the device (computeStructureFactor with `components`; default 0..14 = the reference's 1:15)
+    ssum = scmc.structureFactorSum(cfg, ks)
+    assert ssum.shape == (R, len(ks)) and np.allclose(ssum, direct[:, :15, :].sum(axis=1), rtol=1e-9, atol=1e-10 * scale)
+    assert np.allclose(scmc.structureFactorSum(cfg, ks, components=[4, 8, 12]), direct[:, [4, 8, 12], :].sum(axis=1), rtol=1e-9, atol=1e-10 * scale)
+    off = ks[:5] + 1e-3                                       # not allowed momenta
+    assert np.array_equal(scmc.structureFactor(cfg, off), scmc.structureFactor(cfg, off, method="direct"))
+    assert np.allclose(scmc.structureFactorSum(cfg, off), scmc.structureFactor(cfg, off, method="direct")[:, :15, :].sum(axis=1), rtol=1e-12)
+    with pytest.raises(ValueError):
+        scmc.structureFactor(cfg, off, method="grid")
