@@ -20,12 +20,12 @@ class LogBinner:
         for x in xs:
             self.push(x)
 
-    @property
-    def count(self):
-        return len(self.data)
-
     def _arr(self):
         return np.stack(self.data) if self.data else np.zeros((0,) + self.shape)
+
+    @property
+    def count(self):
+        return self._arr().shape[0]
 
     def mean(self):
         return self._arr().mean(axis=0)
@@ -91,3 +91,89 @@ class ErrorPropagator:
         g = np.asarray(grad(self.means()), dtype=np.float64)
         cov = np.atleast_2d(np.cov(X, rowvar=False, ddof=1))
         return float(np.sqrt(abs(g @ cov @ g) / X.shape[0]))
+
+
+class _ViewBinner(LogBinner):
+    """LogBinner of ONE replica over the block storage of a ReplicaSeries (plus anything pushed to it directly)."""
+
+    def __init__(self, parent, pick):
+        super().__init__(np.zeros(parent.shape))
+        self._parent, self._pick = parent, pick
+
+    def _arr(self):
+        base = self._parent._all()
+        mine = self._pick(base) if base is not None else np.zeros((0,) + self.shape)
+        if self.data:
+            return np.concatenate([mine, np.stack(self.data)], axis=0)
+        return mine
+
+
+class ReplicaSeries:
+    """Time series of one (vector-valued) observable for R replicas.  Measurements arrive as blocks [n, R, *shape] and are appended in one
+    call (no Python loop over replicas per measurement); `series[r]` is that replica's LogBinner (same estimators as a per-replica one)."""
+
+    def __init__(self, R, zero=0.0):
+        self.R, self.shape, self.blocks, self._cat, self._views = int(R), np.shape(zero), [], None, {}
+
+    def push_block(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        assert x.shape[1] == self.R and x.shape[2:] == self.shape, (x.shape, self.R, self.shape)
+        self.blocks.append(x.copy())
+        self._cat = None
+
+    def _all(self):
+        if not self.blocks:
+            return None
+        if self._cat is None:
+            self._cat = self.blocks[0] if len(self.blocks) == 1 else np.concatenate(self.blocks, axis=0)
+            self.blocks = [self._cat]
+        return self._cat
+
+    def __len__(self):
+        return self.R
+
+    def __getitem__(self, r):
+        r = range(self.R)[r]
+        if r not in self._views:
+            self._views[r] = _ViewBinner(self, lambda a, r=r: a[:, r])
+        return self._views[r]
+
+
+class _ViewPropagator(ErrorPropagator):
+    def __init__(self, parent, r):
+        self.bins = [_ViewBinner(parent._component(i), lambda a, r=r: a[:, r]) for i in range(parent.n_args)]
+
+
+class _Component:
+    """Scalar component i of a ReplicaPropagator's blocks, with the interface _ViewBinner needs."""
+
+    def __init__(self, parent, i):
+        self.parent, self.i, self.shape = parent, i, ()
+
+    def _all(self):
+        a = self.parent.series._all()
+        return None if a is None else a[..., self.i]
+
+
+class ReplicaPropagator:
+    """ErrorPropagator for R replicas: blocks [n, R, n_args]; `prop[r]` is that replica's ErrorPropagator."""
+
+    def __init__(self, R, n_args=2):
+        self.R, self.n_args = int(R), int(n_args)
+        self.series = ReplicaSeries(R, np.zeros(n_args))
+        self._views = {}
+
+    def push_block(self, x):
+        self.series.push_block(x)
+
+    def _component(self, i):
+        return _Component(self, i)
+
+    def __len__(self):
+        return self.R
+
+    def __getitem__(self, r):
+        r = range(self.R)[r]
+        if r not in self._views:
+            self._views[r] = _ViewPropagator(self, r)
+        return self._views[r]

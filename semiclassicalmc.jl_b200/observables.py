@@ -3,7 +3,7 @@ Reductions over the lattice (energy, magnetisation, correlations, structure fact
 import numpy as np
 
 from . import _lib
-from .binning import LogBinner, ErrorPropagator
+from .binning import LogBinner, ErrorPropagator, ReplicaSeries, ReplicaPropagator
 from .lattice import getKsInBox  # noqa: F401  (re-export, Observables.jl:91-98)
 
 
@@ -138,11 +138,12 @@ class ObservablesGeneric(Observables):
 
     def __init__(self, cfg, correlations=False):
         R = cfg.n_replicas
-        self.energy = [ErrorPropagator(2) for _ in range(R)]
-        self.sigma = [LogBinner() for _ in range(R)]
-        self.tau = [LogBinner() for _ in range(R)]
-        self.sigmatau = [LogBinner() for _ in range(R)]
-        self.magnetizationVec = [LogBinner(np.zeros(16)) for _ in range(R)]
+        # block storage over replicas (binning.ReplicaSeries): a measurement of all replicas is appended in one call; x[r] is replica r's binner
+        self.energy = ReplicaPropagator(R, 2)
+        self.sigma = ReplicaSeries(R)
+        self.tau = ReplicaSeries(R)
+        self.sigmatau = ReplicaSeries(R)
+        self.magnetizationVec = ReplicaSeries(R, np.zeros(16))
         self.rs = getRs(cfg)
         self.with_correlations = correlations
         self.project = getProject(cfg) if correlations else None
@@ -150,10 +151,11 @@ class ObservablesGeneric(Observables):
 
     def push_rows(self, rows):
         """rows: [n, R, 21] measurement rows from the device."""
-        for row in rows:
-            for r, x in enumerate(row):
-                self.energy[r].push(x[0], x[1]); self.sigma[r].push(x[2]); self.tau[r].push(x[3]); self.sigmatau[r].push(x[4])
-                self.magnetizationVec[r].push(x[5:21])
+        rows = np.asarray(rows, dtype=np.float64)
+        if rows.shape[0] == 0:
+            return
+        self.energy.push_block(rows[:, :, 0:2]); self.sigma.push_block(rows[:, :, 2]); self.tau.push_block(rows[:, :, 3])
+        self.sigmatau.push_block(rows[:, :, 4]); self.magnetizationVec.push_block(rows[:, :, 5:21])
 
 
 def initializeObservables(obstype, cfg, **kw):
@@ -238,9 +240,9 @@ class ObservablesTgHbn(Observables):
     def __init__(self, cfg):
         R = cfg.n_replicas
         self.siteLabels = getSiteLabelsTriangular120(cfg)
-        self.energy = [ErrorPropagator(2) for _ in range(R)]
-        self.series = {n: [LogBinner() for _ in range(R)] for n in self.NAMES}
-        self.binder = {n: [ErrorPropagator(2) for _ in range(R)] for n in self.NAMES}
+        self.energy = ReplicaPropagator(R, 2)
+        self.series = {n: ReplicaSeries(R) for n in self.NAMES}
+        self.binder = {n: ReplicaPropagator(R, 2) for n in self.NAMES}
         self.with_correlations = False
 
     def values(self, cfg):
@@ -259,12 +261,11 @@ def measureTgHbn_(obs, cfg):
     """measure!(::ObservablesTgHbn, cfg, E) (ObservablesTgHbn.jl:47-98); E re-summed on the device."""
     row = cfg.measure()
     vals = obs.values(cfg)
-    for r in range(cfg.n_replicas):
-        obs.energy[r].push(row[r, 0], row[r, 1])
-        for n in obs.NAMES:
-            x = float(vals[n][r])
-            obs.series[n][r].push(x)
-            obs.binder[n][r].push(x ** 2, x ** 4)
+    obs.energy.push_block(row[None, :, 0:2])
+    for n in obs.NAMES:
+        x = np.asarray(vals[n], dtype=np.float64)
+        obs.series[n].push_block(x[None])
+        obs.binder[n].push_block(np.stack([x ** 2, x ** 4], axis=-1)[None])
 
 
 def meansTgHbn(obs, cfg, beta, replica=0):

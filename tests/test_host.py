@@ -86,3 +86,29 @@ def test_ks_in_box(scmc):
     pos = pl.getLatticePeriodic(pl.getUnitcell("triangular"), 6).positions
     sup = 6 * np.stack(pl.getUnitcell("triangular").lattice_vectors)
     assert np.allclose(np.exp(1j * ks @ sup.T), 1.0)           # allowed momenta of the periodic cluster
+
+
+def test_replica_block_storage_equals_per_replica_binners(scmc):
+    """ObservablesGeneric / ObservablesTgHbn keep their series as blocks over replicas (one append per measurement of all replicas instead of a
+    Python push per replica and observable); every replica's view must give exactly the estimators of a binner fed sample by sample."""
+    from scmc_b200.binning import LogBinner, ErrorPropagator, ReplicaSeries, ReplicaPropagator
+    rng = np.random.default_rng(0)
+    R, n = 5, 200
+    x = rng.normal(size=(n, R)).cumsum(axis=0) * 0.1 + rng.normal(size=(n, R))
+    v = rng.normal(size=(n, R, 16))
+    e = rng.normal(size=(n, R, 2))
+    S, V, P = ReplicaSeries(R), ReplicaSeries(R, np.zeros(16)), ReplicaPropagator(R, 2)
+    for a, b in ((0, 70), (70, 71), (71, 200)):
+        S.push_block(x[a:b]); V.push_block(v[a:b]); P.push_block(e[a:b])
+    f = lambda m: m[1] - m[0] ** 2
+    df = lambda m: np.array([-2 * m[0], 1.0])
+    for r in range(R):
+        b1, b16, p = LogBinner(), LogBinner(np.zeros(16)), ErrorPropagator(2)
+        for t in range(n):
+            b1.push(x[t, r]); b16.push(v[t, r]); p.push(e[t, r, 0], e[t, r, 1])
+        assert S[r].count == b1.count == n and len(S) == R
+        assert S[r].mean() == b1.mean() and S[r].std_error() == b1.std_error() and S[r].reliable_level() == b1.reliable_level()
+        assert np.array_equal(V[r].mean(), b16.mean()) and np.array_equal(V[r].std_error(), b16.std_error())
+        assert P[r].means() == p.means() and P[r].std_errors() == p.std_errors() and P[r].mean(f) == p.mean(f) and P[r].std_error(df) == p.std_error(df)
+    S[2].push(3.0)
+    assert S[2].count == n + 1 and S[1].count == n
