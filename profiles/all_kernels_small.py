@@ -23,7 +23,10 @@ for model, lat, Js, L, n, prec in cases:
         scmc.runAnnealing_(cfg, 2.0, T_fac=0.8, N_max=40, N_o=2, N_per_T=5, min_acc_per_site=2, min_accrate=0.01)
         if mode == 0:
             B = 2 * np.pi * np.linalg.inv(np.stack(cfg.unitVectors) * cfg.L).T
-            scmc.structureFactor(cfg, np.array([B[0], B[1], B[0] + B[1]]))
+            ks = np.array([B[0], B[1], B[0] + B[1]])
+            scmc.structureFactor(cfg, ks)                       # allowed momenta: separable DFT over the cell indices (2-D lattices)
+            scmc.structureFactorSum(cfg, ks)                    # summed over components on the device
+            scmc.structureFactor(cfg, ks + 1e-3)                # arbitrary momenta: direct sum per momentum
             if cfg.nSites <= 80:
                 scmc.getCorrelations(cfg, scmc.getProject(cfg), 1)
             if model == "tg-hbn":
