@@ -112,3 +112,17 @@ def test_replica_block_storage_equals_per_replica_binners(scmc):
         assert P[r].means() == p.means() and P[r].std_errors() == p.std_errors() and P[r].mean(f) == p.mean(f) and P[r].std_error(df) == p.std_error(df)
     S[2].push(3.0)
     assert S[2].count == n + 1 and S[1].count == n
+
+
+def test_tghbn_norms_vectorised_equals_reference_formulas(scmc):
+    """The component-set norms of ObservablesTgHbn for all replicas in a few array operations vs the formulas of ObservablesTgHbn.jl:47-98
+    written out per set (norm over the set's components, mean over the sublattices)."""
+    import scmc_b200.observables as ob
+    rng = np.random.default_rng(3)
+    sub = rng.normal(size=(7, 3, 16))                          # [R, n_sub, 16]: the device reduction's layout
+    got = ob._tghbn_norms(sub)
+    subM = np.transpose(sub, (0, 2, 1))                        # [R, 16, n_sub] as in the reference's formulas
+    m = subM.mean(axis=2)
+    for key, comps in ob._TGHBN_SETS.items():
+        assert np.allclose(got["subM" + key], np.linalg.norm(subM[:, comps, :], axis=1).mean(axis=1), rtol=1e-13, atol=0)
+        assert np.allclose(got["m" + key], np.linalg.norm(m[:, comps], axis=1), rtol=1e-13, atol=0)
