@@ -132,7 +132,10 @@ def cpu_reference_rate(L, J, target_seconds, sweeps=None):
     orc.build(fast=True, force=not _ORACLE_BUILT)   # rebuilt once on this host: -march=native must match the box's CPU
     _ORACLE_BUILT = True
     pos, nbr, lab, bl = ol.triangular(L)
-    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))      # the cores this process may actually run on (cpu_count ignores affinity / cgroup masks)
+    except AttributeError:
+        cores = os.cpu_count() or 1
     chains = []
     for c in range(cores):
         o = orc.Oracle(nbr, lab, J, np.zeros(16), 1, fast=True)
