@@ -118,6 +118,14 @@ int32_t scmc_structure_factor(scmc_t* h, const double* ks, const double* pos, in
 int32_t scmc_structure_factor_grid(scmc_t* h, int32_t L1, int32_t L2, int32_t n_basis, const int32_t* cell /* [N][2] */, const int32_t* basis /* [N] */,
                                    int32_t nk, const int32_t* m /* [nk][2] */, const double* phase /* [nk][n_basis][2] */, double n_rs, uint32_t comp_mask,
                                    double* Sak);
+/* Running sum over measurements on the device: the component-summed S(k) of this call (same arguments, comp_mask != 0) is ADDED to a buffer
+ * [R][nk] owned by the handle instead of being copied out (a measurement then costs the DFT only, not the copy).  scmc_structure_factor_fetch
+ * returns the SUM (divide by *count for the mean; Sk may be NULL to read the count only) and, with reset != 0, drops the buffer.  The momentum
+ * list and mask must stay the same between resets.  Mirrors how the reference averages correlations before computeStructureFactor
+ * (ObservablesGeneric.jl:32-46, 49-72). */
+int32_t scmc_structure_factor_accumulate(scmc_t* h, int32_t L1, int32_t L2, int32_t n_basis, const int32_t* cell, const int32_t* basis, int32_t nk,
+                                         const int32_t* m, const double* phase, double n_rs, uint32_t comp_mask);
+int32_t scmc_structure_factor_fetch(scmc_t* h, double* Sk /* [R][nk] or NULL */, int64_t* count, int32_t reset);
 /* getCorrelations (Observables.jl:22-41) of one replica for a caller-supplied project map [N][N] (0-based), C [16][n_rs] */
 int32_t scmc_correlations(scmc_t* h, int64_t replica, const int32_t* project, int64_t n_rs, double* C);
 

@@ -23,7 +23,9 @@ for lat, L, n, R, box, nk_direct in (("honeycomb", 24, 2, 64, 4 * np.pi, None), 
     t_g, Sg = timed(lambda: scmc.structureFactor(cfg, sub, method="grid"), 3)
     t_gall, Sall = timed(lambda: scmc.structureFactor(cfg, ks, method="grid"), 3)
     t_sum, Ssum = timed(lambda: scmc.structureFactorSum(cfg, ks), 3)
+    plan = scmc.StructureFactorPlan(cfg, ks); plan.accumulate()
+    t_acc, _ = timed(lambda: plan.accumulate(), 5); plan.mean()
     err = np.abs(Sg - Sd).max() / np.abs(Sd).max()
     print(f"{lat} L={L} n={n} R={R}: N={cfg.nSites}, {len(ks)} allowed k in the box; sweep {1e3*t_sw:.3f} ms | {len(sub)} k: direct {1e3*t_d:8.1f} ms, grid {1e3*t_g:7.1f} ms ({t_d/t_g:6.1f}x), "
-          f"max rel. diff {err:.1e} | all {len(ks)} k through the grid path: {1e3*t_gall:8.1f} ms = {t_gall/t_sw:7.1f} sweeps (output {Sall.nbytes/2**20:.0f} MiB; direct would take ~{1e3*t_d*len(ks)/len(sub):.0f} ms); summed over components 0..14 on the device: {1e3*t_sum:7.1f} ms = {t_sum/t_sw:6.1f} sweeps (output {Ssum.nbytes/2**20:.0f} MiB)", flush=True)
+          f"max rel. diff {err:.1e} | all {len(ks)} k through the grid path: {1e3*t_gall:8.1f} ms = {t_gall/t_sw:7.1f} sweeps (output {Sall.nbytes/2**20:.0f} MiB; direct would take ~{1e3*t_d*len(ks)/len(sub):.0f} ms); summed over components 0..14 on the device: {1e3*t_sum:7.1f} ms = {t_sum/t_sw:6.1f} sweeps (output {Ssum.nbytes/2**20:.0f} MiB); accumulated on the device (no copy): {1e3*t_acc:7.2f} ms = {t_acc/t_sw:6.1f} sweeps", flush=True)
     cfg.close()

@@ -5,6 +5,7 @@ Host-side mirror of the reference's Julia API (src/SemiClassicalMC.jl:19-87) on 
 Julia's `f!` names are spelled `f_` here.
 """
 from . import _lib
+from ._lib import ScmcError      # the exception every failing library call raises
 from .build import build as build_library
 
 

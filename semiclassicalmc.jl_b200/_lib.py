@@ -63,6 +63,8 @@ SIGNATURES = {
     "scmc_measure": (C.c_int32, [C.c_void_p, c_dp]),
     "scmc_structure_factor": (C.c_int32, [C.c_void_p, c_dp, c_dp, C.c_int32, C.c_int32, C.c_double, c_dp]),
     "scmc_structure_factor_grid": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_ip, c_ip, C.c_int32, c_ip, c_dp, C.c_double, C.c_uint32, c_dp]),
+    "scmc_structure_factor_accumulate": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, c_ip, c_ip, C.c_int32, c_ip, c_dp, C.c_double, C.c_uint32]),
+    "scmc_structure_factor_fetch": (C.c_int32, [C.c_void_p, c_dp, C.POINTER(C.c_int64), C.c_int32]),
     "scmc_correlations": (C.c_int32, [C.c_void_p, C.c_int64, c_ip, C.c_int64, c_dp]),
     "scmc_sublattice_magnetization": (C.c_int32, [C.c_void_p, c_ip, C.c_int32, c_dp]),
     "scmc_chirality": (C.c_int32, [C.c_void_p, c_ip, c_dp]),

@@ -77,6 +77,10 @@ struct scmc_handle {
     static constexpr int N_SCRATCH = 8;
     void* scratch[N_SCRATCH] = {nullptr};
     size_t scratch_bytes[N_SCRATCH] = {0};
+    // running sum of the component-summed structure factor over measurements (scmc_structure_factor_accumulate / _fetch)
+    double* sf_acc = nullptr;                    // [R][sf_acc_nk]
+    int64_t sf_acc_nk = 0, sf_acc_count = 0;
+    uint32_t sf_acc_mask = 0;
     double* d_meas_partial = nullptr;            // [R][parts][17] per-CTA partial sums of the psi-family measurement
     size_t meas_partial_bytes = 0;
     void* pinned = nullptr;                      // pinned host staging for the beta / sigma tables

@@ -1617,7 +1617,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
 int32_t scmc_destroy(scmc_t* h) {
     if (!h) return SCMC_OK;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->d_meas_partial, h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16, h->d_cls_site, h->d_cls_nbr};
+    void* ptrs[] = {h->sf_acc, h->d_meas_partial, h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16, h->d_cls_site, h->d_cls_nbr};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < scmc_handle::N_SCRATCH; i++) if (h->scratch[i]) cudaFree(h->scratch[i]);
     if (h->pinned) cudaFreeHost(h->pinned);

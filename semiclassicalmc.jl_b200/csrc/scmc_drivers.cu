@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) k_sf_dft_cols(const double2* __restrict__
 // S^a(k) for the requested momenta: out[r][a][k] = |sum_b phase[k][b] F[r][b][a][m1_k][m2_k]|^2 / n_rs;  grid (ceil(nk / 128), replicas)
 // comp_mask != 0: out[r][k] = sum over the components a with bit a set (computeStructureFactor, Observables.jl:101-113)
 __global__ void __launch_bounds__(128) k_sf_combine(const double2* __restrict__ F, const int32_t* __restrict__ m, const double2* __restrict__ phase, int nk, int L1, int L2, int nb,
-                                                    double inv_nrs, int64_t r0, uint32_t comp_mask, double* __restrict__ out) {
+                                                    double inv_nrs, int64_t r0, uint32_t comp_mask, int add, double* __restrict__ out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nk) return;
     const int m1 = m[2 * k], m2 = m[2 * k + 1];
@@ -274,7 +274,10 @@ __global__ void __launch_bounds__(128) k_sf_combine(const double2* __restrict__ 
         if (comp_mask) total += v;
         else out[((size_t)(r0 + blockIdx.y) * NG + a) * nk + k] = v;
     }
-    if (comp_mask) out[(size_t)(r0 + blockIdx.y) * nk + k] = total;
+    if (comp_mask) {
+        double* o = out + (size_t)(r0 + blockIdx.y) * nk + k;       // one thread per (replica, momentum): no atomics needed
+        *o = add ? *o + total : total;
+    }
 }
 
 // C[a][project[i][j]] += T_i^a T_j^a  (Observables.jl:22-41); project given in the caller's site order
@@ -689,9 +692,11 @@ int32_t scmc_structure_factor(scmc_t* h, const double* ks, const double* pos, in
     return SCMC_OK;
 }
 
-int32_t scmc_structure_factor_grid(scmc_t* h, int32_t L1, int32_t L2, int32_t n_basis, const int32_t* cell, const int32_t* basis, int32_t nk, const int32_t* m,
-                                   const double* phase, double n_rs, uint32_t comp_mask, double* Sak) {
-    SCMC_ARG(h && cell && basis && m && phase && Sak, "null argument");
+// shared body of scmc_structure_factor_grid (Sak != nullptr: result copied to the host) and scmc_structure_factor_accumulate (Sak == nullptr:
+// the component-summed result is added to the handle's running sum on the device)
+static int32_t sf_grid_run(scmc_t* h, int32_t L1, int32_t L2, int32_t n_basis, const int32_t* cell, const int32_t* basis, int32_t nk, const int32_t* m,
+                           const double* phase, double n_rs, uint32_t comp_mask, double* Sak) {
+    SCMC_ARG(h && cell && basis && m && phase, "null argument");
     SCMC_ARG(L1 >= 1 && L2 >= 1 && n_basis >= 1 && nk >= 1 && n_rs > 0, "scmc_structure_factor_grid: bad sizes");
     SCMC_ARG((int64_t)L1 * L2 * n_basis == h->N, "scmc_structure_factor_grid: L1 * L2 * n_basis must equal the number of sites");
     SCMC_ARG(comp_mask <= 0xFFFFu, "scmc_structure_factor_grid: component mask has bits above 15");
@@ -717,7 +722,22 @@ int32_t scmc_structure_factor_grid(scmc_t* h, int32_t L1, int32_t L2, int32_t n_
     SCMC_CK(dgs.alloc(gs.size() * 4)); SCMC_CK(dtw.alloc(tw.size() * 8)); SCMC_CK(dX.alloc(per_rep * rb)); SCMC_CK(dF.alloc(per_rep * rb));
     SCMC_CK(dm.alloc((size_t)nk * 2 * 4)); SCMC_CK(dph.alloc((size_t)nk * n_basis * 16));
     const size_t out_bytes = (size_t)h->R * (comp_mask ? 1 : 16) * nk * 8;
-    SCMC_CK(dout.alloc(out_bytes));
+    const bool accumulate = Sak == nullptr;
+    if (accumulate) {
+        SCMC_ARG(comp_mask != 0, "scmc_structure_factor_accumulate: a component mask is required");
+        if (h->sf_acc && (h->sf_acc_nk != nk || h->sf_acc_mask != comp_mask)) {
+            set_error("scmc_structure_factor_accumulate: momentum count or component mask differs from the running sum; fetch with reset first");
+            return SCMC_ERR_ARG;
+        }
+        if (!h->sf_acc) {
+            SCMC_CK(cudaMalloc(&h->sf_acc, out_bytes));
+            SCMC_CK(cudaMemsetAsync(h->sf_acc, 0, out_bytes, h->stream));
+            h->sf_acc_nk = nk; h->sf_acc_mask = comp_mask; h->sf_acc_count = 0;
+        }
+    } else {
+        SCMC_CK(dout.alloc(out_bytes));
+    }
+    double* d_result = accumulate ? h->sf_acc : dout.as<double>();
     SCMC_CK(cudaMemcpyAsync(dgs.p, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice, h->stream));
     SCMC_CK(cudaMemcpyAsync(dtw.p, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice, h->stream));
     SCMC_CK(cudaMemcpyAsync(dm.p, m, (size_t)nk * 2 * 4, cudaMemcpyHostToDevice, h->stream));
@@ -738,12 +758,39 @@ int32_t scmc_structure_factor_grid(scmc_t* h, int32_t L1, int32_t L2, int32_t n_
         const dim3 g2((unsigned)((L1 + 7) / 8), (unsigned)(16 * n_basis), (unsigned)rc);
         k_sf_dft_cols<<<g2, 256, smem2, h->stream>>>(dX.as<double2>(), tw2, L1, L2, n_basis, dF.as<double2>());
         const dim3 g3(grid_for(nk, 128), (unsigned)rc);
-        k_sf_combine<<<g3, 128, 0, h->stream>>>(dF.as<double2>(), dm.as<int32_t>(), dph.as<double2>(), nk, L1, L2, n_basis, 1.0 / n_rs, r0, comp_mask, dout.as<double>());
+        k_sf_combine<<<g3, 128, 0, h->stream>>>(dF.as<double2>(), dm.as<int32_t>(), dph.as<double2>(), nk, L1, L2, n_basis, 1.0 / n_rs, r0, comp_mask, accumulate ? 1 : 0, d_result);
         h->launches += 3;
         SCMC_CK(cudaGetLastError());
     }
-    SCMC_CK(cudaMemcpyAsync(Sak, dout.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (accumulate) h->sf_acc_count++;
+    else SCMC_CK(cudaMemcpyAsync(Sak, dout.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
     SCMC_CK(cudaStreamSynchronize(h->stream));
+    return SCMC_OK;
+}
+
+int32_t scmc_structure_factor_grid(scmc_t* h, int32_t L1, int32_t L2, int32_t n_basis, const int32_t* cell, const int32_t* basis, int32_t nk, const int32_t* m,
+                                   const double* phase, double n_rs, uint32_t comp_mask, double* Sak) {
+    SCMC_ARG(Sak != nullptr, "null argument");
+    return sf_grid_run(h, L1, L2, n_basis, cell, basis, nk, m, phase, n_rs, comp_mask, Sak);
+}
+
+int32_t scmc_structure_factor_accumulate(scmc_t* h, int32_t L1, int32_t L2, int32_t n_basis, const int32_t* cell, const int32_t* basis, int32_t nk, const int32_t* m,
+                                         const double* phase, double n_rs, uint32_t comp_mask) {
+    return sf_grid_run(h, L1, L2, n_basis, cell, basis, nk, m, phase, n_rs, comp_mask, nullptr);
+}
+
+int32_t scmc_structure_factor_fetch(scmc_t* h, double* Sk, int64_t* count, int32_t reset) {
+    SCMC_ARG(h && count, "null argument");
+    *count = h->sf_acc_count;
+    if (!h->sf_acc) return SCMC_OK;
+    SCMC_CK(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)h->R * h->sf_acc_nk * 8;
+    if (Sk && h->sf_acc_count > 0) SCMC_CK(cudaMemcpyAsync(Sk, h->sf_acc, bytes, cudaMemcpyDeviceToHost, h->stream));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    if (reset) {
+        SCMC_CK(cudaFree(h->sf_acc));
+        h->sf_acc = nullptr; h->sf_acc_nk = 0; h->sf_acc_count = 0; h->sf_acc_mask = 0;
+    }
     return SCMC_OK;
 }
 

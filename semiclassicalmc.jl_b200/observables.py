@@ -100,6 +100,43 @@ def structureFactorSum(cfg, ks, components=None):
     return _structure_factor_grid(cfg, ks, mi, mask)
 
 
+class StructureFactorPlan:
+    """S(k) summed over `components` on a fixed list of allowed momenta of a 2-D periodic cluster, averaged over measurements ON THE DEVICE:
+    `accumulate()` after every measurement interval adds the current S(k) of all replicas to a running sum held by the handle (no copy to the
+    host), `mean()` returns [R, nk] and the number of measurements.  The momentum tables are prepared once.  Device counterpart of averaging
+    correlations and calling computeStructureFactor at the end (ObservablesGeneric.jl:32-46, 49-72; Observables.jl:101-113)."""
+
+    def __init__(self, cfg, ks, components=None):
+        comps = list(range(15)) if components is None else [int(c) for c in components]
+        ks = _lib.f64(ks)
+        mi = _allowed_momentum_indices(cfg, ks)
+        if mi is None or len(set(comps)) != len(comps):
+            raise ValueError("StructureFactorPlan: needs allowed momenta of a 2-D periodic cluster and distinct components")
+        lat = cfg.lattice
+        self.cfg, self.nk, self.L, self.nb = cfg, ks.shape[0], lat.L, len(cfg.basis)
+        self.mask = 0
+        for c in comps:
+            self.mask |= 1 << c
+        self.m = np.ascontiguousarray(np.mod(mi, lat.L), dtype=np.int32)
+        ang = ks @ np.stack(cfg.basis).astype(float).T
+        self.phase = np.ascontiguousarray(np.stack([np.cos(ang), np.sin(ang)], axis=-1))
+        self.cell = np.ascontiguousarray(lat.cells, dtype=np.int32)
+        self.basis = np.ascontiguousarray(lat.basis_labels - 1, dtype=np.int32)
+
+    def accumulate(self):
+        c = self.cfg
+        _lib.check(c._lib.scmc_structure_factor_accumulate(c._h, self.L, self.L, self.nb, _lib.iptr(self.cell), _lib.iptr(self.basis), self.nk, _lib.iptr(self.m),
+                                                           _lib.dptr(self.phase), float(self.nb * c.nSites), self.mask))
+
+    def mean(self, reset=True):
+        """([R, nk] mean over the accumulated measurements, their number)."""
+        import ctypes as C
+        c = self.cfg
+        out = np.zeros((c.n_replicas, self.nk)); cnt = C.c_int64(0)
+        _lib.check(c._lib.scmc_structure_factor_fetch(c._h, _lib.dptr(out), C.byref(cnt), 1 if reset else 0))
+        return (out / cnt.value if cnt.value else out), int(cnt.value)
+
+
 def _structure_factor_grid(cfg, ks, mi, mask):
     lat = cfg.lattice
     L, nb = lat.L, len(cfg.basis)

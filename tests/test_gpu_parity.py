@@ -669,3 +669,31 @@ def test_structure_factor_grid_equals_direct_sum(scmc, lattice, L, n, precision)
     assert np.allclose(scmc.structureFactorSum(cfg, off), scmc.structureFactor(cfg, off, method="direct")[:, :15, :].sum(axis=1), rtol=1e-12)
     with pytest.raises(ValueError):
         scmc.structureFactor(cfg, off, method="grid")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lattice, L, n", [("honeycomb", 8, 2), ("triangular", 12, 1)])
+def test_structure_factor_running_sum_on_the_device(scmc, lattice, L, n):
+    """StructureFactorPlan: S(k) summed over components, accumulated on the device over measurements and fetched once, against the host-side
+    average of structureFactorSum taken at the same points of the chain."""
+    R = 4
+    J = [np.eye(16)] if n == 2 else [NOTEBOOK_J]
+    cfg = scmc.initializeCfg("nearest-neighbor", lattice, J, L, n, n_replicas=R, precision=32, seed=23)
+    ks = scmc.getKsInBox(lattice, L, [4 * np.pi, 4 * np.pi], [0.0, 0.0])
+    plan = scmc.StructureFactorPlan(cfg, ks)
+    assert plan.mean(reset=False)[1] == 0                      # nothing accumulated yet
+    beta, sigma = np.array([0.5, 1.0, 3.0, 9.0]), np.full(R, 0.4)
+    host = np.zeros((R, len(ks))); n_meas = 5
+    for _ in range(n_meas):
+        cfg.sweep(3, beta, sigma)
+        plan.accumulate()
+        host += scmc.structureFactorSum(cfg, ks)
+    with pytest.raises(scmc.ScmcError):                        # another momentum list while a sum is running
+        scmc.StructureFactorPlan(cfg, ks[:-3]).accumulate()
+    mean, cnt = plan.mean(reset=True)
+    assert cnt == n_meas and np.allclose(mean, host / n_meas, rtol=1e-12, atol=1e-12 * np.abs(host).max())
+    assert plan.mean()[1] == 0                                 # reset dropped the running sum
+    other = scmc.StructureFactorPlan(cfg, ks[:-3], components=[4, 8, 12])
+    other.accumulate()
+    m2, c2 = other.mean()
+    assert c2 == 1 and np.allclose(m2, scmc.structureFactorSum(cfg, ks[:-3], components=[4, 8, 12]), rtol=1e-12)
