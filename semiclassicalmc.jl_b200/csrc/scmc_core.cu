@@ -1120,8 +1120,7 @@ cudaError_t scratch_get(scmc_handle* h, int slot, size_t bytes, void** p) {
         }
         cudaError_t e = cudaMalloc(&h->scratch[slot], bytes);
         if (e != cudaSuccess) { h->scratch[slot] = nullptr; return e; }
-        h->scratch_bytes[slot] = bytes;
-        h->bytes += 0;      // scratch is not part of the model footprint reported by scmc_info
+        h->scratch_bytes[slot] = bytes;      // (scratch is not part of the model footprint scmc_info reports)
     }
     *p = h->scratch[slot];
     return cudaSuccess;
