@@ -20,7 +20,7 @@ def launch_(filename, model, n, obstype, latticename, L, J, T, T_i, N_therm, N_m
     obs = initializeObservables(obstype or ObservablesGeneric, cfg)
     res = run_(cfg, obs, Ts, T_i, N_therm, N_measure, filename, measurement_rate=measurement_rate, checkpoint_rate=checkpoint_rate,
                report_rate=report_rate, hits=hits)
-    res["means"] = [means(obs, cfg, 1.0 / Ts[r], r) for r in range(len(Ts))]
+    res["means"] = [obs.means(cfg, 1.0 / Ts[r], r) for r in range(len(Ts))]      # saveMeans! of the observables type
     res["cfg"], res["obs"], res["T"] = cfg, obs, Ts
     return res
 

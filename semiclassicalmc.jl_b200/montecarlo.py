@@ -46,6 +46,9 @@ def run_(cfg, obs, T, T_i, N_therm, N_measure, filename=None, *, measurement_rat
     R = cfg.n_replicas
     T, T_i, sig = _per_replica(T, R), _per_replica(T_i, R), _per_replica(σ, R)
     rate = int(measurement_rate)
+    if obs is not None and not hasattr(obs, "push_rows"):
+        return _run_with_own_measure(cfg, obs, T, T_i, sig, int(N_therm), int(N_measure), rate, int(current_sweep), int(hits), energy, βs,
+                                     filename, verbose)
     n_rows = max(0, (N_therm + N_measure) // rate - max(N_therm, current_sweep) // rate)
     series = np.zeros((max(n_rows, 1), R, _lib.NOBS)) if keep_series else None
     mean = np.zeros((R, _lib.NOBS)); accr = np.zeros(R)
@@ -75,6 +78,49 @@ def run_(cfg, obs, T, T_i, N_therm, N_measure, filename=None, *, measurement_rat
     if verbose and filename:
         print(f"{filename}: Calculation finished", flush=True)
     return dict(sigma=sig, acc_rate=accr, series=series[:rows] if keep_series else None, mean=mean, therm_energy=therm[:n_log], rows=rows)
+
+
+def _run_with_own_measure(cfg, obs, T, T_i, sig, N_therm, N_measure, rate, current_sweep, hits, energy, βs, filename, verbose):
+    """run! for an observables type whose measure! needs more than the device's 21-value rows (ObservablesTgHbn: sublattice magnetisations,
+    chiralities; the reference dispatches measure!(obs, cfg, E) on the type, MonteCarlo.jl:82-86).  Thermalisation goes through the driver
+    (ramp, sigma adaptation, energy log on the device); the measurement phase runs in intervals of `rate` sweeps at frozen beta / sigma with
+    `obs.measure(cfg)` after each.  Same visit numbers as the all-device run, so the chain is the one run_(cfg, None, ...) produces."""
+    R = cfg.n_replicas
+    n_log = max(0, N_therm // rate - current_sweep // rate)
+    therm = np.zeros((max(n_log, 1), R)); mean = np.zeros((R, _lib.NOBS)); accr = np.zeros(R)
+    p = _lib.RunParams(N_therm, 0, rate, hits, 0, C.c_uint64(cfg.seed), C.c_uint64(current_sweep), _lib.dptr(T), _lib.dptr(T_i), _lib.dptr(sig))
+    out = _lib.RunResults(None, 0, _lib.dptr(mean), _lib.dptr(accr), _lib.dptr(therm))
+    if verbose and filename:
+        print(f"{filename}: Starting thermalization sweeps", flush=True)
+    _lib.check(cfg._lib.scmc_run_metropolis(cfg._h, C.byref(p), C.byref(out)))
+    beta = 1.0 / T
+    acc_tot = np.zeros(R); att_tot = np.zeros(R)
+    rows = 0
+    s = max(N_therm, current_sweep)              # sweeps done so far; sweep s + 1 uses visit base s * hits (as scmc_run_metropolis does)
+    total = N_therm + N_measure
+    while s < total:
+        n = min(total, (s // rate + 1) * rate) - s
+        cfg.sweep_counter = s
+        acc, att = cfg.sweep(n, beta, sig, hits=hits)
+        acc_tot += acc; att_tot += att
+        s += n
+        if s % rate == 0:
+            obs.measure(cfg)
+            rows += 1
+    cfg.sweep_counter = max(cfg.sweep_counter, total)
+    accr = np.divide(acc_tot, att_tot, out=np.zeros(R), where=att_tot > 0)
+    if energy is not None:
+        energy.extend(therm[:n_log, 0].tolist())
+    if βs is not None:
+        n_anneal = int(np.ceil(0.75 * N_therm))
+        for q in range(current_sweep + 1, N_therm + 1):
+            if q % rate == 0:
+                t = T_i[0] * (T[0] / T_i[0]) ** ((q - 1) / (n_anneal - 1)) if (q <= n_anneal and n_anneal > 1) else T[0]
+                βs.append(1.0 / t)
+        βs.extend([1.0 / T[0]] * rows)
+    if verbose and filename:
+        print(f"{filename}: Calculation finished", flush=True)
+    return dict(sigma=sig, acc_rate=accr, series=None, mean=None, therm_energy=therm[:n_log], rows=rows)
 
 
 def runAnnealing_(cfg, T_i, filename=None, *, T_fac=0.98, N_max=10_000_000, N_o=0, N_per_T=10000, min_acc_per_site=100,

@@ -186,6 +186,13 @@ class ObservablesGeneric(Observables):
         self.project = getProject(cfg) if correlations else None
         self.correlations = [LogBinner(np.zeros((16, len(cfg.basis) * cfg.nSites))) for _ in range(R)] if correlations else None
 
+    def measure(self, cfg):
+        """measure!(obs, cfg, E) for this observables type (ObservablesGeneric.jl:32-46)."""
+        measure_(self, cfg)
+
+    def means(self, cfg, beta, replica=0):
+        return means(self, cfg, beta, replica)
+
     def push_rows(self, rows):
         """rows: [n, R, 21] measurement rows from the device."""
         rows = np.asarray(rows, dtype=np.float64)
@@ -308,6 +315,13 @@ class ObservablesTgHbn(Observables):
         self.series = {n: ReplicaSeries(R) for n in self.NAMES}
         self.binder = {n: ReplicaPropagator(R, 2) for n in self.NAMES}
         self.with_correlations = False
+
+    def measure(self, cfg):
+        """measure!(obs, cfg, E) for this observables type (ObservablesTgHbn.jl:47-98)."""
+        measureTgHbn_(self, cfg)
+
+    def means(self, cfg, beta, replica=0):
+        return meansTgHbn(self, cfg, beta, replica)
 
     def values(self, cfg):
         """One measurement of every replica: dict name -> [R] (the quantities pushed by measure!, ObservablesTgHbn.jl:47-98)."""
