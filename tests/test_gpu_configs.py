@@ -161,3 +161,30 @@ def test_C4_full_schedule_reaches_exact_ground_state(scmc, golden):
     e = res["E"] / cfg.nSites
     assert abs(e.min() - golden["annealing"]["exact_E_per_site"]) < 1e-8, e.min()
     assert np.all(e >= -3.6 - 1e-9)
+
+
+@pytest.mark.gpu
+def test_run_and_launch_dispatch_on_the_observables_type(scmc):
+    """run!(cfg, obs::ObservablesTgHbn, ...) (the reference dispatches measure! on the observables type, MonteCarlo.jl:82-86; launch! passes the
+    type through, Launcher.jl:49-90): the measurement phase calls the TG/h-BN measure! after every interval, the chain is the one the all-device
+    run produces, and launch_ returns the TG/h-BN means."""
+    Jtg = [1.0, 0.3, 0.2, 0.15, 0.8]
+    R = 5
+    Ts = np.geomspace(0.05, 1.0, R)
+    mk = lambda: scmc.initializeCfg("tg-hbn", "triangular", Jtg, 12, 2, n_replicas=R, precision=32, seed=41)
+    a = mk(); ra = scmc.run_(a, None, Ts, 2.0, 60, 85, measurement_rate=10)
+    b = mk(); obs = scmc.initializeObservables(scmc.ObservablesTgHbn, b)
+    rb = scmc.run_(b, obs, Ts, 2.0, 60, 85, measurement_rate=10)
+    assert ra["rows"] == rb["rows"] == 8
+    assert np.array_equal(a.get_state(), b.get_state()) and np.array_equal(ra["sigma"], rb["sigma"])
+    assert np.allclose(ra["acc_rate"], rb["acc_rate"], rtol=1e-14, atol=0)
+    assert obs.energy[0].count == 8 and obs.series["msd"][R - 1].count == 8 and obs.binder["spinChirality"][2].count == 8
+    for r in range(R):
+        assert abs(obs.energy[r].means()[0] - ra["mean"][r, 0]) < 2e-5
+    m = obs.means(b, 1.0 / Ts[0], 0)
+    assert {"energy", "heat", "msd", "binder_msd", "subMsd", "spinChirality"} <= set(m) and np.isfinite(m["heat"][0])
+    res = scmc.launch_("tghbn_test", "tg-hbn", 2, scmc.ObservablesTgHbn, "triangular", 12, Jtg, Ts, 2.0, 60, 85, measurement_rate=10, seed=41)
+    assert res["rows"] == 8 and len(res["means"]) == R and "binder_msz" in res["means"][0]
+    assert np.array_equal(res["cfg"].get_state(), a.get_state())
+    gen = scmc.launch_("generic_test", "tg-hbn", 2, None, "triangular", 12, Jtg, Ts, 2.0, 60, 85, measurement_rate=10, seed=41)
+    assert gen["rows"] == 8 and "magnetizationVec" in gen["means"][0] and np.array_equal(gen["cfg"].get_state(), a.get_state())
