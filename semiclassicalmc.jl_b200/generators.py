@@ -48,7 +48,10 @@ def _one_body(M, states):
 
 
 def getGenerators(n):
-    """[16, d, d] complex; G[a] = sigma^mu (x) tau^nu, a = 4 mu + nu (0-based)."""
+    """[16, d, d] complex; G[a] = sigma^mu (x) tau^nu, a = 4 mu + nu (0-based).  Like the reference's two methods, getGenerators(n::Int)
+    (Generators.jl:2) and getGenerators(cfg) (Configuration.jl:108), the argument may be a filling or a Configuration."""
+    if hasattr(n, "generators"):
+        return n.generators
     if n not in (1, 2, 3):
         raise ValueError("filling n must be 1, 2 or 3")
     states = fock_states(n)
@@ -56,6 +59,9 @@ def getGenerators(n):
 
 
 def getGeneratorsSq(n):
+    """Matrix squares (G^a)^2 for a filling, or the stored ones of a Configuration (Configuration.jl:52, 112)."""
+    if hasattr(n, "generatorsSq"):
+        return n.generatorsSq
     g = getGenerators(n)
     return np.einsum("aij,ajk->aik", g, g)
 

@@ -188,3 +188,42 @@ def test_run_and_launch_dispatch_on_the_observables_type(scmc):
     assert np.array_equal(res["cfg"].get_state(), a.get_state())
     gen = scmc.launch_("generic_test", "tg-hbn", 2, None, "triangular", 12, Jtg, Ts, 2.0, 60, 85, measurement_rate=10, seed=41)
     assert gen["rows"] == 8 and "magnetizationVec" in gen["means"][0] and np.array_equal(gen["cfg"].get_state(), a.get_state())
+
+
+@pytest.mark.gpu
+def test_reference_accessors_against_direct_formulas(scmc):
+    """The exported accessor names of the reference (Configuration.jl:80-298, Observables.jl:16-18, MonteCarlo.jl:244-260) through the host
+    mirror, on an n = 2 model with on-site couplings: each is called once and checked against the formula it stands for."""
+    Jon = np.diag(np.linspace(-0.3, 0.4, 16))
+    rng = np.random.default_rng(12)
+    A = rng.uniform(-1, 1, (16, 16)); Jnn = 0.5 * (A + A.T)
+    cfg = scmc.initializeCfg("nearest-neighbor", "honeycomb", [Jon, Jnn], 4, 2, n_replicas=2, precision=64, seed=3)
+    N, d = cfg.nSites, cfg.d
+    assert len(cfg) == N == 32 and d == 6
+    assert scmc.getPosition(cfg, 5).shape == (2,) and len(scmc.getBasis(cfg)) == 2
+    nb, lb = scmc.getInteractionSites(cfg, 7), scmc.getInteractionLabels(cfg, 7)
+    assert len(nb) == len(lb) == 3 and set(lb.tolist()) == {1}
+    assert np.array_equal(scmc.getInteraction(cfg, 1), Jnn) and np.array_equal(scmc.getOnsiteInteraction(cfg), np.diag(Jon))
+    psi = cfg.get_state(0, 1)[0]
+    G, Gsq = scmc.getGenerators(cfg), scmc.getGeneratorsSq(cfg)
+    assert np.array_equal(scmc.getState(cfg, 9), psi[9]) and abs(np.linalg.norm(psi[9]) - 1) < 1e-12
+    T = np.stack([scmc.computeSpinExpectation(psi[i], G) for i in range(N)])
+    Tsq = np.stack([scmc.computeSpinExpectation(psi[i], Gsq) for i in range(N)])
+    assert np.allclose(scmc.getSpinExpectation(cfg), T, atol=1e-12) and np.allclose(scmc.getSpinExpectation(cfg, 9), T[9], atol=1e-12)
+    assert np.allclose(scmc.getSpinSqExpectation(cfg), Tsq, atol=1e-12)
+    buf = np.zeros(16); scmc.computeSpinExpectation_(buf, psi[3], G); assert np.array_equal(buf, T[3])
+    # getEnergy = sum_i [K.Tsq_i + 1/2 sum_j T_i J T_j] (Configuration.jl:236-253)
+    E = sum(scmc.onsiteEnergy(Tsq[i], cfg.onsiteInteraction) + 0.5 * sum(scmc.exchangeEnergy(T[i], Jnn, T[j]) for j in scmc.getInteractionSites(cfg, i)) for i in range(N))
+    assert abs(scmc.getEnergy(cfg) - E) < 1e-11 and np.allclose(scmc.getEnergy(cfg, "all"), cfg.energies())
+    # getEnergyDifference for a proposed state of site 9 = E(new) - E(old)
+    new = scmc.getRandomState(d, rng); assert abs(np.linalg.norm(new) - 1) < 1e-12
+    prop = np.zeros(d, dtype=complex); scmc.getRandomState_(prop, psi[9], 0.3, rng); assert abs(np.linalg.norm(prop) - 1) < 1e-12
+    dE = scmc.getEnergyDifference(cfg, 9, scmc.computeSpinExpectation(new, G), scmc.computeSpinExpectation(new, Gsq))
+    psi2 = psi.copy(); psi2[9] = new
+    cfg.set_state(psi2[None], 0)
+    assert abs((scmc.getEnergy(cfg) - E) - dE) < 1e-11
+    assert np.allclose(scmc.getMagnetization(cfg), scmc.getSpinExpectation(cfg).mean(axis=0), atol=1e-13)
+    obs = scmc.initializeObservables(scmc.ObservablesGeneric, cfg)
+    scmc.measure_(obs, cfg); scmc.measure_(obs, cfg)
+    assert obs.energy[0].count == 2 and abs(obs.energy[0].means()[0] - scmc.getEnergy(cfg) / N) < 1e-12
+    assert np.allclose(obs.magnetizationVec[0].mean(), scmc.getMagnetization(cfg), atol=1e-13)
