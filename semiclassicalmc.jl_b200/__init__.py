@@ -11,10 +11,10 @@ from .build import build as build_library
 
 def __getattr__(name):   # lazy: the API modules need numpy only, the CUDA library is loaded on first use
     import importlib
-    _mods = ("generators", "lattice", "configuration", "models", "observables", "montecarlo", "launcher", "binning", "distributed", "io")
+    _mods = ("generators", "lattice", "configuration", "models", "observables", "montecarlo", "launcher", "binning", "distributed", "io", "hdf5")
     if name in _mods:
         return importlib.import_module(f".{name}", __name__)
-    for mod in ("generators", "lattice", "configuration", "models", "observables", "montecarlo", "launcher", "binning", "distributed", "io"):
+    for mod in ("generators", "lattice", "configuration", "models", "observables", "montecarlo", "launcher", "binning", "distributed", "io", "hdf5"):
         try:
             m = importlib.import_module(f".{mod}", __name__)
         except ModuleNotFoundError:

@@ -6,6 +6,26 @@ import numpy as np
 from .models import initializeCfg
 from .observables import initializeObservables, ObservablesGeneric, means
 from .montecarlo import run_, runAnnealing_
+from . import io as _io
+
+
+def resultFilename(filename, T, replica, n_replicas):
+    """File of one chain of a packed launch.  The reference runs one `launch!` per temperature with its own file (Launcher.jl:49-66,
+    notebook cell 22: `filename(T)`); here `filename` is either such a function of T, or a path: used as is for a single chain,
+    otherwise `<stem>_T<T>[_r<replica>]<.ext>` (replica index only when a temperature occurs more than once)."""
+    if callable(filename):
+        return filename(T)
+    if n_replicas == 1:
+        return str(filename)
+    stem, dot, ext = str(filename).rpartition(".")
+    if not dot:
+        stem, ext = ext, "h5"
+    return f"{stem}_T{T:.6g}" + (f"_r{replica}" if replica is not None else "") + "." + ext
+
+
+def _writes_files(filename):
+    """HDF5 result files are written for a `filename(T)` function or a path ending in .h5 / .hdf5; any other name is a label for the log."""
+    return callable(filename) or (isinstance(filename, str) and filename.lower().endswith((".h5", ".hdf5")))
 
 
 def launch_(filename, model, n, obstype, latticename, L, J, T, T_i, N_therm, N_measure, *, measurement_rate=10,
@@ -22,6 +42,15 @@ def launch_(filename, model, n, obstype, latticename, L, J, T, T_i, N_therm, N_m
                report_rate=report_rate, hits=hits)
     res["means"] = [obs.means(cfg, 1.0 / Ts[r], r) for r in range(len(Ts))]      # saveMeans! of the observables type
     res["cfg"], res["obs"], res["T"] = cfg, obs, Ts
+    if _writes_files(filename):              # checkpoint! + saveMeans! at the end of run! (MonteCarlo.jl:103-104), one HDF5 file per chain
+        res["files"] = []
+        for r in range(len(Ts)):
+            fn = resultFilename(filename, Ts[r], r if replicas_per_T > 1 else None, len(Ts))
+            series = res.get("series")
+            energy = np.concatenate([res["therm_energy"][:, r], series[:, r, 0]]) if series is not None else res["therm_energy"][:, r]
+            _io.checkpointH5_(fn, cfg, N_therm + N_measure, [], energy, res["sigma"], replica=r)
+            _io.saveMeans_(fn, obs, cfg, 1.0 / Ts[r], replica=r)
+            res["files"].append(fn)
     return res
 
 
@@ -37,4 +66,10 @@ def launchAnnealing_(filename, model, n, latticename, L, J, T_i, *, T_fac=0.98, 
                         min_accrate=min_accrate, checkpoint_rate=checkpoint_rate, σ_min=σ_min, verbose=verbose, hits=hits)
     res["cfg"] = cfg
     res["state"] = cfg.get_state()          # f["state"] (MonteCarlo.jl:232-234), [R, N, d]
+    if _writes_files(filename):             # checkpoint! + f["state"] at the end of runAnnealing! (MonteCarlo.jl:230-234), one file per restart
+        res["files"] = []
+        for r in range(n_restarts):
+            fn = filename(r) if callable(filename) else resultFilename(filename, float(r), None, n_restarts)
+            _io.checkpointH5_(fn, cfg, int(res["sweeps"][r]), [float(res["beta"][r])], [float(res["E"][r] / cfg.nSites)], res["sigma"], replica=r)
+            res["files"].append(fn)
     return res

@@ -308,6 +308,31 @@ def test_checkpoint_resume_continues_the_chain(scmc, tmp_path):
     assert m.shape == (1, 3)
 
 
+def test_launch_writes_the_reference_result_files(scmc, tmp_path):
+    """launch! ends in checkpoint! + saveMeans! (MonteCarlo.jl:103-104): one HDF5 file per temperature with `means/<key>/{mean,error}`,
+    `rs`, `energy`, `σ`, `current_sweep`, `state` (d x N); getmeans / getenergies (IO.jl:64-143) collect them over the grid."""
+    Ts = [0.1, 0.4, 1.6]
+    fn = str(tmp_path / "run.h5")
+    res = scmc.launch_(fn, "nearest-neighbor", 1, None, "triangular", 6, [NOTEBOOK_J], Ts, 2.0, 40, 60, measurement_rate=10, seed=3)
+    assert res["files"] == [str(tmp_path / f"run_T{T:.6g}.h5") for T in Ts]
+    psi = res["cfg"].get_state()
+    for r, f in enumerate(res["files"]):
+        one = scmc.readCheckpointH5(f)
+        assert np.array_equal(one["state"], psi[r].T) and one["rs"].shape == (2, 36) and int(one["current_sweep"]) == 100
+        assert one["energy"].shape == (4 + 6,) and float(one["σ"]) == res["sigma"][r]
+        for key, (mean, err) in res["means"][r].items():
+            assert np.array_equal(one["means"][key]["mean"], mean) and np.array_equal(one["means"][key]["error"], err)
+    name = lambda T: str(tmp_path / f"run_T{T:.6g}.h5")
+    out = scmc.getmeansH5(name, str(tmp_path / "means.h5"), Ts)
+    assert np.array_equal(out["energy/mean"], [m["energy"][0] for m in res["means"]]) and out["magnetizationVec/mean"].shape == (16, 3)
+    en = scmc.getenergiesH5(name, str(tmp_path / "energies.h5"), Ts)
+    assert np.array_equal(en["0.4"], scmc.readCheckpointH5(res["files"][1])["energy"])
+    ann = scmc.launchAnnealing_(str(tmp_path / "sa.h5"), "nearest-neighbor", 1, "triangular", 6, [NOTEBOOK_J], 3.0, N_max=300, N_per_T=20,
+                                min_acc_per_site=5, seed=5, n_restarts=2)
+    assert len(ann["files"]) == 2
+    assert np.allclose(scmc.readCheckpointH5(ann["files"][1])["state"], ann["state"][1].T, atol=0, rtol=0)
+
+
 @pytest.mark.parametrize("precision", [32, 64])
 def test_device_side_annealing_equals_host_driven_loop(scmc, precision):
     """runAnnealing!'s cooling loop inside the persistent resident kernel (one CTA per replica) vs the same loop driven from the
