@@ -1,6 +1,8 @@
 """launch! / launchAnnealing! -- host mirror of /root/reference/src/Launcher.jl:49-90, 142-182 (seed, build, run).
 The Slurm / launcher-file generators of Launcher.jl are out of scope: a temperature grid is
 packed into ONE launch as replicas instead of one job step per temperature."""
+import os
+
 import numpy as np
 
 from .models import initializeCfg
@@ -33,6 +35,16 @@ def launch_(filename, model, n, obstype, latticename, L, J, T, T_i, N_therm, N_m
             replica_offset=0, hits=2):
     """launch! (Launcher.jl:49-90).  `T` may be a list of temperatures: each becomes `replicas_per_T` replicas of one launch."""
     Ts = np.repeat(np.atleast_1d(np.asarray(T, dtype=float)), replicas_per_T)
+    if not overwrite and _writes_files(filename):
+        # overwrite = false (Launcher.jl:78-88): chains whose files already hold N_therm + N_measure sweeps are not run again.  Files are
+        # written once, at the end of a run, so a file is either complete or absent; anything else starts from scratch.
+        files = [resultFilename(filename, Ts[r], r if replicas_per_T > 1 else None, len(Ts)) for r in range(len(Ts))]
+        if all(os.path.exists(f) for f in files):
+            done = [_io.readCheckpointH5(f) for f in files]
+            if all(int(d["current_sweep"]) >= N_therm + N_measure and "means" in d for d in done):
+                print(f"{files[0]}: Already reached {N_therm + N_measure} sweeps, terminating.", flush=True)
+                return dict(files=files, T=Ts, means=[{k: (g["mean"], g["error"]) for k, g in d["means"].items()} for d in done],
+                            sigma=np.array([float(d["σ"]) for d in done]), resumed=True)
     cfg = initializeCfg(model, latticename, J, L, n, n_replicas=len(Ts), precision=precision, device=device, seed=seed,
                         replica_offset=replica_offset)
     if cfg is None:
@@ -69,7 +81,8 @@ def launchAnnealing_(filename, model, n, latticename, L, J, T_i, *, T_fac=0.98, 
     if _writes_files(filename):             # checkpoint! + f["state"] at the end of runAnnealing! (MonteCarlo.jl:230-234), one file per restart
         res["files"] = []
         for r in range(n_restarts):
-            fn = filename(r) if callable(filename) else resultFilename(filename, float(r), None, n_restarts)
+            stem, _, ext = str(filename).rpartition(".")
+            fn = filename(r) if callable(filename) else (str(filename) if n_restarts == 1 else f"{stem}_r{r}.{ext}")
             _io.checkpointH5_(fn, cfg, int(res["sweeps"][r]), [float(res["beta"][r])], [float(res["E"][r] / cfg.nSites)], res["sigma"], replica=r)
             res["files"].append(fn)
     return res

@@ -322,6 +322,8 @@ def test_launch_writes_the_reference_result_files(scmc, tmp_path):
         assert one["energy"].shape == (4 + 6,) and float(one["σ"]) == res["sigma"][r]
         for key, (mean, err) in res["means"][r].items():
             assert np.array_equal(one["means"][key]["mean"], mean) and np.array_equal(one["means"][key]["error"], err)
+    again = scmc.launch_(fn, "nearest-neighbor", 1, None, "triangular", 6, [NOTEBOOK_J], Ts, 2.0, 40, 60, measurement_rate=10, seed=3, overwrite=False)
+    assert again["resumed"] and again["files"] == res["files"] and again["means"][2]["energy"][0] == res["means"][2]["energy"][0]
     name = lambda T: str(tmp_path / f"run_T{T:.6g}.h5")
     out = scmc.getmeansH5(name, str(tmp_path / "means.h5"), Ts)
     assert np.array_equal(out["energy/mean"], [m["energy"][0] for m in res["means"]]) and out["magnetizationVec/mean"].shape == (16, 3)
