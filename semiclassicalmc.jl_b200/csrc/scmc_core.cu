@@ -51,6 +51,9 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #ifndef SCMC_SWEEP_BLOCKS_F64
 #define SCMC_SWEEP_BLOCKS_F64 3
 #endif
+#ifndef SCMC_SWEEP_BLOCKS_MMA
+#define SCMC_SWEEP_BLOCKS_MMA SCMC_SWEEP_BLOCKS     // the tensor-core mat-vec experiment (SCMC_MMA=1)
+#endif
 #ifndef SCMC_SWEEP_BLOCKS_NL
 #define SCMC_SWEEP_BLOCKS_NL SCMC_SWEEP_BLOCKS      // FP32 instantiations with several coupling labels
 #endif
@@ -329,13 +332,85 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
 // (64 bytes).  sum_j T_j = map(sum_j P_j) with P = conj(psi) psi^T, so the gather accumulates density-matrix entries with
 // FMAs and maps once per visit.  Nothing but psi is read or written: DRAM traffic per visit drops from ~272 B to ~150 B and
 // the T planes become a lazily refreshed cache (ensure_T).  Rounding differs from the T-gather kernels at the 1-ulp level.
-template <class R, int GEN, bool ONSITE>
-__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEEP_PSI_BLOCKS_F64 : SCMC_SWEEP_BLOCKS) k_sweep_colour_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A) {
+// MMA = true (experiment, SCMC_MMA=1, FP32 / 16 density entries / no on-site term only): the 32 sites of a warp multiply the SAME Jq, so
+// Hq[16 x 32] = Jq[16 x 16] . P[16 x 32] runs as 24 mma.sync.m16n8k8 in 3xTF32 (operands split into a 19-bit head and an exactly
+// representable tail) with the density sums and the result transposed through a per-warp shared-memory tile.  Different rounding
+// than the FFMA order of field_from_sums_smem, so it is NOT part of the bit-identity contract of the psi family.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+constexpr int MMA_LD = 20;           // row stride (floats) of the padded tiles: fragment loads, tile rows and 128-bit row accesses are conflict-free
+__device__ __forceinline__ void matvec_mma(const float* sAhi, const float* sAlo, float* tile, const float* P, float* h) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int q = 0; q < 4; q++) *reinterpret_cast<float4*>(tile + lane * MMA_LD + 4 * q) = make_float4(P[4 * q], P[4 * q + 1], P[4 * q + 2], P[4 * q + 3]);
+    __syncwarp();
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[j][c] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 2; kh++) {
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int idx = (g + 8 * (c & 1)) * MMA_LD + 8 * kh + t + 4 * (c >> 1);
+            ah[c] = __float_as_uint(sAhi[idx]); al[c] = __float_as_uint(sAlo[idx]);
+        }
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const float b = tile[(8 * j + g) * MMA_LD + 8 * kh + t + 4 * c];
+                bh[j][c] = __float_as_uint(b) & 0xffffe000u;
+                bl[j][c] = __float_as_uint(b - __uint_as_float(bh[j][c]));
+            }
+        // the three products of one accumulator are issued four MMAs apart (the four site tiles are independent)
+#pragma unroll
+        for (int j = 0; j < 4; j++) mma_tf32(acc[j], al, bh[j][0], bh[j][1]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) mma_tf32(acc[j], ah, bl[j][0], bl[j][1]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) mma_tf32(acc[j], ah, bh[j][0], bh[j][1]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        tile[(8 * j + 2 * t) * MMA_LD + g] = acc[j][0];
+        tile[(8 * j + 2 * t + 1) * MMA_LD + g] = acc[j][1];
+        tile[(8 * j + 2 * t) * MMA_LD + g + 8] = acc[j][2];
+        tile[(8 * j + 2 * t + 1) * MMA_LD + g + 8] = acc[j][3];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float4 v = *reinterpret_cast<const float4*>(tile + lane * MMA_LD + 4 * q);
+        h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+    }
+    __syncwarp();
+}
+
+template <class R, int GEN, bool ONSITE, bool MMA = false>
+__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEEP_PSI_BLOCKS_F64 : (MMA ? SCMC_SWEEP_BLOCKS_MMA : SCMC_SWEEP_BLOCKS)) k_sweep_colour_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A) {
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
+    static_assert(!MMA || (sizeof(R) == 4 && !ONSITE && NP == NG), "MMA mat-vec: FP32, 16 density entries, no on-site term");
     const int64_t r = A.r0 + blockIdx.y;
-    __shared__ __align__(16) R sJt[NG * NG];
+    __shared__ __align__(16) R sJt[MMA ? 1 : NG * NG];
+    __shared__ __align__(16) float sM[MMA ? 2 * NG * MMA_LD + (SCMC_SWEEP_THREADS / 32) * 32 * MMA_LD : 1];
     const bool fused = !ONSITE && NP == NG && A.Jqt != nullptr;      // density sums -> energy coefficients in one 16x16 mat-vec
-    for (int t = threadIdx.x; t < NG * NG; t += blockDim.x) sJt[t] = ((const R*)(fused ? A.Jqt : A.Jt))[t];
+    if constexpr (MMA) {
+        for (int t = threadIdx.x; t < NG * NG; t += blockDim.x) {      // Jq[m][k] = Jqt[k][m], split into TF32 head and tail
+            const float v = ((const float*)A.Jqt)[t];
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            const int k = t / NG, m = t % NG;
+            sM[m * MMA_LD + k] = hi; sM[NG * MMA_LD + m * MMA_LD + k] = v - hi;
+        }
+    } else {
+        for (int t = threadIdx.x; t < NG * NG; t += blockDim.x) sJt[t] = ((const R*)(fused ? A.Jqt : A.Jt))[t];
+    }
     const bool alive = (A.active == nullptr || A.active[r]);
     const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
     const R nbeta = neg_beta_scaled(beta);
@@ -352,7 +427,10 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
     unsigned nacc = 0;
     for (int colour = A.colour; colour <= A.colour_last; colour++) {
         const int nc = M.col_off[colour + 1] - M.col_off[colour];
-        for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nc && alive; s += gridDim.x * blockDim.x) {
+        // MMA: the loop condition is warp-uniform (mma.sync needs all 32 lanes); lanes past the end of the class redo its last site and do not store
+        for (int s0 = blockIdx.x * blockDim.x + threadIdx.x; (MMA ? s0 - (int)(threadIdx.x & 31) : s0) < nc && alive; s0 += gridDim.x * blockDim.x) {
+            const bool valid = !MMA || s0 < nc;
+            const int s = valid ? s0 : nc - 1;
             const int cp = M.col_off[colour] + s;          // class position: p, site and neighbour slots are independent loads
             const int p = M.col_list[cp];
             const int site = M.cls_site[cp];
@@ -381,7 +459,9 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
                         GenOps<GEN>::density_acc(nr, ni, P);
                     }
                 }
-                if (!fused) {
+                if constexpr (MMA) {
+                    matvec_mma(sM, sM + NG * MMA_LD, sM + 2 * NG * MMA_LD + (threadIdx.x >> 5) * 32 * MMA_LD, P, h);
+                } else if (!fused) {
                     R S[1][NG];
                     GenOps<GEN>::expect_from_density(P, S[0]);
                     field_from_sums_smem<1>(sJt, S, h);
@@ -401,7 +481,7 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
                 }
             } else {
                 R Hq[GenOps<GEN>::NDENS];
-                if (fused) {
+                if (fused || MMA) {
 #pragma unroll
                     for (int t = 0; t < (NP == NG ? NG : 0); t++) Hq[t] = h[t];
                 } else {
@@ -425,6 +505,7 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
                     mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
                 }
             }
+            if (!valid) mine = 0;
             if (mine) store_psi<R, D>(M.psi + rbase + p, ps, re, im);
             nacc += mine;
         }
@@ -1193,6 +1274,13 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A, cudaStream
                             const size_t smem = (size_t)(h->z + 1) * (GenOps<GEN>::D / 2) * SCMC_SWEEP_THREADS * sizeof(float4);
                             SCMC_CK(cudaFuncSetAttribute(k_sweep_colour_psi_async<GEN, ONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
                             k_sweep_colour_psi_async<GEN, ONS><<<grid, SCMC_SWEEP_THREADS, smem, stream>>>(M, B);
+                            launched = true;
+                        }
+                    }
+                    if constexpr (std::is_same<R, float>::value && !ONS && GenOps<GEN>::NDENS == NG) {
+                        static const bool use_mma = getenv("SCMC_MMA") && atoi(getenv("SCMC_MMA")) != 0;     // experiment, see matvec_mma
+                        if (!launched && use_mma && B.Jqt != nullptr) {
+                            k_sweep_colour_psi<R, GEN, ONS, true><<<grid, SCMC_SWEEP_THREADS, 0, stream>>>(M, B);
                             launched = true;
                         }
                     }

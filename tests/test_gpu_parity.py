@@ -308,6 +308,34 @@ def test_checkpoint_resume_continues_the_chain(scmc, tmp_path):
     assert m.shape == (1, 3)
 
 
+def test_tensor_core_matvec_experiment_differs_by_rounding_only():
+    """SCMC_MMA=1 (opt-in experiment): the 16x16 mat-vec of the streaming psi-gather kernel as 3xTF32 mma.sync over the
+    32 sites of a warp.  Same stream, so after a few sweeps the acceptance counts and energies agree with the default FFMA path to FP32
+    rounding; L = 10 has colour classes that are not multiples of 32 (tail lanes of the warp-uniform loop) and seam classes."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json, numpy as np; sys.path.insert(0, %r); import scmc_b200 as scmc\n"
+        "out = []\n"
+        "for L, R in ((10, 7), (24, 40)):\n"
+        "    J = np.diag([0, 0.2, 0.2, 0.2, -1, 0.2, 0.2, 0.2, -1, 0.2, 0.2, 0.2, -1, 0.2, 0.2, 0.2]).astype(float)\n"
+        "    cfg = scmc.initializeCfg('nearest-neighbor', 'triangular', [J], L, 1, n_replicas=R, precision=32, seed=77)\n"
+        "    cfg.set_sweep_mode(3)\n"
+        "    acc, att = cfg.sweep(5, np.linspace(0.5, 8, R), np.full(R, 0.3))\n"
+        "    out.append(dict(acc=acc.tolist(), att=att.tolist(), E=(cfg.energies() / cfg.nSites).tolist()))\n"
+        "print(json.dumps(out))\n" % root)
+    res = {}
+    for m in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SCMC_MMA=m), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[m] = json.loads(r.stdout.strip().splitlines()[-1])
+    for a, b in zip(res["0"], res["1"]):
+        assert a["att"] == b["att"]
+        acc0, acc1 = np.array(a["acc"], dtype=float), np.array(b["acc"], dtype=float)
+        assert np.all(np.abs(acc0 - acc1) <= 2 + 1e-3 * acc0)              # a decision flips only on a near-tie
+        assert np.allclose(a["E"], b["E"], rtol=0, atol=2e-3)             # ... and a flipped decision moves E/N by O(1/N)
+
+
 def test_launch_writes_the_reference_result_files(scmc, tmp_path):
     """launch! ends in checkpoint! + saveMeans! (MonteCarlo.jl:103-104): one HDF5 file per temperature with `means/<key>/{mean,error}`,
     `rs`, `energy`, `σ`, `current_sweep`, `state` (d x N); getmeans / getenergies (IO.jl:64-143) collect them over the grid."""
