@@ -16,6 +16,7 @@ def arm(dense):
         rng = np.random.default_rng(7); A = rng.uniform(-1, 1, (16, 16)); Jm = 0.5 * (A + A.T); Jm[0, 0] = 0
     cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [Jm], L, 1, n_replicas=R, precision=32, seed=11)
     cfg.set_sweep_mode(3)                                   # streaming psi-gather
+    cfg.set_lanes(int(os.environ.get("AB_LANES", "0")))     # 0 auto (two replica lanes), 1 one stream
     T = np.tile(np.geomspace(0.02, 2.0, 64), R // 64); beta = 1 / T; sigma = np.clip(0.6 * np.sqrt(T), 0.02, 60)
     e0 = cfg.energies() / cfg.nSites
     acc, att = cfg.sweep(4, beta, sigma)
@@ -25,7 +26,7 @@ def arm(dense):
     for _ in range(4):
         cfg.sweep(10, beta, sigma, want_counts=False); n += 10
     torch.cuda.synchronize(); dt = (time.perf_counter() - t) / n
-    print(json.dumps(dict(mma=os.environ.get("SCMC_MMA", "0"), dense=dense, ms_per_sweep=1e3 * dt, updates_per_s=2 * L * L * R / dt,
+    print(json.dumps(dict(mma=os.environ.get("SCMC_MMA", "0"), lanes=os.environ.get("AB_LANES", "0"), dense=dense, ms_per_sweep=1e3 * dt, updates_per_s=2 * L * L * R / dt,
                           acc=int(acc.sum()), att=int(att.sum()), e0=float(e0.mean()), e1_mean=float(e1.mean()), e1=[float(x) for x in e1[:4]])), flush=True)
     cfg.close()
 
