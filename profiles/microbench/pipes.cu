@@ -16,6 +16,10 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, uint32_
     asm volatile("mov.b64 %0, {%1, %1};" : "=l"(mm) : "f"(m));
     asm volatile("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
     uint32_t x0 = threadIdx.x + seed, x1 = x0 * 3 + 1, x2 = x0 * 5 + 2, x3 = x0 * 7 + 3;
+    float h[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) h[i] = a0 + i;
+#pragma unroll 4
     for (int i = 0; i < ITERS; i++) {
         if (MODE == 0) {          // 8 FFMA
             a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
@@ -65,6 +69,18 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, uint32_
             x0 = t0 ^ x1; x1 = t1 ^ x2; x2 = t2 ^ x3; x3 = t3 ^ x0;
         } else if (MODE == 11) {  // 8 LOP3/IADD only (ALU pipe reference)
             x0 = (x0 ^ x1) + 0x9E3779B9u; x1 = (x1 ^ x2) + 0xBB67AE85u; x2 = (x2 ^ x3) + 0x9E3779B9u; x3 = (x3 ^ x0) + 0xBB67AE85u;
+        } else if (MODE == 12 || MODE == 13) {   // 4 independent legacy HMMA.1688.F32.TF32 (mma.sync m16n8k8), MODE 13: + 8 FFMA
+            uint32_t b0 = x0 & 0xffffe000u, b1 = x1 & 0xffffe000u;
+#define HMMA(d0, d1, d2, d3) asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+                : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b0), "r"(b1))
+            HMMA(h[0], h[1], h[2], h[3]); HMMA(h[4], h[5], h[6], h[7]); HMMA(h[8], h[9], h[10], h[11]); HMMA(h[12], h[13], h[14], h[15]);
+            if (MODE == 13) {
+                a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+                a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+            }
+        } else if (MODE == 14 || MODE == 15) {  // 4 DEPENDENT HMMAs (one accumulator): latency
+            uint32_t b0 = x0 & 0xffffe000u, b1 = x1 & 0xffffe000u;
+            HMMA(h[0], h[1], h[2], h[3]); HMMA(h[0], h[1], h[2], h[3]); HMMA(h[0], h[1], h[2], h[3]); HMMA(h[0], h[1], h[2], h[3]);
         } else if (MODE == 7) {   // 8 FFMA + 8 LOP3 (dual issue across pipes?)
             a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
             a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
@@ -72,18 +88,20 @@ template <int MODE> __global__ void __launch_bounds__(256) k(float* out, uint32_
         }
     }
     float lo, hi; float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += h[i];
     asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p0 ^ p1 ^ p2 ^ p3));
     out[blockIdx.x * blockDim.x + threadIdx.x] = s + lo + hi + (float)(x0 ^ x1 ^ x2 ^ x3);
 }
-template <int MODE> void run(const char* name, double ops_per_iter, float* out) {
-    const int blocks = 148 * 8;
+template <int MODE> void run(const char* name, double ops_per_iter, float* out, int threads = 256) {
+    const int blocks = threads == 256 ? 148 * 8 : 148;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k<MODE><<<blocks, 256>>>(out, 1); cudaDeviceSynchronize();
+    k<MODE><<<blocks, threads>>>(out, 1); cudaDeviceSynchronize();
     cudaEventRecord(e0);
-    for (int r = 0; r < 5; r++) k<MODE><<<blocks, 256>>>(out, r);
+    for (int r = 0; r < 5; r++) k<MODE><<<blocks, threads>>>(out, r);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    double warp_iters = 5.0 * blocks * 8 * ITERS;
+    double warp_iters = 5.0 * blocks * (threads / 32) * ITERS;
     double t = ms * 1e-3;
     printf("%-34s %8.3f ms  %7.2f warp-iters/ns  => %6.2f listed-ops per SM per clk @1.9GHz (x32 lanes)\n", name, ms, warp_iters / t * 1e-9,
            warp_iters * ops_per_iter / t / 148 / 1.9e9);
@@ -102,5 +120,9 @@ int main() {
     run<9>("4 IMAD.HI + 4 LOP", 8, out);
     run<10>("4 mul.wide.u16 + 4 LOP", 8, out);
     run<11>("4 LOP + 4 IADD", 8, out);
+    run<12>("4 HMMA.1688.TF32 (independent)", 4, out);
+    run<13>("4 HMMA.1688.TF32 + 8 FFMA", 12, out);
+    run<14>("4 HMMA.1688.TF32 (one chain)", 4, out);
+    run<15>("4 HMMA (one chain), 1 warp/SMSP", 4, out, 4 * 32);
     return 0;
 }
