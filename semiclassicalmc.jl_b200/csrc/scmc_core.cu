@@ -52,13 +52,16 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #define SCMC_SWEEP_BLOCKS_F64 3
 #endif
 #ifndef SCMC_SWEEP_BLOCKS_MMA
-#define SCMC_SWEEP_BLOCKS_MMA SCMC_SWEEP_BLOCKS     // the tensor-core mat-vec experiment (SCMC_MMA=1)
+#define SCMC_SWEEP_BLOCKS_MMA 8                     // the tensor-core mat-vec experiment (SCMC_MMA=1): 64 registers, no spills; measured best of 4 ... 9
 #endif
 #ifndef SCMC_SWEEP_BLOCKS_NL
 #define SCMC_SWEEP_BLOCKS_NL SCMC_SWEEP_BLOCKS      // FP32 instantiations with several coupling labels
 #endif
 #ifndef SCMC_SWEEP_PSI_BLOCKS_F64
 #define SCMC_SWEEP_PSI_BLOCKS_F64 4
+#endif
+#ifndef SCMC_GATHER6
+#define SCMC_GATHER6 0        // experiment: the FFMA psi-gather kernel with z = 6 issues all six neighbours' loads before the first density product
 #endif
 #ifndef SCMC_HIT_UNROLL2
 #define SCMC_HIT_UNROLL2 0
@@ -441,6 +444,25 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
 #pragma unroll
                 for (int t = 0; t < NP; t++) P[t] = R(0);
                 const int32_t* nb = M.cls_nbr + cp;
+                // all six neighbours in flight before the first density product (same summation order => same bits).  Pays only where registers
+                // allow it: the MMA variant (64 registers at 8 CTAs per SM, +4.7 %); the FFMA kernel spills at its 96-register cap (-1.4 %, SCMC_GATHER6=1)
+                if ((MMA || SCMC_GATHER6) && M.z == 6) {
+                    unsigned j[6];
+#pragma unroll
+                    for (int t = 0; t < 6; t++) j[t] = (unsigned)nb[(unsigned)t * stride];
+                    vec4<R> v[6][NPV];
+#pragma unroll
+                    for (int t = 0; t < 6; t++)
+#pragma unroll
+                        for (int q = 0; q < NPV; q++) v[t][q] = *reinterpret_cast<const vec4<R>*>(Pq[q] + (unsigned long long)j[t] * sizeof(vec4<R>));
+#pragma unroll
+                    for (int t = 0; t < 6; t++) {
+                        R nr[D], ni[D];
+#pragma unroll
+                        for (int q = 0; q < NPV; q++) { nr[2 * q] = v[t][q].x; ni[2 * q] = v[t][q].y; nr[2 * q + 1] = v[t][q].z; ni[2 * q + 1] = v[t][q].w; }
+                        GenOps<GEN>::density_acc(nr, ni, P);
+                    }
+                } else
 #pragma unroll 2
                 for (int k = 0; k < M.z; k += 3) {
                     unsigned j[3];
