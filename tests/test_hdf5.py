@@ -145,3 +145,14 @@ def test_result_files_and_post_processing(scmc, tmp_path):
     back = scmc.hdf5.read(str(tmp_path / "energies.h5"))
     assert sorted(back) == ["0.5", "1.0", "2.0", "3.0"] and np.array_equal(back["2.0"], np.arange(4.0) + 2) and np.array_equal(back["3.0"], [0.0])
     assert set(en) == set(back)
+
+
+def test_result_file_names_of_a_packed_launch(scmc):
+    """One file per chain: `filename(T)` as in notebook cell 22, or a path that gets the temperature (and the replica index when a
+    temperature occurs more than once); names that are not .h5 paths are labels for the log and write nothing."""
+    f = scmc.launcher.resultFilename
+    assert f("out/run.h5", 0.5, None, 1) == "out/run.h5"
+    assert f("out/run.h5", 0.5, None, 3) == "out/run_T0.5.h5" and f("out/run.h5", 0.02, 4, 8) == "out/run_T0.02_r4.h5"
+    assert f(lambda T: f"x{T}.h5", 2.0, None, 5) == "x2.0.h5"
+    w = scmc.launcher._writes_files
+    assert w("a.h5") and w("b.HDF5") and w(lambda T: "c") and not w("label") and not w(None)
