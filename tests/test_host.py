@@ -126,3 +126,25 @@ def test_tghbn_norms_vectorised_equals_reference_formulas(scmc):
     for key, comps in ob._TGHBN_SETS.items():
         assert np.allclose(got["subM" + key], np.linalg.norm(subM[:, comps, :], axis=1).mean(axis=1), rtol=1e-13, atol=0)
         assert np.allclose(got["m" + key], np.linalg.norm(m[:, comps], axis=1), rtol=1e-13, atol=0)
+
+
+def test_3xtf32_split_keeps_fp32_accuracy():
+    """Arithmetic of the SCMC_MMA experiment (csrc/scmc_core.cu: matvec_mma) restated in NumPy: operands split into a 19-bit TF32 head
+    (mask 0xffffe000) and the exactly representable tail, products a_lo.b_hi + a_hi.b_lo + a_hi.b_hi with the tensor core truncating the
+    tails to TF32 as well.  The 16x16 mat-vec then agrees with FP64 to a few 1e-7 relative -- FP32 class, well inside north_star's 1e-5 --
+    whereas plain TF32 (heads only) is three orders worse, which is why the kernel issues three MMAs per tile."""
+    rng = np.random.default_rng(12)
+
+    def head(x):
+        return (x.astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+    J = rng.uniform(-1, 1, (16, 16)).astype(np.float32)
+    P = rng.uniform(-3, 3, (16, 4096)).astype(np.float32)           # density sums of six neighbours
+    Jh, Ph = head(J), head(P)
+    Jl, Pl = head(J - Jh), head(P - Ph)                             # J - Jh is exact in FP32; the MMA reads its TF32 head
+    assert np.array_equal((J - Jh).astype(np.float64), J.astype(np.float64) - Jh.astype(np.float64))
+    exact = J.astype(np.float64) @ P.astype(np.float64)
+    three = (Jl.astype(np.float64) @ Ph + Jh.astype(np.float64) @ Pl + Jh.astype(np.float64) @ Ph).astype(np.float32)
+    one = (Jh.astype(np.float64) @ Ph).astype(np.float32)
+    scale = np.abs(J.astype(np.float64)) @ np.abs(P.astype(np.float64))
+    err3, err1 = np.max(np.abs(three - exact) / scale), np.max(np.abs(one - exact) / scale)
+    assert err3 < 5e-7 and err1 > 1e-4 and err1 < 2e-3
