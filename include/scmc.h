@@ -92,7 +92,9 @@ int32_t scmc_sweep(scmc_t* h, int64_t n_sweeps, int32_t hits, const double* beta
 int32_t scmc_sweep_async(scmc_t* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter);
 /* kernel selection for the stream-driven sweeps: 0 = auto; T-gather family (neighbours enter through the cached T vectors):
  * 1 = streaming colour-pass kernel, 2 = replica-resident cluster kernel; psi-gather family (neighbours enter through their
- * states via density-matrix sums, one coupling label only): 3 = streaming, 4 = replica-resident.  Kernels of one family produce
+ * states via density-matrix sums, one coupling label only): 3 = streaming with a per-thread gather, 4 = replica-resident,
+ * 5 = streaming, TMA-pipelined (cp.async.bulk + mbarrier ring; classes that do not decompose into bulk copies fall back to the
+ * gather of mode 3; this is what auto uses for streaming passes of the psi family).  Kernels of one family produce
  * bit-identical chains; the two families differ by rounding.  Auto picks the family from the model alone (never from the replica
  * count), so sharding replicas over GPUs cannot change a chain.  batch = replicas per batch for the streaming path (0 = all). */
 int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch);

@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscmc_b200.so")
-SOURCES = ["scmc_core.cu", "scmc_drivers.cu", "scmc_resident.cu"]
+SOURCES = ["scmc_core.cu", "scmc_drivers.cu", "scmc_resident.cu", "scmc_tma.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "-use_fast_math",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

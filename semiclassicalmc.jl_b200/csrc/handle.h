@@ -45,6 +45,25 @@ struct DevModel {
     Couplings<R, NL> cp;
 };
 
+// Arguments of one colour pass (streaming kernels of scmc_core.cu and scmc_tma.cu)
+struct SweepArgs {
+    int32_t colour, colour_last, hits;   // classes [colour, colour_last] are visited in order by ONE block per replica when colour_last > colour
+    int64_t r0, rcount;        // replica batch [r0, r0 + rcount)
+    uint64_t visit0, seed;     // visit number of hit 0 of this pass; stream key
+    int64_t roff;              // global replica id of replica 0
+    const void *beta, *sigma;  // [R] reals
+    const void* Jqt;           // [16][16] psi family with 16 density entries: transposed Jq = C^T J C, or nullptr
+    const void* Jt;            // [NL][16][16] transposed couplings Jt[l][b][a] = J_l^{ab} in the handle's precision (global)
+    const uint8_t* active;     // [R] or nullptr
+    unsigned long long* acc;   // [R]
+    // deterministic test mode (nullptr in production): injected randoms / recorded decisions, caller's site order
+    const double *inj_xi, *inj_u;
+    uint8_t* out_acc;
+    double* out_dE;
+    int32_t lab_major;            // several labels: label l owns neighbour slots [lab_off[l], lab_off[l+1]) at every site
+    int32_t lab_off[MAXL + 1];
+};
+
 }  // namespace scmc
 
 struct scmc_handle {
@@ -97,6 +116,17 @@ struct scmc_handle {
         int cta_col_off[16][scmc::MAXC + 1] = {{0}};   // local offsets of the colour classes inside a chunk
     } res;
     int64_t batch = 0;
+    // TMA-pipelined streaming psi-gather kernel (scmc_tma.cu): per colour class, the class positions are cut into tiles of <= 128 sites; the
+    // states a tile needs (its own sites and all their neighbours, each once) are a few runs of consecutive permuted indices, which one
+    // cp.async.bulk per run and plane brings into a shared-memory stage.  ok = 0: the class keeps the direct-gather kernel (seam classes).
+    struct TmaClass { int ok = 0, n_tiles = 0, tile = 0, first = 0; };
+    struct {
+        int ready = 0, cap = 0, max_runs = 0;        // cap: float4 slots per plane and stage (largest tile + the all-zero slot, multiple of 8)
+        TmaClass cls[scmc::MAXC];
+        void* d_meta = nullptr;                      // [tiles][128][2] uint4: stage slots of a thread's own site and neighbours, caller's site number, permuted index
+        void* d_runs = nullptr;                      // [tiles][TMA_MAX_RUNS] uint2: first permuted index, stage slot | length << 16
+        int32_t* d_tile = nullptr;                   // [tiles][4]: sites in the tile, runs, slots copied per plane, first class position
+    } tma;
     // replica lanes of the streaming path: the replicas of a call are split over side streams so that the tail of one lane's
     // colour pass overlaps with the other lane's next pass (colour passes of different replicas are independent)
     cudaStream_t lane_stream[2] = {nullptr, nullptr};
@@ -120,6 +150,11 @@ bool resident_preferred(const scmc_handle* h);      // the auto policy's cluster
 int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint64_t seed, double att_per_sweep, double min_accepted,
                                double beta_fac, double min_accrate, double sigma_min, int64_t n_per_T, int64_t n_total,
                                int64_t* d_sweeps_at_T, int64_t* d_sweeps_done, int* d_n_active);
+// implemented in scmc_tma.cu
+constexpr int TMA_TILE = 128, TMA_MAX_RUNS = 16, TMA_STAGES = 2, TMA_RC = 16;
+void plan_tma(scmc_handle* h, const std::vector<int32_t>& col_list, const std::vector<int32_t>& nb /* [z][N] permuted neighbour by permuted site */);
+bool tma_pass_available(const scmc_handle* h, const SweepArgs& A);
+int32_t launch_colour_pass_tma(scmc_handle* h, const SweepArgs& A, cudaStream_t stream);
 // implemented in scmc_resident.cu
 void plan_resident(scmc_handle* h, const std::vector<int>& owner_of_perm);
 int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter, const uint8_t* active, bool psi);

@@ -86,23 +86,7 @@ int32_t dev_alloc(scmc_handle* h, void** p, size_t bytes) {
 #define SCMC_SWEEP_TILES 16     // site tiles (of SCMC_SWEEP_THREADS sites) a block walks over
 #endif
 #define SCMC_MEASURE_THREADS 128
-struct SweepArgs {
-    int32_t colour, colour_last, hits;   // classes [colour, colour_last] are visited in order by ONE block per replica when colour_last > colour
-    int64_t r0, rcount;        // replica batch [r0, r0 + rcount)
-    uint64_t visit0, seed;     // visit number of hit 0 of this pass; stream key
-    int64_t roff;              // global replica id of replica 0
-    const void *beta, *sigma;  // [R] reals
-    const void* Jqt;           // [16][16] psi family with 16 density entries: transposed Jq = C^T J C, or nullptr
-    const void* Jt;            // [NL][16][16] transposed couplings Jt[l][b][a] = J_l^{ab} in the handle's precision (global)
-    const uint8_t* active;     // [R] or nullptr
-    unsigned long long* acc;   // [R]
-    // deterministic test mode (nullptr in production): injected randoms / recorded decisions, caller's site order
-    const double *inj_xi, *inj_u;
-    uint8_t* out_acc;
-    double* out_dE;
-    int32_t lab_major;            // several labels: label l owns neighbour slots [lab_off[l], lab_off[l+1]) at every site
-    int32_t lab_off[MAXL + 1];
-};
+// struct SweepArgs: see handle.h (shared with scmc_tma.cu)
 
 // S_l = sum of T_j over the neighbours with label l.  The neighbour table is padded to a multiple of 3 slots; padding slots
 // (and missing bonds) point at site N, whose T planes are identically zero, so the loop is branch-free and every chunk
@@ -1202,7 +1186,7 @@ int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma) 
 // Which arithmetic family the production (stream-driven) sweeps of this handle use.  It depends on the model only -- never on
 // the replica count or the number of sweeps per call -- so that a replica's chain is identical however replicas are sharded.
 bool uses_psi_gather(const scmc_handle* h) {
-    if (h->sweep_mode == 3 || h->sweep_mode == 4) return h->n_labels == 1;
+    if (h->sweep_mode == 3 || h->sweep_mode == 4 || h->sweep_mode == 5) return h->n_labels == 1;
     if (h->sweep_mode == 1 || h->sweep_mode == 2) return false;
     return h->n_labels == 1 && (h->d == 4 || h->onsite) && !h->res_family_T;      // measured: d = 6 without on-site term is on par / slightly faster with T-gather
 }
@@ -1261,6 +1245,10 @@ int32_t ensure_T(scmc_handle* h) {
 static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A, cudaStream_t stream, int lanes = 1) {
     const bool psi = !A.inj_xi && uses_psi_gather(h);
     if (!psi && stream == h->stream) SCMC_TRY(ensure_T(h));      // lanes: the caller refreshed T on h->stream before forking
+    // TMA-pipelined form of the psi-gather pass (scmc_tma.cu): bit-identical chains, used wherever the class decomposes into bulk copies;
+    // mode 3 keeps the direct-gather kernel (the reference point of the bit-identity tests)
+    if (psi && h->sweep_mode != 3 && !h->async_pipeline && !(getenv("SCMC_MMA") && atoi(getenv("SCMC_MMA")) != 0) && tma_pass_available(h, A))
+        return launch_colour_pass_tma(h, A, stream);
     return dispatch(h, [&](auto rt, auto gen, auto ons, auto nl) -> int32_t {
         using R = decltype(rt);
         constexpr int GEN = decltype(gen)::value, NL = decltype(nl)::value;
@@ -1719,6 +1707,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     C(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     if (ce != cudaSuccess) { scmc_destroy(h); return cuda_fail(ce, "scmc_create lanes", __FILE__, __LINE__); }
     plan_resident(h, owner_of_perm);     // neighbour codes, launch geometry, eligibility of the replica-resident kernel
+    plan_tma(h, col_list, nb);           // tiles, bulk-copy runs and stage slots of the TMA-pipelined streaming kernel
     *out = h;
     return SCMC_OK;
 }
@@ -1726,7 +1715,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
 int32_t scmc_destroy(scmc_t* h) {
     if (!h) return SCMC_OK;
     cudaSetDevice(h->device);
-    void* ptrs[] = {h->sf_acc, h->d_meas_partial, h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16, h->d_cls_site, h->d_cls_nbr};
+    void* ptrs[] = {h->sf_acc, h->d_meas_partial, h->psi, h->T, h->Tsq, h->nbr, h->lab, h->d_orig, h->beta, h->sigma, h->acc, h->active, h->obs, h->d_Jt, h->d_Jqt, h->d_col_list, h->d_nbr16, h->d_cls_site, h->d_cls_nbr, h->tma.d_meta, h->tma.d_runs, h->tma.d_tile};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < scmc_handle::N_SCRATCH; i++) if (h->scratch[i]) cudaFree(h->scratch[i]);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -1754,13 +1743,13 @@ int32_t scmc_set_lanes(scmc_t* h, int32_t lanes) {
 
 int32_t scmc_info(scmc_t* h, int64_t* info) {
     SCMC_ARG(h && info, "null argument");
-    info[0] = h->n_col; info[1] = h->gen_id; info[2] = h->bytes; info[3] = h->res.eligible | (h->res.eligible_psi << 1); info[4] = h->res.cs; info[5] = h->launches; info[6] = h->N; info[7] = h->R;
+    info[0] = h->n_col; info[1] = h->gen_id; info[2] = h->bytes; info[3] = h->res.eligible | (h->res.eligible_psi << 1) | (h->tma.ready << 2); info[4] = h->res.cs; info[5] = h->launches; info[6] = h->N; info[7] = h->R;
     return SCMC_OK;
 }
 
 int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch) {
     SCMC_ARG(h, "null handle");
-    SCMC_ARG(mode >= 0 && mode <= 4 && batch >= 0, "scmc_set_sweep_mode: bad mode / batch");
+    SCMC_ARG(mode >= 0 && mode <= 5 && batch >= 0, "scmc_set_sweep_mode: bad mode / batch");
     h->sweep_mode = mode; h->batch = batch;
     return SCMC_OK;
 }

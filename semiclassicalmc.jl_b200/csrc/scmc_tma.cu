@@ -1,0 +1,362 @@
+// scmc_tma.cu -- TMA-pipelined streaming colour pass of the psi-gather family (sm_100a).
+//
+// Replaces, for the production workload, the per-thread gather of k_sweep_colour_psi (scmc_core.cu): same arithmetic in the same order
+// (density sums over the neighbour slots 0..z-1, one 16x16 mat-vec with Jq, hits) => bit-identical chains; what changes is how the states
+// reach the SM.  Reference work unit: localUpdate! (src/MonteCarlo.jl:263-286) inside the 2N-update loops (src/MonteCarlo.jl:40-44, 76-80).
+//
+//   * scmc_create cuts every colour class into tiles of <= 128 class positions (plan_tma).  The states a tile needs -- its own sites and all
+//     their neighbours, each ONCE -- are a handful of runs of consecutive permuted indices on translation-invariant lattices (128x128
+//     triangular: 547 states in 5.4 runs per tile instead of 7 x 128 gathered states), found from the neighbour table alone.
+//   * one CTA owns ONE tile and walks over a chunk of replicas.  Per replica, one elected warp issues a cp.async.bulk (UBLKCP) per run and
+//     plane into a 2-stage shared-memory ring, completion on an mbarrier (SYNCS); the stage slots of a thread's own site and neighbours, its
+//     site number and its store address are loaded ONCE per CTA and stay in registers for all replicas, so a visit has no index load, no
+//     address arithmetic and no DRAM round trip in its dependent chain: the next replica's states land while this one's hits run.
+//   * classes whose tiles do not decompose into a few runs (the seam-repair classes of L % 3 != 0, irregular graphs) keep the direct gather.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+#include "handle.h"
+
+namespace scmc {
+
+#ifndef SCMC_TMA_BLOCKS
+#define SCMC_TMA_BLOCKS 5        // CTAs per SM the kernel is compiled for (128 threads each)
+#endif
+constexpr int TMA_GAP = 8;       // runs closer than this many unused states are merged into one copy
+
+// ------------------------------------------------------------------------------------------------ planning (host)
+void plan_tma(scmc_handle* h, const std::vector<int32_t>& col_list, const std::vector<int32_t>& nb) {
+    auto& P = h->tma;
+    P.ready = 0;
+    if (getenv("SCMC_TMA") && atoi(getenv("SCMC_TMA")) == 0) return;
+    if (h->n_labels != 1 || h->z > 6) return;
+    const int64_t N = h->N;
+    const int z = h->z;
+    struct Tile { int cnt, nruns, slots, cp0; std::vector<uint32_t> meta; std::vector<uint32_t> runs; };
+    std::vector<Tile> tiles;
+    int cap = 0, max_runs = 0;
+    std::vector<int32_t> loc_of(N + 1, -1);
+    for (int c = 0; c < h->n_col; c++) {
+        auto& C = P.cls[c];
+        C = {};
+        const int nc = h->col_off[c + 1] - h->col_off[c];
+        if (nc < 4 * TMA_TILE) continue;                              // small classes: the direct-gather kernel visits them in one launch
+        const int nt = (nc + TMA_TILE - 1) / TMA_TILE, ts = (nc + nt - 1) / nt;
+        std::vector<Tile> mine;
+        bool ok = true;
+        int cls_cap = 0, cls_runs = 0;
+        for (int t = 0; t < nt && ok; t++) {
+            const int cp0 = h->col_off[c] + t * ts, cnt = std::min(ts, h->col_off[c + 1] - cp0);
+            std::vector<int32_t> need;
+            need.reserve((size_t)cnt * (z + 1));
+            for (int i = 0; i < cnt; i++) {
+                const int32_t p = col_list[cp0 + i];
+                need.push_back(p);
+                for (int k = 0; k < z; k++) {
+                    const int32_t j = nb[(size_t)k * N + p];
+                    if (j < N) need.push_back(j);
+                }
+            }
+            std::sort(need.begin(), need.end());
+            need.erase(std::unique(need.begin(), need.end()), need.end());
+            Tile T;
+            T.cnt = cnt; T.cp0 = cp0; T.nruns = 0; T.slots = 0;
+            size_t i = 0;
+            while (i < need.size()) {
+                size_t j = i;
+                while (j + 1 < need.size() && need[j + 1] - need[j] <= TMA_GAP + 1) j++;
+                const int32_t start = need[i], len = need[j] - need[i] + 1;
+                if (len > 65535) { ok = false; break; }
+                T.runs.push_back((uint32_t)start);
+                T.runs.push_back((uint32_t)T.slots | ((uint32_t)len << 16));
+                for (size_t q = i; q <= j; q++) loc_of[need[q]] = T.slots + (need[q] - start);
+                T.slots += len; T.nruns++;
+                i = j + 1;
+            }
+            if (!ok || T.nruns > TMA_MAX_RUNS || T.slots + 1 > 4000) { ok = false; break; }
+            // average run must be long enough for the bulk copies to pay (irregular graphs: keep the gather)
+            if (T.slots < 16 * T.nruns) { ok = false; break; }
+            T.meta.assign((size_t)TMA_TILE * 8, 0);
+            for (int i2 = 0; i2 < TMA_TILE; i2++) {
+                uint32_t* m = &T.meta[(size_t)i2 * 8];
+                uint32_t loc[8] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu, 0};      // 0xFFFF = the all-zero slot
+                if (i2 < cnt) {
+                    const int32_t p = col_list[cp0 + i2];
+                    loc[0] = (uint32_t)loc_of[p];
+                    for (int k = 0; k < z; k++) {
+                        const int32_t j = nb[(size_t)k * N + p];
+                        if (j < N) loc[1 + k] = (uint32_t)loc_of[j];
+                    }
+                    loc[7] = 1;
+                    m[4] = (uint32_t)h->orig[p]; m[5] = (uint32_t)p;
+                }
+                for (int q = 0; q < 4; q++) m[q] = loc[2 * q] | (loc[2 * q + 1] << 16);
+            }
+            cls_cap = std::max(cls_cap, T.slots + 1);
+            cls_runs = std::max(cls_runs, T.nruns);
+            mine.push_back(std::move(T));
+        }
+        if (!ok) continue;
+        C.ok = 1; C.n_tiles = nt; C.tile = ts; C.first = (int)tiles.size();
+        cap = std::max(cap, cls_cap); max_runs = std::max(max_runs, cls_runs);
+        for (auto& T : mine) tiles.push_back(std::move(T));
+    }
+    if (tiles.empty()) return;
+    P.cap = (cap + 7) / 8 * 8;
+    P.max_runs = max_runs;
+    const size_t nt = tiles.size();
+    std::vector<uint32_t> meta(nt * TMA_TILE * 8), runs(nt * TMA_MAX_RUNS * 2, 0);
+    std::vector<int32_t> info(nt * 4);
+    for (size_t t = 0; t < nt; t++) {
+        memcpy(&meta[t * TMA_TILE * 8], tiles[t].meta.data(), sizeof(uint32_t) * TMA_TILE * 8);
+        memcpy(&runs[t * TMA_MAX_RUNS * 2], tiles[t].runs.data(), sizeof(uint32_t) * tiles[t].runs.size());
+        info[t * 4 + 0] = tiles[t].cnt; info[t * 4 + 1] = tiles[t].nruns; info[t * 4 + 2] = tiles[t].slots; info[t * 4 + 3] = tiles[t].cp0;
+    }
+    bool okd = cudaMalloc(&P.d_meta, meta.size() * 4) == cudaSuccess && cudaMalloc(&P.d_runs, runs.size() * 4) == cudaSuccess &&
+               cudaMalloc((void**)&P.d_tile, info.size() * 4) == cudaSuccess;
+    okd = okd && cudaMemcpy(P.d_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+          cudaMemcpy(P.d_runs, runs.data(), runs.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+          cudaMemcpy(P.d_tile, info.data(), info.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!okd) {
+        cudaGetLastError();
+        if (P.d_meta) cudaFree(P.d_meta);
+        if (P.d_runs) cudaFree(P.d_runs);
+        if (P.d_tile) cudaFree(P.d_tile);
+        P.d_meta = P.d_runs = nullptr; P.d_tile = nullptr;
+        return;
+    }
+    h->bytes += (int64_t)(meta.size() + runs.size() + info.size()) * 4;
+    P.ready = 1;
+}
+
+// ------------------------------------------------------------------------------------------------ mbarrier / bulk-copy primitives
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct TmaArgs {
+    const uint4* meta;       // [tiles][128][2]
+    const uint2* runs;       // [tiles][TMA_MAX_RUNS]
+    const int32_t* tile;     // [tiles][4]
+    int32_t first, cap, rc;  // first tile of the class, slots per plane and stage, replicas per CTA
+};
+
+// ------------------------------------------------------------------------------------------------ kernel
+template <class R, int GEN, int Z>
+__global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A, const TmaArgs T) {
+    constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
+    static_assert(NP == NG, "fused density basis (16 entries) only");
+    using V = vec4<R>;
+    constexpr uint32_t VB = sizeof(V);
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t plane_bytes = (uint32_t)T.cap * VB, stage_bytes = NPV * plane_bytes;
+    R* sJt = reinterpret_cast<R*>(smem + TMA_STAGES * stage_bytes);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sJt + NG * NG);      // full[0..S), empty[0..S)
+    int32_t* sRep = reinterpret_cast<int32_t*>(bars + 2 * TMA_STAGES);                    // replicas of this CTA that are alive
+    R* sBeta = reinterpret_cast<R*>(sRep + TMA_RC);
+    R* sSigma = sBeta + TMA_RC;
+    __shared__ int s_nit;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = T.first + blockIdx.x;
+    const int64_t rb = A.r0 + (int64_t)blockIdx.y * T.rc;
+    const int rcnt = (int)min((int64_t)T.rc, A.r0 + A.rcount - rb);
+
+    // per-thread constants of the tile: stage slots (as byte offsets) of the own site and the neighbours, site number, permuted index
+    const uint4 m0 = T.meta[((size_t)tile * TMA_TILE + tid) * 2], m1 = T.meta[((size_t)tile * TMA_TILE + tid) * 2 + 1];
+    const uint32_t zero_off = (uint32_t)(T.cap - 1) * VB;
+    uint32_t off[7];
+    {
+        const uint32_t w[4] = {m0.x, m0.y, m0.z, m0.w};
+#pragma unroll
+        for (int k = 0; k < 7; k++) {
+            const uint32_t l = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            off[k] = l == 0xFFFFu ? zero_off : l * VB;
+        }
+    }
+    const bool valid = (m0.w >> 16) != 0;
+    const uint32_t site = m1.x, p = m1.y;
+
+    for (int t = tid; t < NG * NG; t += TMA_TILE) sJt[t] = ((const R*)A.Jqt)[t];
+    if (tid < NPV * TMA_STAGES) {                                  // the all-zero slot of every plane of every stage (never a copy target)
+        V zv; zv.x = zv.y = zv.z = zv.w = R(0);
+        *reinterpret_cast<V*>(smem + tid * plane_bytes + zero_off) = zv;
+    }
+    if (warp == 0) {                                               // alive replicas of this chunk, in order
+        const bool al = lane < rcnt && (A.active == nullptr || A.active[rb + lane]);
+        const unsigned mask = __ballot_sync(0xffffffffu, al);
+        if (al) {
+            const int at = __popc(mask & ((1u << lane) - 1));
+            sRep[at] = lane;
+            sBeta[at] = ((const R*)A.beta)[rb + lane];
+            sSigma[at] = ((const R*)A.sigma)[rb + lane];
+        }
+        if (lane == 0) {
+            s_nit = __popc(mask);
+#pragma unroll
+            for (int s = 0; s < TMA_STAGES; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + TMA_STAGES + s), TMA_TILE / 32); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    const int n_it = s_nit;
+    const size_t ps = (size_t)M.nrep * M.Ns;
+
+    // copy descriptor of this lane (warp 0 issues): run = lane / NPV, plane = lane % NPV
+    const int nruns = T.tile[tile * 4 + 1];
+    const uint32_t tile_bytes = (uint32_t)T.tile[tile * 4 + 2] * VB * NPV;
+    const char* c_src = nullptr;
+    uint32_t c_dst = 0, c_bytes = 0;
+    if (warp == 0 && lane < nruns * NPV) {
+        const uint2 rd = T.runs[(size_t)tile * TMA_MAX_RUNS + lane / NPV];
+        const int v = lane % NPV;
+        c_src = reinterpret_cast<const char*>(M.psi + (size_t)v * ps + rb * M.Ns + rd.x);
+        c_dst = (uint32_t)v * plane_bytes + (rd.y & 0xFFFFu) * VB;
+        c_bytes = (rd.y >> 16) * VB;
+    }
+    const uint32_t smem0 = smem_u32(smem), bar0 = smem_u32(bars);
+    auto issue = [&](int it, int s) {
+        if (lane == 0) mbar_expect_tx(bar0 + 8 * s, tile_bytes);
+        __syncwarp();
+        if (c_bytes) bulk_g2s(smem0 + s * stage_bytes + c_dst, c_src + (size_t)sRep[it] * M.Ns * VB, c_bytes, bar0 + 8 * s);
+    };
+    if (warp == 0) {
+#pragma unroll
+        for (int s = 0; s < TMA_STAGES; s++)
+            if (s < n_it) issue(s, s);
+    }
+
+    for (int it = 0; it < n_it; it++) {
+        const int s = it % TMA_STAGES;
+        const uint32_t parity = (it / TMA_STAGES) & 1;
+        const int rl = sRep[it];
+        const int64_t r = rb + rl;
+        const R sigma = sSigma[it], nbeta = neg_beta_scaled(sBeta[it]);
+        mbar_wait(bar0 + 8 * s, parity);
+        const unsigned char* st = smem + s * stage_bytes;
+        R re[D], im[D], P[NP];
+#pragma unroll
+        for (int v = 0; v < NPV; v++) {
+            const V q = *reinterpret_cast<const V*>(st + v * plane_bytes + off[0]);
+            re[2 * v] = q.x; im[2 * v] = q.y; re[2 * v + 1] = q.z; im[2 * v + 1] = q.w;
+        }
+#pragma unroll
+        for (int t = 0; t < NP; t++) P[t] = R(0);
+#pragma unroll
+        for (int k = 0; k < Z; k++) {
+            R nr[D], ni[D];
+#pragma unroll
+            for (int v = 0; v < NPV; v++) {
+                const V q = *reinterpret_cast<const V*>(st + v * plane_bytes + off[1 + k]);
+                nr[2 * v] = q.x; ni[2 * v] = q.y; nr[2 * v + 1] = q.z; ni[2 * v + 1] = q.w;
+            }
+            GenOps<GEN>::density_acc(nr, ni, P);
+        }
+        // this warp is done with the stage: release it; warp 0 refills it with the states of replica it + STAGES once all warps have
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8 * (TMA_STAGES + s));
+        if (warp == 0 && it + TMA_STAGES < n_it) {
+            mbar_wait(bar0 + 8 * (TMA_STAGES + s), parity);
+            issue(it + TMA_STAGES, s);
+        }
+        R Hq[NG];
+        field_from_sums_smem<1>(sJt, (const R(*)[NG])P, Hq);       // Hq = Jq . Psum
+        R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
+        unsigned mine = 0;
+        for (int hit = 0; hit < A.hits; hit++) {
+            R xr[D], xi[D], u, dE;
+            stream_v1<R, D>(A.seed, site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+            mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+        }
+        if (!valid) mine = 0;
+        if (mine) store_psi<R, D>(M.psi + r * M.Ns + p, ps, re, im);
+        const unsigned tot = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launch
+template <class R>
+static DevModel<R, 1> make_model_t(const scmc_handle* h) {
+    DevModel<R, 1> M;
+    memset(&M, 0, sizeof M);
+    M.psi = (vec4<R>*)h->psi; M.T = (vec4<R>*)h->T; M.Tsq = (vec4<R>*)h->Tsq;
+    M.nbr = h->nbr; M.lab = h->lab; M.orig = h->d_orig; M.col_list = h->d_col_list; M.cls_site = h->d_cls_site; M.cls_nbr = h->d_cls_nbr;
+    M.N = (int32_t)h->N; M.Ns = (int32_t)h->Ns; M.z = h->z; M.n_col = h->n_col; M.nrep = h->R;
+    for (int c = 0; c <= MAXC; c++) M.col_off[c] = h->col_off[c];
+    for (int t = 0; t < 256; t++) M.cp.J[0][t] = (R)h->J[0][t];
+    for (int a = 0; a < NG; a++) M.cp.K[a] = (R)h->K[a];
+    return M;
+}
+
+static size_t tma_smem_bytes(const scmc_handle* h) {
+    const size_t VB = 4 * h->esz();
+    return (size_t)TMA_STAGES * (h->d / 2) * h->tma.cap * VB + 256 * h->esz() + 2 * TMA_STAGES * 8 + TMA_RC * (4 + 2 * h->esz()) + 16;
+}
+
+// The pipelined kernel serves FP32, d = 4 (n = 1, 3), one coupling label, no on-site term, z = 3 or 6 neighbour slots, single-class passes.
+bool tma_pass_available(const scmc_handle* h, const SweepArgs& A) {
+    if (!h->tma.ready || h->prec != 32 || !h->fused_density || h->onsite || (h->gen_id != 1 && h->gen_id != 3)) return false;
+    if (h->z != 3 && h->z != 6) return false;
+    if (A.colour_last != A.colour || A.inj_xi) return false;
+    if (tma_smem_bytes(h) > 200 * 1024) return false;
+    return h->tma.cls[A.colour].ok != 0;
+}
+
+template <int GEN, int Z>
+static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t stream) {
+    using R = float;
+    auto M = make_model_t<R>(h);
+    const auto& C = h->tma.cls[A.colour];
+    TmaArgs T;
+    T.meta = (const uint4*)h->tma.d_meta; T.runs = (const uint2*)h->tma.d_runs; T.tile = h->tma.d_tile;
+    T.first = C.first; T.cap = h->tma.cap;
+    // replicas per CTA: TMA_RC, fewer when that leaves the chip with less than a few waves of CTAs (small shards)
+    int rc = TMA_RC;
+    while (rc > 2 && (int64_t)C.n_tiles * ((A.rcount + rc - 1) / rc) < 3000) rc /= 2;
+    T.rc = rc;
+    const size_t smem = tma_smem_bytes(h);
+    static size_t attr_set[64] = {0};      // per device: largest dynamic shared-memory size opted into so far
+    if (attr_set[h->device & 63] < smem) {
+        SCMC_CK(cudaFuncSetAttribute(k_sweep_tma_psi<R, GEN, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[h->device & 63] = smem;
+    }
+    for (int64_t y0 = 0; y0 < A.rcount; y0 += (int64_t)65535 * rc) {
+        SweepArgs B = A;
+        B.r0 = A.r0 + y0; B.rcount = std::min<int64_t>((int64_t)65535 * rc, A.rcount - y0);
+        B.Jqt = h->d_Jqt; B.Jt = h->d_Jt;
+        const dim3 grid((unsigned)C.n_tiles, (unsigned)((B.rcount + rc - 1) / rc));
+        k_sweep_tma_psi<R, GEN, Z><<<grid, TMA_TILE, smem, stream>>>(M, B, T);
+        h->launches++;
+    }
+    SCMC_CK(cudaGetLastError());
+    h->T_stale = true;
+    return SCMC_OK;
+}
+
+int32_t launch_colour_pass_tma(scmc_handle* h, const SweepArgs& A, cudaStream_t stream) {
+    if (A.rcount == 0) return SCMC_OK;
+    if (h->gen_id == 1) return h->z == 6 ? launch_one<1, 6>(h, A, stream) : launch_one<1, 3>(h, A, stream);
+    return h->z == 6 ? launch_one<3, 6>(h, A, stream) : launch_one<3, 3>(h, A, stream);
+}
+
+}  // namespace scmc
