@@ -98,6 +98,11 @@ int32_t scmc_sweep_async(scmc_t* h, int64_t n_sweeps, int32_t hits, uint64_t see
  * bit-identical chains; the two families differ by rounding.  Auto picks the family from the model alone (never from the replica
  * count), so sharding replicas over GPUs cannot change a chain.  batch = replicas per batch for the streaming path (0 = all). */
 int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch);
+/* Random stream of the stream-driven sweeps (the chain definition; stands in for randn!(local_rng(), ...) and rand(),
+ * MonteCarlo.jl:255-256, 278): 1 (default) = Philox4x32-10, two calls and 24-bit Box-Muller pairs per update; 2 = Philox4x32-7, one call
+ * and 16-bit Box-Muller pairs per update, acceptance uniforms of four visits from one further call.  Both are pure functions of
+ * (seed, site, global replica, visit); a checkpoint must be resumed with the version it was written with.  scmc_randomize always uses 1. */
+int32_t scmc_set_stream_version(scmc_t* h, int32_t version);
 /* Replica lanes of the streaming kernels: 0 = auto (two lanes whenever a call is a chain of several launches), 1 = everything on
  * the handle's stream, 2 = the replicas of a call are split over two internal side streams that fork from / join into the
  * handle's stream, so the tail of one lane's colour pass is filled by the other lane's next pass.  Replicas never interact:

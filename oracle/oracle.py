@@ -41,7 +41,7 @@ def _lib(fast=False):
         lib.orc_energy.restype = C.c_double
         lib.orc_energy_difference.restype = C.c_double
         lib.orc_local_optimization.restype = C.c_double
-        for name in ("orc_sweeps_random", "orc_updates_injected", "orc_run_metropolis", "orc_run_annealing", "orc_sweeps_colour_v1"):
+        for name in ("orc_sweeps_random", "orc_updates_injected", "orc_run_metropolis", "orc_run_annealing", "orc_sweeps_colour_v1", "orc_sweeps_colour"):
             getattr(lib, name).restype = C.c_long
         lib.orc_local_update.restype = C.c_int
         _libs[fast] = lib
@@ -155,6 +155,20 @@ class Oracle:
                                             C.c_double(beta), C.c_double(sigma), C.c_uint64(seed), C.c_uint32(replica),
                                             C.c_uint64(sweep0), mask.ctypes.data_as(_up) if want_mask else None)
         return (acc, mask) if want_mask else acc
+
+    def sweeps_colour(self, version, n_sweeps, hits, colour, beta, sigma, seed, replica=0, sweep0=0, want_mask=False):
+        """Colour-ordered sweeps driven by random stream `version` (1 | 2): the product's chain definition, restated."""
+        colour = np.ascontiguousarray(colour, dtype=np.int32)
+        mask = np.zeros((n_sweeps, hits, self.N), dtype=np.uint8) if want_mask else None
+        acc = self.lib.orc_sweeps_colour(self.h, C.c_int(version), C.c_long(n_sweeps), C.c_int(hits), _i(colour), C.c_int(int(colour.max()) + 1),
+                                         C.c_double(beta), C.c_double(sigma), C.c_uint64(seed), C.c_uint32(replica),
+                                         C.c_uint64(sweep0), mask.ctypes.data_as(_up) if want_mask else None)
+        return (acc, mask) if want_mask else acc
+
+    def stream(self, version, seed, site, replica, visit):
+        xi = np.empty(2 * self.d); u = C.c_double()
+        self.lib.orc_stream(C.c_int(version), C.c_uint64(seed), C.c_uint32(site), C.c_uint32(replica), C.c_uint64(visit), C.c_int(self.d), _d(xi), C.byref(u))
+        return xi, u.value
 
     def stream_v1(self, seed, site, replica, visit):
         xi = np.empty(2 * self.d); u = C.c_double()

@@ -438,10 +438,48 @@ void orc_stream_v1(uint64_t seed, uint32_t site, uint32_t replica, uint64_t visi
     uint32_t x = (w[0] & 0xFFu) | ((w[2] & 0xFFu) << 8) | ((w[4] & 0xFFu) << 16) | ((w[6] & 0xFFu) << 24);
     *u = (double)x * (1.0 / 4294967296.0);
 }
+/* "stream v2" (DESIGN.md section 5), restated independently of the device code: Philox4x32-7; ONE call gives the d complex normals of an
+ * update for d <= 4 (two calls for d = 6): word m -> u1 = (2 (w >> 16) + 1) / 2^17, u2 = (w & 0xFFFF) / 2^16, Box-Muller; the acceptance
+ * uniform of visit v is word (v & 3) of one further call whose counter holds v >> 2 and the tag 8. */
+static void philox4x32_r(uint32_t c[4], uint32_t k0, uint32_t k1, int rounds) {
+    for (int r = 0; r < rounds; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+void orc_stream_v2(uint64_t seed, uint32_t site, uint32_t replica, uint64_t visit, int d, double *xi, double *u) {
+    uint32_t w[8]; int ncall = (d + 3) / 4;
+    for (int call = 0; call < ncall; call++) {
+        uint32_t c[4] = {site, replica, (uint32_t)visit, (uint32_t)((visit >> 32) << 4) | (uint32_t)call};
+        philox4x32_r(c, (uint32_t)seed, (uint32_t)(seed >> 32), 7);
+        memcpy(w + 4 * call, c, sizeof(c));
+    }
+    for (int m = 0; m < d; m++) {
+        double u1 = (double)((w[m] >> 15) | 1u) * (1.0 / 131072.0);
+        double u2 = (double)(w[m] & 0xFFFFu) * (1.0 / 65536.0);
+        double r = sqrt(-2.0 * log(u1)), a = 6.283185307179586476925 * u2;
+        xi[m] = r * cos(a); xi[d + m] = r * sin(a);
+    }
+    uint64_t g = visit >> 2;
+    uint32_t c[4] = {site, replica, (uint32_t)g, (uint32_t)((g >> 32) << 4) | 8u};
+    philox4x32_r(c, (uint32_t)seed, (uint32_t)(seed >> 32), 7);
+    *u = (double)c[visit & 3] * (1.0 / 4294967296.0);
+}
+void orc_stream(int version, uint64_t seed, uint32_t site, uint32_t replica, uint64_t visit, int d, double *xi, double *u) {
+    if (version == 2) orc_stream_v2(seed, site, replica, visit, d, xi, u); else orc_stream_v1(seed, site, replica, visit, d, xi, u);
+}
 /* Colour-ordered sweeps driven by stream v1 (the product's chain definition): for each sweep, colours in ascending order, every
  * site of the colour receives `hits` consecutive updates, visit = (sweep0 + s) * hits + hit.  site_ids = original site numbers. */
+long orc_sweeps_colour(orc_t *o, int version, long n_sweeps, int hits, const int *colour, int n_colours, double beta, double sigma,
+                       uint64_t seed, uint32_t replica, uint64_t sweep0, unsigned char *accept /* [n_sweeps][hits][N] or NULL */);
 long orc_sweeps_colour_v1(orc_t *o, long n_sweeps, int hits, const int *colour, int n_colours, double beta, double sigma,
                           uint64_t seed, uint32_t replica, uint64_t sweep0, unsigned char *accept /* [n_sweeps][hits][N] or NULL */) {
+    return orc_sweeps_colour(o, 1, n_sweeps, hits, colour, n_colours, beta, sigma, seed, replica, sweep0, accept);
+}
+long orc_sweeps_colour(orc_t *o, int version, long n_sweeps, int hits, const int *colour, int n_colours, double beta, double sigma,
+                       uint64_t seed, uint32_t replica, uint64_t sweep0, unsigned char *accept /* [n_sweeps][hits][N] or NULL */) {
     long acc = 0; double xi[16], u;
     for (long s = 0; s < n_sweeps; s++)
         for (int c = 0; c < n_colours; c++)
@@ -449,7 +487,7 @@ long orc_sweeps_colour_v1(orc_t *o, long n_sweeps, int hits, const int *colour, 
                 if (colour[i] != c) continue;
                 for (int hit = 0; hit < hits; hit++) {
                     uint64_t visit = (sweep0 + (uint64_t)s) * (uint64_t)hits + (uint64_t)hit;
-                    orc_stream_v1(seed, (uint32_t)i, replica, visit, o->d, xi, &u);
+                    orc_stream(version, seed, (uint32_t)i, replica, visit, o->d, xi, &u);
                     int a = orc_local_update(o, i, xi, u, beta, sigma, NULL);
                     if (accept) accept[((size_t)s * hits + hit) * o->N + i] = (unsigned char)a;
                     acc += a;

@@ -59,6 +59,7 @@ SIGNATURES = {
     "scmc_sweep": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, c_dp, c_dp, C.c_uint64, C.c_uint64, c_lp, c_lp]),
     "scmc_sweep_async": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64]),
     "scmc_set_sweep_mode": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64]),
+    "scmc_set_stream_version": (C.c_int32, [C.c_void_p, C.c_int32]),
     "scmc_set_lanes": (C.c_int32, [C.c_void_p, C.c_int32]),
     "scmc_measure": (C.c_int32, [C.c_void_p, c_dp]),
     "scmc_structure_factor": (C.c_int32, [C.c_void_p, c_dp, c_dp, C.c_int32, C.c_int32, C.c_double, c_dp]),

@@ -18,7 +18,7 @@ class Configuration:
     """struct Configuration (Configuration.jl:2-24) + constructor (Configuration.jl:27-77)."""
 
     def __init__(self, latticename, L, uc, interactions, onsiteInteraction, n, *, n_replicas=1, precision=64, device=0,
-                 replica_offset=0, seed=None, colour=None):
+                 replica_offset=0, seed=None, colour=None, stream=1):
         lat = getLatticePeriodic(uc, L)
         self.latticename, self.L, self.n = latticename, int(L), int(n)
         self.lattice = lat
@@ -54,6 +54,9 @@ class Configuration:
         self._h, self._lib = h, lib
         # random initial product state (Configuration.jl:62)
         _lib.check(lib.scmc_randomize(self._h, C.c_uint64(self.seed)))
+        self.stream = 1
+        if stream != 1:
+            self.set_stream_version(stream)
 
     # ---- lifetime
     def close(self):
@@ -119,6 +122,11 @@ class Configuration:
         """0 auto | 1 streaming T-gather | 2 resident T-gather | 3 streaming psi-gather, direct gather | 4 resident psi-gather |
         5 streaming psi-gather, TMA-pipelined where the class decomposes into bulk copies (include/scmc.h)."""
         _lib.check(self._lib.scmc_set_sweep_mode(self._h, mode, batch))
+
+    def set_stream_version(self, version=1):
+        """Random stream of the sweeps (include/scmc.h): 1 = Philox4x32-10 / 24-bit Box-Muller, 2 = Philox4x32-7 / 16-bit Box-Muller."""
+        _lib.check(self._lib.scmc_set_stream_version(self._h, int(version)))
+        self.stream = int(version)
 
     def set_lanes(self, lanes=0):
         """0 auto | 1 one stream | 2 two replica lanes on side streams (streaming kernels; chains unchanged)."""

@@ -69,9 +69,10 @@ __device__ __forceinline__ void mulhilo(uint32_t m, uint32_t x, uint32_t& hi, ui
     // one IMAD.WIDE.U32; written in PTX so the 64-bit product is split without extra carry/IADD3 instructions
     asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1, %0}, p;\n\t}" : "=r"(hi), "=r"(lo) : "r"(m), "r"(x));
 }
-__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+template <int ROUNDS>
+__device__ __forceinline__ void philox4x32(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int r = 0; r < 10; r++) {
+    for (int r = 0; r < ROUNDS; r++) {
         uint32_t hi0, lo0, hi1, lo1;
         mulhilo(0xD2511F53u, c0, hi0, lo0);
         mulhilo(0xCD9E8D57u, c2, hi1, lo1);
@@ -80,6 +81,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
+__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) { philox4x32<10>(c0, c1, c2, c3, k0, k1); }
 
 // math flavours: FP32 uses the SFU approximations (MUFU.LG2/SIN/COS/EX2/RSQ), FP64 the accurate library routines
 __device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& g0, float& g1) {
@@ -120,6 +122,62 @@ __device__ __forceinline__ void stream_v1(uint64_t seed, uint32_t site, uint32_t
     for (int m = 0; m < D; m++) box_muller(w[2 * m], w[2 * m + 1], xr[m], xi[m]);
     const uint32_t x = (w[0] & 0xFFu) | ((w[2] & 0xFFu) << 8) | ((w[4] & 0xFFu) << 16) | ((w[6] & 0xFFu) << 24);
     u = unit_uniform(x, R(0));
+}
+
+// "stream v2" (scmc_set_stream): fewer wide multiplies per update.  Philox4x32-7 (the Crush-resistant round count of
+// Salmon et al., SC'11) instead of -10; ONE call gives the four complex normals of an update (d = 4; two calls for d = 6): word m holds a
+// 16-bit radius index and a 16-bit angle, u1 = (2 k1 + 1) / 2^17 in (0, 1), u2 = k2 / 2^16; the acceptance uniforms of four consecutive
+// visits come from one further call (counter word 3 tagged 8), word visit & 3.  Same counter layout as v1 otherwise.
+__device__ __forceinline__ void box_muller16(uint32_t w, float& g0, float& g1) {
+    const float a = (float)((w >> 15) | 1u);                                  // 2 k1 + 1
+    const float ang = (float)(w & 0xFFFFu) * (6.283185307179586f * 1.52587890625e-05f);
+    const float r = sqrtf(fmaf(__log2f(a), -1.3862943611198906f, 17.0f * 1.3862943611198906f));      // sqrt(-2 ln(a / 2^17))
+    float s, c;
+    __sincosf(ang, &s, &c);
+    g0 = r * c; g1 = r * s;
+}
+__device__ __forceinline__ void box_muller16(uint32_t w, double& g0, double& g1) {
+    const double u1 = (double)((w >> 15) | 1u) * (1.0 / 131072.0);
+    const double u2 = (double)(w & 0xFFFFu) * (1.0 / 65536.0);
+    const double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    g0 = r * c; g1 = r * s;
+}
+template <class R, int D>
+__device__ __forceinline__ void stream_v2_normals(uint64_t seed, uint32_t site, uint32_t replica, uint64_t visit, R* xr, R* xi) {
+    constexpr int NCALL = (D + 3) / 4;
+    uint32_t w[4 * NCALL];
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const uint32_t vlo = (uint32_t)visit, vhi = (uint32_t)(visit >> 32) << 4;
+#pragma unroll
+    for (int call = 0; call < NCALL; call++) {
+        uint32_t c0 = site, c1 = replica, c2 = vlo, c3 = vhi | (uint32_t)call;
+        philox4x32<7>(c0, c1, c2, c3, k0, k1);
+        w[4 * call + 0] = c0; w[4 * call + 1] = c1; w[4 * call + 2] = c2; w[4 * call + 3] = c3;
+    }
+#pragma unroll
+    for (int m = 0; m < D; m++) box_muller16(w[m], xr[m], xi[m]);
+}
+// acceptance-uniform words of visits 4 g .. 4 g + 3
+__device__ __forceinline__ void stream_v2_uniform_words(uint64_t seed, uint32_t site, uint32_t replica, uint64_t group, uint32_t* w) {
+    uint32_t c0 = site, c1 = replica, c2 = (uint32_t)group, c3 = ((uint32_t)(group >> 32) << 4) | 8u;
+    philox4x32<7>(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
+__device__ __forceinline__ uint32_t pick_word(const uint32_t* w, uint32_t i) { return i == 0 ? w[0] : i == 1 ? w[1] : i == 2 ? w[2] : w[3]; }
+// one update's numbers as a pure function of (seed, site, replica, visit) -- the form the kernels without a cached uniform call use
+template <class R, int D>
+__device__ __forceinline__ void stream_v2(uint64_t seed, uint32_t site, uint32_t replica, uint64_t visit, R* xr, R* xi, R& u) {
+    stream_v2_normals<R, D>(seed, site, replica, visit, xr, xi);
+    uint32_t w[4];
+    stream_v2_uniform_words(seed, site, replica, visit >> 2, w);
+    u = unit_uniform(pick_word(w, (uint32_t)visit & 3u), R(0));
+}
+template <class R, int D>
+__device__ __forceinline__ void stream_any(int version, uint64_t seed, uint32_t site, uint32_t replica, uint64_t visit, R* xr, R* xi, R& u) {
+    if (version == 2) stream_v2<R, D>(seed, site, replica, visit, xr, xi, u);
+    else stream_v1<R, D>(seed, site, replica, visit, xr, xi, u);
 }
 
 // ------------------------------------------------------------------------------------------------ local field

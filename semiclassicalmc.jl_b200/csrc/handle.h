@@ -50,6 +50,7 @@ struct SweepArgs {
     int32_t colour, colour_last, hits;   // classes [colour, colour_last] are visited in order by ONE block per replica when colour_last > colour
     int64_t r0, rcount;        // replica batch [r0, r0 + rcount)
     uint64_t visit0, seed;     // visit number of hit 0 of this pass; stream key
+    int32_t stream;            // random stream version (1 | 2, device_core.cuh)
     int64_t roff;              // global replica id of replica 0
     const void *beta, *sigma;  // [R] reals
     const void* Jqt;           // [16][16] psi family with 16 density entries: transposed Jq = C^T J C, or nullptr
@@ -104,6 +105,7 @@ struct scmc_handle {
     size_t meas_partial_bytes = 0;
     void* pinned = nullptr;                      // pinned host staging for the beta / sigma tables
     int64_t bytes = 0, launches = 0;
+    int32_t stream_version = 1;                  // counter-based random stream of the sweeps: 1 = Philox4x32-10 / 24-bit Box-Muller, 2 = Philox4x32-7 / 16-bit (scmc_set_stream_version)
     int32_t sweep_mode = 0;                      // 0 auto, 1 streaming T-gather, 2 resident T-gather, 3 streaming psi-gather, 4 resident psi-gather
     bool res_family_T = false;                   // reserved: force the T-gather arithmetic family in auto mode
     bool T_stale = false;                        // psi-gather sweeps leave the T / Tsq planes behind; ensure_T() refreshes them on demand
@@ -151,7 +153,7 @@ int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint
                                double beta_fac, double min_accrate, double sigma_min, int64_t n_per_T, int64_t n_total,
                                int64_t* d_sweeps_at_T, int64_t* d_sweeps_done, int* d_n_active);
 // implemented in scmc_tma.cu
-constexpr int TMA_TILE = 128, TMA_MAX_RUNS = 16, TMA_STAGES = 2, TMA_RC = 16;
+constexpr int TMA_TILE = 128, TMA_MAX_RUNS = 16, TMA_STAGES = 2, TMA_RC = 16;   // TMA_RC: replicas one CTA walks over (<= 32)
 void plan_tma(scmc_handle* h, const std::vector<int32_t>& col_list, const std::vector<int32_t>& nb /* [z][N] permuted neighbour by permuted site */);
 bool tma_pass_available(const scmc_handle* h, const SweepArgs& A);
 int32_t launch_colour_pass_tma(scmc_handle* h, const SweepArgs& A, cudaStream_t stream);

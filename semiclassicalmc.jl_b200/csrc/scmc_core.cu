@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
                 for (int k = 0; k < D; k++) { xr[k] = (R)A.inj_xi[t * 2 * D + k]; xi[k] = (R)A.inj_xi[t * 2 * D + D + k]; }
                 u = (R)A.inj_u[t];
             } else {
-                stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+                stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
             }
             const bool ok = metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE);
             if (INJECT) {
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
                 R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
                 for (int hit = 0; hit < A.hits; hit++) {
                     R xr[D], xi[D], u, dE;
-                    stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+                    stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
                     mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
                 }
             } else {
@@ -499,15 +499,15 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
                 // two hits per iteration: both Philox / Box-Muller streams are independent of psi, so they interleave (ILP)
                 for (; hit + 1 < A.hits; hit += 2) {
                     R xr0[D], xi0[D], u0, xr1[D], xi1[D], u1, dE;
-                    stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr0, xi0, u0);
-                    stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit + 1, xr1, xi1, u1);
+                    stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr0, xi0, u0);
+                    stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit + 1, xr1, xi1, u1);
                     mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr0, xi0, u0, nbeta, sigma, eloc, dE) ? 1u : 0u;
                     mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr1, xi1, u1, nbeta, sigma, eloc, dE) ? 1u : 0u;
                 }
 #endif
                 for (; hit < A.hits; hit++) {
                     R xr[D], xi[D], u, dE;
-                    stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+                    stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
                     mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
                 }
             }
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
                 R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
                 for (int hit = 0; hit < A.hits; hit++) {
                     R xr[D], xi[D], u, dE;
-                    stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+                    stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
                     mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
                 }
             } else {
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, SCMC_SWEEP_BLOCKS) k_sweep
                 R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
                 for (int hit = 0; hit < A.hits; hit++) {
                     R xr[D], xi[D], u, dE;
-                    stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+                    stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
                     mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
                 }
             }
@@ -791,7 +791,7 @@ __global__ void __launch_bounds__(SCMC_ASYNC_THREADS, SCMC_ASYNC_BLOCKS) k_sweep
             unsigned mine = 0;
             for (int hit = 0; hit < A.hits; hit++) {
                 R xr[D], xi[D], u, dE;
-                stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+                stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
                 mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
             }
             if (mine) {
@@ -1369,7 +1369,7 @@ int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t s
                 SweepArgs A{};
                 A.colour = c; A.colour_last = c; A.hits = hits;
                 if (c >= first_small) { A.colour_last = h->n_col - 1; }
-                A.visit0 = (sweep_counter + (uint64_t)s) * (uint64_t)hits; A.seed = seed; A.roff = h->roff;
+                A.visit0 = (sweep_counter + (uint64_t)s) * (uint64_t)hits; A.seed = seed; A.roff = h->roff; A.stream = h->stream_version;
                 A.beta = h->beta; A.sigma = h->sigma; A.active = active; A.acc = h->acc;
                 for (int l = 0; l < lanes && status == SCMC_OK; l++) {
                     A.r0 = lane_r0[l]; A.rcount = lane_rc[l];
@@ -1747,6 +1747,13 @@ int32_t scmc_info(scmc_t* h, int64_t* info) {
     return SCMC_OK;
 }
 
+int32_t scmc_set_stream_version(scmc_t* h, int32_t version) {
+    SCMC_ARG(h, "null handle");
+    SCMC_ARG(version == 1 || version == 2, "scmc_set_stream_version: version must be 1 or 2");
+    h->stream_version = version;
+    return SCMC_OK;
+}
+
 int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch) {
     SCMC_ARG(h, "null handle");
     SCMC_ARG(mode >= 0 && mode <= 5 && batch >= 0, "scmc_set_sweep_mode: bad mode / batch");
@@ -1938,7 +1945,7 @@ int32_t scmc_sweep_deterministic(scmc_t* h, int32_t hits, const double* beta, co
     }
     for (int c = 0; c < h->n_col && st == SCMC_OK; c++) {
         SweepArgs A{};
-        A.colour = c; A.colour_last = c; A.hits = hits; A.r0 = 0; A.rcount = h->R; A.visit0 = 0; A.seed = 0; A.roff = h->roff;
+        A.colour = c; A.colour_last = c; A.hits = hits; A.r0 = 0; A.rcount = h->R; A.visit0 = 0; A.seed = 0; A.roff = h->roff; A.stream = 1;
         A.beta = h->beta; A.sigma = h->sigma; A.active = nullptr; A.acc = h->acc;
         A.inj_xi = dxi; A.inj_u = du; A.out_acc = dacc; A.out_dE = ddE;
         st = launch_colour_pass(h, A, h->stream);

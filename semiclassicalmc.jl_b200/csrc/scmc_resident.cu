@@ -24,6 +24,7 @@ struct ResidentArgs {
     int64_t nrep, roff;
     int32_t n_sweeps, hits, cs, n_own_max, cap, n_clusters;
     uint64_t visit0, seed;
+    int32_t stream;                 // random stream version (1 | 2)
     const void *beta, *sigma, *Jt, *Jqt;
     const uint8_t* active;
     unsigned long long* acc;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(512, 1) k_resident(const __grid_constant__ Dev
                     unsigned mine = 0;
                     for (int hit = 0; hit < A.hits; hit++) {
                         R xr[D], xi[D], u, dE;
-                        stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
+                        stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
                         mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
                     }
                     if (mine) {
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                         R eloc = local_energy<R, ONSITE>(T, Tsq, h, M.cp.K);
                         for (int hit = 0; hit < A.hits; hit++) {
                             R xr[D], xi[D], u, dE;
-                            stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
+                            stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
                             mine += metropolis_hit<R, GEN, ONSITE>(re, im, T, Tsq, h, M.cp.K, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
                         }
                     } else {
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(512, 1) k_resident_psi(const __grid_constant__
                         R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
                         for (int hit = 0; hit < A.hits; hit++) {
                             R xr[D], xi[D], u, dE;
-                            stream_v1<R, D>(A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
+                            stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), visit_base + hit, xr, xi, u);
                             mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
                         }
                     }
@@ -846,7 +847,7 @@ int32_t launch_resident(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t
         ResidentArgs A;
         memset(&A, 0, sizeof A);
         A.nrep = h->R; A.roff = h->roff; A.hits = hits; A.cs = P.cs; A.n_own_max = P.n_own_max; A.cap = P.cap;
-        A.seed = seed; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.Jqt = h->fused_density ? h->d_Jqt : nullptr; A.active = active; A.acc = h->acc; A.nbr16 = h->d_nbr16;
+        A.seed = seed; A.stream = h->stream_version; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.Jqt = h->fused_density ? h->d_Jqt : nullptr; A.active = active; A.acc = h->acc; A.nbr16 = h->d_nbr16;
         memcpy(A.cta_off, P.cta_off, sizeof A.cta_off);
         memcpy(A.cta_col_off, P.cta_col_off, sizeof A.cta_col_off);
         A.n_clusters = (int32_t)std::min<int64_t>(h->R, psi ? P.max_clusters_psi : P.max_clusters);
@@ -924,7 +925,7 @@ int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint
             ResidentArgs A;
             memset(&A, 0, sizeof A);
             A.nrep = h->R; A.roff = h->roff; A.hits = hits; A.cs = P.cs; A.n_own_max = P.n_own_max; A.cap = P.cap;
-            A.seed = seed; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.Jqt = h->fused_density ? h->d_Jqt : nullptr;
+            A.seed = seed; A.stream = h->stream_version; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.Jqt = h->fused_density ? h->d_Jqt : nullptr;
             A.active = h->active; A.acc = h->acc; A.nbr16 = h->d_nbr16;
             memcpy(A.cta_off, P.cta_off, sizeof A.cta_off);
             memcpy(A.cta_col_off, P.cta_col_off, sizeof A.cta_col_off);
@@ -953,7 +954,7 @@ int32_t launch_resident_run(scmc_handle* h, int mode, int64_t chunk, int32_t hit
             ResidentArgs A;
             memset(&A, 0, sizeof A);
             A.nrep = h->R; A.roff = h->roff; A.hits = hits; A.cs = P.cs; A.n_own_max = P.n_own_max; A.cap = P.cap;
-            A.seed = seed; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.Jqt = h->fused_density ? h->d_Jqt : nullptr;
+            A.seed = seed; A.stream = h->stream_version; A.beta = h->beta; A.sigma = h->sigma; A.Jt = h->d_Jt; A.Jqt = h->fused_density ? h->d_Jqt : nullptr;
             A.active = nullptr; A.acc = h->acc; A.nbr16 = h->d_nbr16;
             memcpy(A.cta_off, P.cta_off, sizeof A.cta_off);
             memcpy(A.cta_col_off, P.cta_col_off, sizeof A.cta_col_off);

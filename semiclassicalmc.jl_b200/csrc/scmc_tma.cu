@@ -161,7 +161,7 @@ struct TmaArgs {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <class R, int GEN, int Z>
+template <class R, int GEN, int Z, int STREAM>
 __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A, const TmaArgs T) {
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
     static_assert(NP == NG, "fused density basis (16 entries) only");
@@ -282,9 +282,17 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
         field_from_sums_smem<1>(sJt, (const R(*)[NG])P, Hq);       // Hq = Jq . Psum
         R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
         unsigned mine = 0;
+        uint32_t uw[4];                                            // stream v2: acceptance-uniform words of the current group of four visits
         for (int hit = 0; hit < A.hits; hit++) {
             R xr[D], xi[D], u, dE;
-            stream_v1<R, D>(A.seed, site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+            if constexpr (STREAM == 2) {
+                const uint64_t visit = A.visit0 + hit;
+                stream_v2_normals<R, D>(A.seed, site, (uint32_t)(A.roff + r), visit, xr, xi);
+                if (hit == 0 || ((uint32_t)visit & 3u) == 0) stream_v2_uniform_words(A.seed, site, (uint32_t)(A.roff + r), visit >> 2, uw);
+                u = unit_uniform(pick_word(uw, (uint32_t)visit & 3u), R(0));
+            } else {
+                stream_v1<R, D>(A.seed, site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+            }
             mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
         }
         if (!valid) mine = 0;
@@ -322,7 +330,7 @@ bool tma_pass_available(const scmc_handle* h, const SweepArgs& A) {
     return h->tma.cls[A.colour].ok != 0;
 }
 
-template <int GEN, int Z>
+template <int GEN, int Z, int STREAM>
 static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t stream) {
     using R = float;
     auto M = make_model_t<R>(h);
@@ -337,7 +345,7 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
     const size_t smem = tma_smem_bytes(h);
     static size_t attr_set[64] = {0};      // per device: largest dynamic shared-memory size opted into so far
     if (attr_set[h->device & 63] < smem) {
-        SCMC_CK(cudaFuncSetAttribute(k_sweep_tma_psi<R, GEN, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCMC_CK(cudaFuncSetAttribute(k_sweep_tma_psi<R, GEN, Z, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[h->device & 63] = smem;
     }
     for (int64_t y0 = 0; y0 < A.rcount; y0 += (int64_t)65535 * rc) {
@@ -345,7 +353,7 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
         B.r0 = A.r0 + y0; B.rcount = std::min<int64_t>((int64_t)65535 * rc, A.rcount - y0);
         B.Jqt = h->d_Jqt; B.Jt = h->d_Jt;
         const dim3 grid((unsigned)C.n_tiles, (unsigned)((B.rcount + rc - 1) / rc));
-        k_sweep_tma_psi<R, GEN, Z><<<grid, TMA_TILE, smem, stream>>>(M, B, T);
+        k_sweep_tma_psi<R, GEN, Z, STREAM><<<grid, TMA_TILE, smem, stream>>>(M, B, T);
         h->launches++;
     }
     SCMC_CK(cudaGetLastError());
@@ -355,8 +363,12 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
 
 int32_t launch_colour_pass_tma(scmc_handle* h, const SweepArgs& A, cudaStream_t stream) {
     if (A.rcount == 0) return SCMC_OK;
-    if (h->gen_id == 1) return h->z == 6 ? launch_one<1, 6>(h, A, stream) : launch_one<1, 3>(h, A, stream);
-    return h->z == 6 ? launch_one<3, 6>(h, A, stream) : launch_one<3, 3>(h, A, stream);
+    if (A.stream == 2) {
+        if (h->gen_id == 1) return h->z == 6 ? launch_one<1, 6, 2>(h, A, stream) : launch_one<1, 3, 2>(h, A, stream);
+        return h->z == 6 ? launch_one<3, 6, 2>(h, A, stream) : launch_one<3, 3, 2>(h, A, stream);
+    }
+    if (h->gen_id == 1) return h->z == 6 ? launch_one<1, 6, 1>(h, A, stream) : launch_one<1, 3, 1>(h, A, stream);
+    return h->z == 6 ? launch_one<3, 6, 1>(h, A, stream) : launch_one<3, 3, 1>(h, A, stream);
 }
 
 }  // namespace scmc

@@ -111,11 +111,18 @@ def test_sweep_deterministic_bit_exact_masks(scmc, oracle_mod, kind):
     assert n_ties == 0
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("stream", [1, 2])
 @pytest.mark.parametrize("kind", ["tri_notebook", "honey_n2_onsite"])
-def test_philox_chain_follows_oracle_fp64(scmc, oracle_mod, kind):
-    """Counter-based stream v1: the FP64 device chain equals the oracle's restatement of the same colour-ordered chain."""
+def test_philox_chain_follows_oracle_fp64(scmc, oracle_mod, kind, stream, mode):
+    """Counter-based streams v1 / v2: the FP64 device chain of EVERY sweep kernel (auto, streaming / resident T-gather, streaming /
+    resident psi-gather) equals the oracle's restatement of the same colour-ordered chain, step results included."""
     R, off, seed = 3, 40, 987654321
-    cfg = build(scmc, kind, 64, R=R, seed=seed, replica_offset=off)
+    cfg = build(scmc, kind, 64, R=R, seed=seed, replica_offset=off, stream=stream)
+    info = cfg.info()
+    if (mode == 2 and not info["resident"]) or (mode == 4 and not info["resident_psi"]):
+        pytest.skip("resident kernel of this family not available for the model")
+    cfg.set_sweep_mode(mode)
     for r in range(R):
         o = make_oracle(cfg, oracle_mod)
         o.randomize_v1(seed, off + r)
@@ -127,8 +134,8 @@ def test_philox_chain_follows_oracle_fp64(scmc, oracle_mod, kind):
     for r in range(R):
         o = make_oracle(cfg, oracle_mod)
         o.randomize_v1(seed, off + r)
-        a1 = o.sweeps_colour_v1(3, 2, cfg.colour, beta[r], sigma[r], seed, off + r, 0)
-        a2 = o.sweeps_colour_v1(2, 2, cfg.colour, beta[r], sigma[r], seed, off + r, 3)
+        a1 = o.sweeps_colour(stream, 3, 2, cfg.colour, beta[r], sigma[r], seed, off + r, 0)
+        a2 = o.sweeps_colour(stream, 2, 2, cfg.colour, beta[r], sigma[r], seed, off + r, 3)
         assert (acc1[r], acc2[r]) == (a1, a2)
         assert np.allclose(cfg.get_state(r, 1)[0], o.get_state(), atol=1e-10)
 
@@ -383,18 +390,23 @@ def test_device_side_annealing_equals_host_driven_loop(scmc, precision):
     assert len(set(ra["sweeps"].tolist())) > 1 or ra["sweeps"][0] == 699      # replicas stop independently (or all hit N_max)
 
 
+@pytest.mark.parametrize("mode,stream", [(0, 1), (1, 1), (2, 2), (3, 2), (4, 1), (0, 2)])
 @pytest.mark.parametrize("lattice,L", [("square", 5), ("cubic", 3), ("chain", 7), ("square", 4)])
-def test_other_lattices_follow_the_oracle_chain(scmc, oracle_mod, lattice, L):
+def test_other_lattices_follow_the_oracle_chain(scmc, oracle_mod, lattice, L, mode, stream):
     """Neighbour counts that are not a multiple of 3 (padding slots -> zero site), odd sizes (greedy colouring), 1-D and 3-D
-    lattices: energies and the FP64 counter-based chain against the oracle."""
+    lattices: energies and the FP64 counter-based chain of every sweep kernel against the oracle."""
     seed = 31415
-    cfg = scmc.initializeCfg("nearest-neighbor", lattice, [random_symmetric_J(5)], L, 1, n_replicas=2, precision=64, seed=seed, replica_offset=3)
+    cfg = scmc.initializeCfg("nearest-neighbor", lattice, [random_symmetric_J(5)], L, 1, n_replicas=2, precision=64, seed=seed, replica_offset=3, stream=stream)
+    info = cfg.info()
+    if (mode == 2 and not info["resident"]) or (mode == 4 and not info["resident_psi"]):
+        pytest.skip("resident kernel of this family not available for the model")
+    cfg.set_sweep_mode(mode)
     o = make_oracle(cfg, oracle_mod)
     o.randomize_v1(seed, 4)
     assert np.allclose(cfg.get_state(1, 1)[0], o.get_state(), atol=1e-13)
     assert abs(cfg.energies()[1] - o.energy()) < 1e-11 * cfg.nSites
     acc, _ = cfg.sweep(4, np.array([1.0, 3.0]), np.array([0.5, 0.3]))
-    a = o.sweeps_colour_v1(4, 2, cfg.colour, 3.0, 0.3, seed, 4, 0)
+    a = o.sweeps_colour(stream, 4, 2, cfg.colour, 3.0, 0.3, seed, 4, 0)
     assert acc[1] == a
     assert np.allclose(cfg.get_state(1, 1)[0], o.get_state(), atol=1e-10)
     assert abs(cfg.energies()[1] - o.energy()) < 1e-9 * cfg.nSites
@@ -760,11 +772,12 @@ def test_structure_factor_running_sum_on_the_device(scmc, lattice, L, n):
     ("honeycomb", 24, 21),       # z = 3
     ("square", 32, 18),          # z = 4, padded to 6 slots (zero-site neighbours)
 ])
-def test_tma_pipelined_kernel_is_bit_identical(scmc, case):
+@pytest.mark.parametrize("stream", [1, 2])
+def test_tma_pipelined_kernel_is_bit_identical(scmc, case, stream):
     """The TMA-pipelined streaming kernel (mode 5: cp.async.bulk + mbarrier ring, scmc_tma.cu) realises the chain of the direct-gather
     kernel (mode 3) bit for bit: same stream, same summation order.  Reference work unit: localUpdate!, MonteCarlo.jl:263-286."""
     lattice, L, R = case
-    mk = lambda: scmc.initializeCfg("nearest-neighbor", lattice, [NOTEBOOK_J], L, 1, n_replicas=R, precision=32, seed=4242, replica_offset=3)
+    mk = lambda: scmc.initializeCfg("nearest-neighbor", lattice, [NOTEBOOK_J], L, 1, n_replicas=R, precision=32, seed=4242, replica_offset=3, stream=stream)
     beta = np.geomspace(0.5, 50.0, R); sigma = np.geomspace(0.8, 0.03, R)
     a = mk(); a.set_sweep_mode(3)
     b = mk(); b.set_sweep_mode(5)
@@ -772,8 +785,9 @@ def test_tma_pipelined_kernel_is_bit_identical(scmc, case):
     for lanes in (1, 2):
         a.set_lanes(lanes); b.set_lanes(lanes)
         for k in (1, 3):
-            acc_a, att_a = a.sweep(k, beta, sigma, hits=2)
-            acc_b, att_b = b.sweep(k, beta, sigma, hits=2)
+            hits = 2 if k == 1 else 3                     # 3 hits per visit: a visit straddles two groups of the v2 acceptance uniforms
+            acc_a, att_a = a.sweep(k, beta, sigma, hits=hits)
+            acc_b, att_b = b.sweep(k, beta, sigma, hits=hits)
             assert np.array_equal(acc_a, acc_b) and np.array_equal(att_a, att_b)
             assert np.array_equal(a.get_state(), b.get_state())
     assert np.array_equal(a.energies(), b.energies())

@@ -159,3 +159,37 @@ def test_stream_v1_moments():
     assert abs(xs.mean()) < 0.02 and abs(xs.var() - 1) < 0.03 and abs(np.mean(xs ** 4) - 3) < 0.2
     assert abs(us.mean() - 0.5) < 0.02 and 0 <= us.min() and us.max() < 1
     assert abs(np.corrcoef(xs[:, 0], xs[:, 4])[0, 1]) < 0.05
+
+
+def test_stream_v2_moments_and_independence():
+    """Stream v2 (Philox4x32-7, one call per update, 16-bit Box-Muller pairs, shared acceptance-uniform call) as restated by the oracle:
+    N(0,1) normals up to the 6th moment, U[0,1) uniforms, no correlation between the components of an update, between consecutive
+    visits of a site, between neighbouring sites / replicas, or between the normals and the acceptance uniform of an update."""
+    o, _, _ = tri_oracle(3)
+    seed = 20230301
+    n = 20000
+    xs = np.empty((n, 8)); us = np.empty(n)
+    for v in range(n):
+        xs[v], us[v] = o.stream(2, seed, 5, 7, v)          # one site, one replica, consecutive visits
+    z = xs.ravel()
+    se = 1 / np.sqrt(z.size)
+    assert abs(z.mean()) < 5 * se and abs(z.var() - 1) < 5 * np.sqrt(2) * se
+    assert abs(np.mean(z ** 4) - 3) < 5 * np.sqrt(96) * se and abs(np.mean(z ** 6) - 15) < 5 * np.sqrt(10170) * se
+    assert np.abs(z).max() < 4.86 and np.abs(z).max() > 3.5      # 16-bit radius index: |xi| <= sqrt(2 ln 2^17) = 4.855
+    assert abs(us.mean() - 0.5) < 5 / np.sqrt(12 * n) and abs(us.var() - 1 / 12) < 0.003 and 0 <= us.min() and us.max() < 1
+    # Kolmogorov-Smirnov distance of the normals to the Gaussian CDF
+    from math import erf
+    zs = np.sort(z); cdf = 0.5 * (1 + np.vectorize(erf)(zs / np.sqrt(2)))
+    ks = np.max(np.abs(cdf - (np.arange(z.size) + 0.5) / z.size))
+    assert ks < 1.63 / np.sqrt(z.size)                      # 1 % critical value
+    c = np.corrcoef(np.column_stack([xs, us]).T)
+    assert np.abs(c - np.eye(9)).max() < 5 / np.sqrt(n)     # components of one update, incl. the uniform
+    assert abs(np.corrcoef(xs[:-1, 0], xs[1:, 0])[0, 1]) < 5 / np.sqrt(n)      # consecutive visits
+    assert abs(np.corrcoef(us[:-1], us[1:])[0, 1]) < 5 / np.sqrt(n)           # uniforms of one call (visits 4g .. 4g+3) and across calls
+    assert abs(np.corrcoef(us[0::4], us[1::4])[0, 1]) < 5 / np.sqrt(n / 4)
+    # neighbouring counters: site +- 1, replica +- 1, and the same counters under stream v1 (different generator, no common words)
+    a = np.array([o.stream(2, seed, 6, 7, v)[0] for v in range(4000)]); b = np.array([o.stream(2, seed, 5, 8, v)[0] for v in range(4000)])
+    for other in (a, b, np.array([o.stream(1, seed, 5, 7, v)[0] for v in range(4000)])):
+        assert abs(np.corrcoef(xs[:4000].ravel(), other.ravel())[0, 1]) < 5 / np.sqrt(32000)
+    # stream is a pure function of its counter
+    assert np.array_equal(o.stream(2, seed, 5, 7, 1234)[0], xs[1234]) and o.stream(2, seed, 5, 7, 1234)[1] == us[1234]
