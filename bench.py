@@ -44,10 +44,13 @@ def parse():
     ap.add_argument("--precision", type=int, default=32)
     ap.add_argument("--coupling", default="notebook", choices=["notebook", "dense"])
     ap.add_argument("--mode", type=int, default=0, help="0 auto, 1/2 streaming/resident T-gather, 3/4 streaming/resident psi-gather")
+    ap.add_argument("--stream", type=int, default=2, choices=[1, 2], help="random stream version (DESIGN.md section 5): 1 = Philox4x32-10, 2 = Philox4x32-7")
     ap.add_argument("--batch", type=int, default=0, help="replicas per L2 batch (streaming path)")
     ap.add_argument("--colouring", default="auto", choices=["auto", "few", "balanced"], help="few = 3 large + seam classes, balanced = 2x2 parity (4 equal classes)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-seconds", type=float, default=1.2, help="a step holds as many measurement intervals as it takes for the timed region to last this long")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-random-J figure in `extra`")
     ap.add_argument("--extra-hits", type=int, default=8, help="also report the throughput at this many updates per site visit (0 = skip)")
     return ap.parse_args()
 
@@ -124,7 +127,7 @@ class ClockSampler:
 _ORACLE_BUILT = False
 
 
-def cpu_reference_rate(L, J, target_seconds, sweeps=None):
+def cpu_reference_rate(L, J, target_seconds, sweeps=None, max_cores=None):
     """The reference's CPU path (C restatement, -O3 -march=native), one independent chain per host core (the reference's
     job-farm model, src/Launcher.jl:286-289) on a single C5 replica each.  Returns (updates/s, cores, sample description)."""
     from oracle import oracle as orc, lattice as ol
@@ -136,6 +139,8 @@ def cpu_reference_rate(L, J, target_seconds, sweeps=None):
         cores = len(os.sched_getaffinity(0))      # the cores this process may actually run on (cpu_count ignores affinity / cgroup masks)
     except AttributeError:
         cores = os.cpu_count() or 1
+    if max_cores:
+        cores = min(cores, max_cores)
     chains = []
     for c in range(cores):
         o = orc.Oracle(nbr, lab, J, np.zeros(16), 1, fast=True)
@@ -183,6 +188,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def kernel_source_hash():
+    """Hash of the sources the headline kernel is compiled from: an ncu traffic figure is only reported while it belongs to this code."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("scmc_tma.cu", "device_core.cuh", "gen_code.h", "handle.h"):
+        with open(os.path.join(ROOT, "semiclassicalmc.jl_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 # ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -209,7 +224,7 @@ def run_ours(args):
         from scmc_b200 import lattice as _pl
         colour = _pl.colourSites(_pl.getLatticePeriodic(_pl.getUnitcell("triangular"), args.L), prefer_few_passes=(args.colouring == "few"))
     cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [J], args.L, 1, n_replicas=R, precision=args.precision, device=local,
-                             seed=SEED, replica_offset=roff, colour=colour)
+                             seed=SEED, replica_offset=roff, colour=colour, stream=args.stream)
     cfg.set_sweep_mode(args.mode, args.batch)
     lib, h = cfg._lib, cfg._h
     N = cfg.nSites
@@ -226,19 +241,28 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from scmc_b200 import distributed as sdist
+    intervals = 1              # measurement intervals per step; raised below so that the timed region lasts >= ~1 s at every GPU count
+
     def device_step():
         nonlocal sweep_ctr
-        _lib.check(lib.scmc_sweep_async(h, args.sweeps, args.hits, C.c_uint64(SEED), C.c_uint64(sweep_ctr)))
-        sweep_ctr += args.sweeps
+        for _ in range(intervals):
+            _lib.check(lib.scmc_sweep_async(h, args.sweeps, args.hits, C.c_uint64(SEED), C.c_uint64(sweep_ctr)))
+            sweep_ctr += args.sweeps
 
     acc_h = np.zeros(R, dtype=np.int64); att_h = np.zeros(R, dtype=np.int64); obs_h = np.zeros((R, _lib.NOBS))
+    gathered = None
 
     def e2e_step():
-        nonlocal sweep_ctr
-        _lib.check(lib.scmc_sweep(h, args.sweeps, args.hits, _lib.dptr(beta), _lib.dptr(sigma), C.c_uint64(SEED), C.c_uint64(sweep_ctr),
-                                  _lib.lptr(acc_h), _lib.lptr(att_h)))
-        sweep_ctr += args.sweeps
-        _lib.check(lib.scmc_measure(h, _lib.dptr(obs_h)))
+        # what a user of the public API does per measurement interval: sweeps with host beta / sigma tables, measure! rows back on the
+        # host, and -- with several GPUs -- the all-gather of the per-replica rows over NCCL (the only collective of the path)
+        nonlocal sweep_ctr, gathered
+        for _ in range(intervals):
+            _lib.check(lib.scmc_sweep(h, args.sweeps, args.hits, _lib.dptr(beta), _lib.dptr(sigma), C.c_uint64(SEED), C.c_uint64(sweep_ctr),
+                                      _lib.lptr(acc_h), _lib.lptr(att_h)))
+            sweep_ctr += args.sweeps
+            _lib.check(lib.scmc_measure(h, _lib.dptr(obs_h)))
+            gathered = sdist.gather_replicas(obs_h, R_total) if world > 1 else obs_h
 
     # ---- device-resident timing
     sampler = ClockSampler(local) if rank == 0 else None       # started before the warm-up so nvidia-smi is already streaming
@@ -246,6 +270,13 @@ def run_ours(args):
     for _ in range(args.warmup):
         device_step()
     barrier()
+    # size the step: one more interval, timed, decides how many intervals a step holds (same number on every rank)
+    tp = time.perf_counter(); device_step(); barrier(); t_one = time.perf_counter() - tp
+    if world > 1:
+        tt = torch.tensor([t_one], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_one = float(tt[0])
+    intervals = max(1, int(np.ceil(args.min_seconds / max(1e-6, t_one * args.steps))))
     l0 = cfg.info()["launches"]
     t_wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -285,7 +316,7 @@ def run_ours(args):
             sweep_ctr += args.sweeps
         extra_step(); barrier()
         x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_extra = max(2, args.steps // 3)
+        n_extra = max(2, args.steps * intervals // 3)
         x0.record()
         for _ in range(n_extra):
             extra_step()
@@ -296,7 +327,37 @@ def run_ours(args):
             dist.all_reduce(tx, op=dist.ReduceOp.MAX)
             ms_x = float(tx[0])
         extra = {"hits_per_visit": args.extra_hits, "value": R_total * N * args.extra_hits * args.sweeps * n_extra / (ms_x * 1e-3), "unit": "site-updates/s"}
-    total_updates = R_total * N * args.hits * args.sweeps * args.steps
+    info = cfg.info()
+    # survey 8(d)(ii): the same workload with a dense random symmetric J (no structure to exploit) -- couplings are always applied as dense 16x16
+    if not args.no_dense and args.coupling == "notebook":
+        cfg.close()
+        cfg2 = scmc.initializeCfg("nearest-neighbor", "triangular", [couplings("dense")], args.L, 1, n_replicas=R, precision=args.precision, device=local,
+                                  seed=SEED, replica_offset=roff, colour=colour, stream=args.stream)
+        cfg2.set_sweep_mode(args.mode, args.batch)
+        th2 = scmc.run_(cfg2, None, Ts, np.full(R, 2.0), 48, 0, measurement_rate=2, hits=args.hits, keep_series=False)
+        ctr2 = cfg2.sweep_counter
+        def dense_step():
+            nonlocal ctr2
+            for _ in range(intervals):
+                _lib.check(lib.scmc_sweep_async(cfg2._h, args.sweeps, args.hits, C.c_uint64(SEED), C.c_uint64(ctr2)))
+                ctr2 += args.sweeps
+        dense_step(); barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_dense = max(2, args.steps // 3)
+        d0.record()
+        for _ in range(n_dense):
+            dense_step()
+        d1.record(); barrier()
+        ms_d = d0.elapsed_time(d1)
+        if world > 1:
+            td = torch.tensor([ms_d], device="cuda", dtype=torch.float64)
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            ms_d = float(td[0])
+        extra = dict(extra or {})
+        extra["dense_random_J"] = {"value": R_total * N * args.hits * args.sweeps * intervals * n_dense / (ms_d * 1e-3), "unit": "site-updates/s",
+                                   "note": "same workload, dense random symmetric 16x16 J (J[0,0] = 0), device-resident"}
+        cfg2.close()
+    total_updates = R_total * N * args.hits * args.sweeps * intervals * args.steps
     value = total_updates / (ms * 1e-3)
     e2e_value = total_updates / (ms_e2e * 1e-3)
     acc_rate = float(acc_h.sum() / max(1, att_h.sum()))
@@ -308,43 +369,53 @@ def run_ours(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         d, w = cfg.d, args.precision // 8
-        info = cfg.info()
         n_launch_local = max(1, launches // world)
         psi_family = args.mode in (3, 4) or (args.mode == 0 and cfg.d == 4)
         small = 1 <= info["cluster"] <= 2 and (args.sweeps >= 4 or R * N / info["n_colours"] < 300000)
         uses_resident = args.mode in (2, 4) or (args.mode == 0 and small and (info["resident_psi"] if psi_family else info["resident"]))
-        kernel_name = (f"replica-resident cluster({info['cluster']})" if uses_resident else "streaming colour-pass") + (", psi-gather" if psi_family else ", T-gather")
+        uses_tma = (not uses_resident) and psi_family and info.get("tma") and args.mode in (0, 5) and args.precision == 32
+        kernel_name = (f"replica-resident cluster({info['cluster']})" if uses_resident else "streaming colour-pass") + (", psi-gather" if psi_family else ", T-gather") + \
+                      (", TMA-pipelined (cp.async.bulk + mbarrier ring; seam classes: direct gather)" if uses_tma else "")
         # algorithmic bytes per kernel launch: state in + state out (4 d w bytes) of every site the launch visits
-        sites_per_launch = R * N * args.sweeps * args.steps / n_launch_local
+        sites_per_launch = R * N * args.sweeps * intervals * args.steps / n_launch_local
         alg_bytes = sites_per_launch * 4 * d * w
         launch_s = (ms * 1e-3) / n_launch_local
         achieved = alg_bytes / launch_s / 1e9
-        traffic = None
+        # DRAM bytes of one launch from the committed ncu capture -- only while that capture belongs to the kernel sources of this tree
+        traffic, traffic_src = None, None
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            if not uses_resident and psi_family and args.precision == 32 and args.L == 128:      # the configuration the ncu capture was taken on
+            same_config = uses_tma and args.L == 128 and args.stream == prof.get("stream") and args.hits == prof.get("hits_per_visit")
+            if same_config and prof.get("kernel_source_hash") == kernel_source_hash():
                 traffic = prof["dram_bytes_per_site_visit"] * sites_per_launch
+                traffic_src = f"{prof['source']} @ git {prof.get('git_sha')}, kernel sources {prof.get('kernel_source_hash')}"
+            else:
+                traffic_src = "dropped: the ncu capture in profiles/traffic.json was taken on other kernel sources or another configuration"
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": "site-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
                 "config": {"workload": f"C5: triangular {args.L}x{args.L} n=1, {R_total} replicas (64 T in [0.02,2] x copies), {args.coupling} J applied dense 16x16, "
-                                       f"{args.sweeps} sweep(s)/step x {args.hits} hits/site-visit, {info['n_colours']}-colour schedule",
-                           "replicas_per_gpu": R, "sites": N, "hits_per_visit": args.hits, "sweeps_per_step": args.sweeps,
+                                       f"{intervals} measurement interval(s)/step x {args.sweeps} sweeps x {args.hits} hits/site-visit, {info['n_colours']}-colour schedule, "
+                                       f"random stream v{args.stream}",
+                           "replicas_per_gpu": R, "sites": N, "hits_per_visit": args.hits, "sweeps_per_step": args.sweeps * intervals, "intervals_per_step": intervals, "stream": args.stream,
                            "kernel": kernel_name,
                            "cache_note": f"state {info['device_bytes'] / 2**30:.1f} GiB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
                            "acceptance_rate": acc_rate, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "updates_per_site_per_launch": args.hits, "launch_us": launch_s * 1e6,
-                             "note": "issue/FMA-pipe bound, not HBM bound: ncu (profiles/r01_ncu_full_k_sweep_colour_psi.txt) shows 67 % issue-slot "
-                                     "utilisation, 55 % FMA pipe, DRAM 2.3 TB/s, ~1150-1270 warp-instructions per site visit"},
-                "e2e": {"value": e2e_value, "unit": "site-updates/s", "h2d_bytes_per_step": int(2 * R * w) * world,
-                        "d2h_bytes_per_step": int(R * 8 + R * _lib.NOBS * 8) * world, "ms_per_step": ms_e2e / args.steps},
+                             "note": "issue / FMA-pipe bound, not HBM bound: see profiles/README.md (round 2) for the ncu summary of this kernel"},
+                "e2e": {"value": e2e_value, "unit": "site-updates/s", "h2d_bytes_per_step": int(2 * R * 8) * world * intervals,      # beta and sigma cross the ABI as FP64 tables
+                        "d2h_bytes_per_step": int(2 * R * 8 + R * _lib.NOBS * 8) * world * intervals, "ms_per_step": ms_e2e / args.steps,
+                        "collective": (f"all_gather of the {_lib.NOBS}-value measure! rows of all {R_total} replicas over NCCL, once per interval" if world > 1 else None)},
                 "gpu_launches": launches, "clocks": clocks, "extra": extra}
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, sample = cpu_reference_rate(args.L, J, args.cpu_seconds)
-            line["cpu_baseline"] = {"value": rate, "unit": "site-updates/s", "cores": cores, "kind": "port", "sample": sample}
+            rate1, _, sample1 = cpu_reference_rate(args.L, J, min(4.0, args.cpu_seconds), max_cores=1)
+            line["cpu_baseline"] = {"value": rate, "unit": "site-updates/s", "cores": cores, "kind": "port", "sample": sample,
+                                    "single_core": {"value": rate1, "unit": "site-updates/s", "cores": 1, "sample": sample1,
+                                                    "note": "the reference's own execution model: one chain, one thread (no threaded code in src/)"}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

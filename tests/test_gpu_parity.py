@@ -175,11 +175,12 @@ def test_invariants_after_sweeps(scmc, precision):
     assert acc_cold[3] > 0 and cfg.energies()[3] <= E1[3] + 1e-6 * abs(E1[3])
 
 
-def test_thermal_statistics_match_reference_chain(scmc, oracle_mod):
-    """BASELINE config C1 (su(4) Heisenberg, honeycomb 6x6, T = 0.1): FP32 colour-ordered device chains vs the oracle's
-    sequential random-site chain.  Different chains, same stationary distribution: e and c agree within error bars."""
+@pytest.mark.parametrize("stream", [1, 2])
+def test_thermal_statistics_match_reference_chain(scmc, oracle_mod, stream):
+    """BASELINE config C1 (su(4) Heisenberg, honeycomb 6x6, T = 0.1): FP32 colour-ordered device chains (random stream v1 and v2) vs
+    the oracle's sequential random-site chain.  Different chains, same stationary distribution: e and c agree within error bars."""
     R = 48
-    cfg = build(scmc, "honey_heis", 32, R=R, seed=31337)
+    cfg = build(scmc, "honey_heis", 32, R=R, seed=31337, stream=stream)
     res = scmc.run_(cfg, None, 0.1, 1.0, 2000, 6000, measurement_rate=10)
     ser = res["series"]                                      # [rows, R, 21]
     e_rep = ser[:, :, 0].mean(axis=0)
@@ -199,10 +200,11 @@ def test_thermal_statistics_match_reference_chain(scmc, oracle_mod):
     assert np.all(np.abs(res["acc_rate"] - 0.5) < 0.1)      # sigma adapted towards 50 % (MonteCarlo.jl:47-54)
 
 
-def test_notebook_observables_on_device(scmc, golden):
+@pytest.mark.parametrize("stream", [1, 2])
+def test_notebook_observables_on_device(scmc, golden, stream):
     """doc/examples.ipynb cell 13 (triangular L = 6, T = 0.02): e = -3.540997(91), |m_sigma| = 0.993221(8), |m_tau| = 0.02001(13)."""
     R = 32
-    cfg = build(scmc, "tri_notebook", 32, R=R, seed=2023)
+    cfg = build(scmc, "tri_notebook", 32, R=R, seed=2023, stream=stream)
     res = scmc.run_(cfg, None, 0.02, 1.0, 4000, 8000, measurement_rate=10)
     m = res["mean"]
     e = m[:, 0]
