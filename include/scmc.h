@@ -151,9 +151,10 @@ typedef struct {
     int64_t n_measure;          /* N_measure */
     int64_t measurement_rate;   /* default 10 */
     int32_t hits;               /* updates per site visit; 2 reproduces the reference's 2N updates per sweep */
-    int32_t reserved;
+    int32_t stop_sweep;         /* 0 = run to the end; else return after this sweep (a multiple of measurement_rate): the caller writes its
+                                 * checkpoint_rate files (MonteCarlo.jl:56-59, 88-91) and continues with sweep0 = stop_sweep */
     uint64_t seed;
-    uint64_t sweep0;            /* current_sweep (resume) */
+    uint64_t sweep0;            /* current_sweep (resume): sweeps sweep0 + 1 ... are run */
     const double* T;            /* [R] target temperatures */
     const double* T_i;          /* [R] initial temperatures of the thermalisation ramp */
     double* sigma;              /* [R] in/out cone widths (default 60.0) */

@@ -191,14 +191,25 @@ class Oracle:
         self.lib.orc_correlations(self.h, _i(project), C.c_int(n_rs), _d(Cm))
         return Cm
 
-    def run_metropolis(self, T, T_i, N_therm, N_measure, measurement_rate=10, sigma=60.0):
+    def set_normal_scale(self, s):
+        """Standard deviation of the proposal normals of the oracle's own chain (1 = N(0,1)); for the sigma-convention experiment."""
+        self.lib.orc_set_normal_scale(self.h, C.c_double(s))
+
+    def run_metropolis(self, T, T_i, N_therm, N_measure, measurement_rate=10, sigma=60.0, sigma_trace=False):
+        if sigma_trace:
+            self._sigma_log = np.zeros(N_therm // measurement_rate + 2)
+            self.lib.orc_set_sigma_log(self.h, _d(self._sigma_log), C.c_long(self._sigma_log.size))
         rows = N_measure // measurement_rate + 2
         series = np.zeros((rows, 21)); s = C.c_double(sigma); accr = C.c_double()
         nlog = (N_therm + N_measure) // measurement_rate + 2
         elog = np.zeros(nlog); blog = np.zeros(nlog)
         n = self.lib.orc_run_metropolis(self.h, C.c_double(T), C.c_double(T_i), C.c_long(N_therm), C.c_long(N_measure),
                                         C.c_long(measurement_rate), C.byref(s), _d(series), _d(elog), _d(blog), C.byref(accr))
-        return dict(series=series[:n], sigma=s.value, acc_rate=accr.value, energy_log=elog, beta_log=blog)
+        out = dict(series=series[:n], sigma=s.value, acc_rate=accr.value, energy_log=elog, beta_log=blog)
+        if sigma_trace:
+            self.lib.orc_set_sigma_log(self.h, None, C.c_long(0))
+            out["sigma_trace"] = self._sigma_log[:N_therm // measurement_rate].copy()      # cone width after the adaptation at sweep rate, 2 rate, ...
+        return out
 
     def run_annealing(self, T_i, T_fac=0.98, N_max=10_000_000, N_o=0, N_per_T=10000, min_acc_per_site=100, min_accrate=1e-5,
                       sigma_min=0.05, sigma=60.0, trace_cap=0):

@@ -38,6 +38,8 @@ typedef struct {
     double *nre, *nim;                   /* proposed state      (Configuration.jl:23) */
     uint64_t s[4];   /* xoshiro256++ state for the reference-shaped random-site chain */
     int have_spare; double spare;
+    double nscale;   /* standard deviation of the proposal normals (1 = N(0,1) as randn! documents; experiments: orc_set_normal_scale) */
+    double *sigma_log; long sigma_log_cap; /* optional: cone width after every adaptation of orc_run_metropolis */
 } orc_t;
 
 /* ------------------------------------------------------------------ RNG (oracle's own chain) */
@@ -58,9 +60,12 @@ static double nrand(orc_t *o) {
     if (o->have_spare) { o->have_spare = 0; return o->spare; }
     double u1 = 1.0 - urand(o), u2 = urand(o);
     double r = sqrt(-2.0 * log(u1)), a = 6.283185307179586476925 * u2;
-    o->spare = r * sin(a); o->have_spare = 1;
-    return r * cos(a);
+    o->spare = o->nscale * r * sin(a); o->have_spare = 1;
+    return o->nscale * r * cos(a);
 }
+/* experiments on the reference's sigma convention (tests/test_oracle_physics.py): normals of standard deviation s; sigma trace */
+void orc_set_normal_scale(orc_t *o, double s) { o->nscale = s; o->have_spare = 0; }
+void orc_set_sigma_log(orc_t *o, double *buf, long cap) { o->sigma_log = buf; o->sigma_log_cap = cap; }
 void orc_seed(orc_t *o, uint64_t seed) {
     for (int i = 0; i < 4; i++) o->s[i] = splitmix(&seed);
     o->have_spare = 0;
@@ -118,6 +123,7 @@ orc_t *orc_create(int N, int d, int z, int n_labels, const int *nbr, const int *
     o->re = (double *)calloc((size_t)N * d, sizeof(double)); o->im = (double *)calloc((size_t)N * d, sizeof(double));
     o->T = (double *)calloc((size_t)N * NG, sizeof(double)); o->Tsq = (double *)calloc((size_t)N * NG, sizeof(double));
     o->nre = (double *)calloc(d, sizeof(double)); o->nim = (double *)calloc(d, sizeof(double));
+    o->nscale = 1.0; o->sigma_log = NULL; o->sigma_log_cap = 0;
     orc_seed(o, 1);
     return o;
 }
@@ -302,6 +308,7 @@ long orc_run_metropolis(orc_t *o, double T, double T_i, long N_therm, long N_mea
             if (energy_log) { energy_log[nlog] = E / o->N; beta_log[nlog] = beta; } nlog++;
             double R = (double)acc / (double)att;
             sigma = fmin(sigma * 0.5 / (1.0 - R), 60.0);
+            if (o->sigma_log && nlog - 1 < o->sigma_log_cap) o->sigma_log[nlog - 1] = sigma;
             att = 0; acc = 0;
         }
     }

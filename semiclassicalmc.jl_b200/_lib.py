@@ -21,7 +21,7 @@ class ScmcError(RuntimeError):
 
 class RunParams(C.Structure):
     _fields_ = [("n_therm", C.c_int64), ("n_measure", C.c_int64), ("measurement_rate", C.c_int64), ("hits", C.c_int32),
-                ("reserved", C.c_int32), ("seed", C.c_uint64), ("sweep0", C.c_uint64), ("T", c_dp), ("T_i", c_dp), ("sigma", c_dp)]
+                ("stop_sweep", C.c_int32), ("seed", C.c_uint64), ("sweep0", C.c_uint64), ("T", c_dp), ("T_i", c_dp), ("sigma", c_dp)]
 
 
 class RunResults(C.Structure):

@@ -37,6 +37,7 @@ class Configuration:
         self.n_replicas, self.precision, self.device, self.replica_offset = int(n_replicas), int(precision), int(device), int(replica_offset)
         self.colour = np.ascontiguousarray(colourSites(lat) if colour is None else colour, dtype=np.int32)
         self.sweep_counter = 0          # position in the counter-based random stream
+        self.stream_epoch = 0           # fresh driver runs after the first use another stream key (montecarlo.stream_seed)
         self.seed = int(np.random.SeedSequence().entropy % (1 << 63)) if seed is None else int(seed)
         n_labels = len(self.interactions)
         if lat.nbr_label.max() > n_labels:
@@ -132,12 +133,13 @@ class Configuration:
         """0 auto | 1 one stream | 2 two replica lanes on side streams (streaming kernels; chains unchanged)."""
         _lib.check(self._lib.scmc_set_lanes(self._h, lanes))
 
-    def sweep(self, n_sweeps, beta, sigma, hits=2, want_counts=True):
-        """n_sweeps colour-ordered sweeps of every replica (the 2N-update loops, MonteCarlo.jl:40-44)."""
+    def sweep(self, n_sweeps, beta, sigma, hits=2, want_counts=True, seed=None):
+        """n_sweeps colour-ordered sweeps of every replica (the 2N-update loops, MonteCarlo.jl:40-44); `seed` overrides the stream key
+        (the drivers pass the key of their stream epoch, montecarlo.stream_seed)."""
         beta = np.broadcast_to(np.asarray(beta, dtype=np.float64), (self.n_replicas,)).copy()
         sigma = np.broadcast_to(np.asarray(sigma, dtype=np.float64), (self.n_replicas,)).copy()
         acc = np.zeros(self.n_replicas, dtype=np.int64); att = np.zeros(self.n_replicas, dtype=np.int64)
-        _lib.check(self._lib.scmc_sweep(self._h, n_sweeps, hits, _lib.dptr(beta), _lib.dptr(sigma), C.c_uint64(self.seed),
+        _lib.check(self._lib.scmc_sweep(self._h, n_sweeps, hits, _lib.dptr(beta), _lib.dptr(sigma), C.c_uint64(self.seed if seed is None else seed),
                                         C.c_uint64(self.sweep_counter), _lib.lptr(acc) if want_counts else None,
                                         _lib.lptr(att) if want_counts else None))
         self.sweep_counter += n_sweeps

@@ -430,7 +430,13 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
     SCMC_CK(cudaSetDevice(h->device));
     const int64_t R = h->R, rate = p->measurement_rate;
     const int64_t n_anneal = (int64_t)std::ceil(0.75 * (double)p->n_therm);
-    const int64_t total = p->n_therm + p->n_measure;
+    // stop_sweep (0 = run to the end): the call ends after that sweep, so that a caller can write checkpoint files every checkpoint_rate
+    // sweeps (MonteCarlo.jl:56-59, 88-91) and continue with sweep0 = stop_sweep; it must not cut a sigma-adaptation / measurement interval
+    const int64_t total_all = p->n_therm + p->n_measure;
+    SCMC_ARG(p->stop_sweep >= 0 && (p->stop_sweep == 0 || p->stop_sweep >= total_all || p->stop_sweep % p->measurement_rate == 0),
+             "scmc_run_metropolis: stop_sweep must be a multiple of measurement_rate");
+    const int64_t total = p->stop_sweep > 0 ? std::min<int64_t>(total_all, p->stop_sweep) : total_all;
+    const int64_t therm_end = std::min<int64_t>(p->n_therm, total);
     const int64_t meas_start = std::max<int64_t>(p->n_therm + 1, (int64_t)p->sweep0 + 1);
     const int64_t rows_total = total >= meas_start ? total / rate - (meas_start - 1) / rate : 0;
     DevBuf dT(h, 0), dTi(h, 1), dser(h, 2);
@@ -465,11 +471,11 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
     if (device_side) {
         // energy log entries (one per sigma-adaptation point) are written by the kernel into one device table, copied out at the end
         const int64_t log_base = (int64_t)p->sweep0 / rate + 1;       // g / rate of the first entry
-        const int64_t n_log_total = std::max<int64_t>(0, p->n_therm / rate - (int64_t)p->sweep0 / rate);
+        const int64_t n_log_total = std::max<int64_t>(0, therm_end / rate - (int64_t)p->sweep0 / rate);
         DevBuf dlog(h, 3);
         if (out->therm_energy && n_log_total > 0) SCMC_CK(dlog.alloc((size_t)n_log_total * R * 8));
-        for (int64_t sweep = (int64_t)p->sweep0 + 1; sweep <= p->n_therm;) {
-            const int64_t chunk = std::min<int64_t>(512, p->n_therm - sweep + 1);
+        for (int64_t sweep = (int64_t)p->sweep0 + 1; sweep <= therm_end;) {
+            const int64_t chunk = std::min<int64_t>(512, therm_end - sweep + 1);
             SCMC_TRY(launch_resident_run(h, 1, chunk, p->hits, p->seed, dT.as<double>(), dTi.as<double>(), n_anneal, rate, sweep, log_base,
                                          dlog.p ? dlog.as<double>() : nullptr));
             sweep += chunk;
@@ -480,11 +486,11 @@ int32_t scmc_run_metropolis(scmc_t* h, const scmc_run_params* p, scmc_run_result
             n_log = n_log_total;
         }
     }
-    for (int64_t sweep = (int64_t)p->sweep0 + 1; !device_side && sweep <= p->n_therm; sweep++) {
+    for (int64_t sweep = (int64_t)p->sweep0 + 1; !device_side && sweep <= therm_end; sweep++) {
         SCMC_TRY(set_beta(sweep));
         int64_t n_batch = 1;
         if (sweep > n_anneal) {      // ramp finished: beta constant, batch up to the next sigma-adaptation point
-            const int64_t next_stop = std::min<int64_t>(p->n_therm, ((sweep + rate - 1) / rate) * rate);
+            const int64_t next_stop = std::min<int64_t>(therm_end, ((sweep + rate - 1) / rate) * rate);
             n_batch = next_stop - sweep + 1;
         }
         SCMC_TRY(launch_sweeps(h, n_batch, p->hits, p->seed, (uint64_t)(sweep - 1), nullptr));

@@ -93,7 +93,8 @@ def checkpointH5_(filename, cfg, current_sweep, βs, energy, σ, replica=0):
     hdf5.write(filename, {"current_sweep": np.int64(current_sweep), "energy": np.asarray(energy, dtype=np.float64),
                           "βs": np.asarray(βs, dtype=np.float64), "σ": np.float64(np.ravel(σ)[replica] if np.ndim(σ) else σ),
                           "state": _julia(vectorToMatrix(psi)), "seed": np.uint64(cfg.seed), "sweep_counter": np.int64(cfg.sweep_counter),
-                          "replica_id": np.int64(cfg.replica_offset + replica)})
+                          "replica_id": np.int64(cfg.replica_offset + replica), "stream_epoch": np.int64(getattr(cfg, "stream_epoch", 0)),
+                          "stream_version": np.int64(getattr(cfg, "stream", 1))})
 
 
 def saveState_(filename, cfg, replica=0):

@@ -224,6 +224,8 @@ def means(obs, cfg, beta, replica=0):
     for name, b in (("σ", obs.sigma), ("τ", obs.tau), ("στ", obs.sigmatau), ("magnetizationVec", obs.magnetizationVec)):
         out[name] = (b[replica].mean(), b[replica].std_error())
     if obs.with_correlations:
+        if obs.correlations[replica].count == 0:
+            raise RuntimeError("means(): no correlation measurement was pushed (run_ measures correlations once per interval when obs.with_correlations is set)")
         out["correlations"] = (obs.correlations[replica].mean(), obs.correlations[replica].std_error())
     return out
 

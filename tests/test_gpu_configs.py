@@ -227,3 +227,70 @@ def test_reference_accessors_against_direct_formulas(scmc):
     scmc.measure_(obs, cfg); scmc.measure_(obs, cfg)
     assert obs.energy[0].count == 2 and abs(obs.energy[0].means()[0] - scmc.getEnergy(cfg) / N) < 1e-12
     assert np.allclose(obs.magnetizationVec[0].mean(), scmc.getMagnetization(cfg), atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_launch_writes_checkpoint_files_during_the_run_and_resumes(scmc, tmp_path):
+    """checkpoint_rate (MonteCarlo.jl:56-59, 88-91): the chains' files exist with the right sweep count after every checkpoint_rate sweeps,
+    carry the reference's `energy` / `βs` series of THEIR chain (one entry per sigma-adaptation / measurement point, MonteCarlo.jl:48-49,
+    84-85) and `means/correlations` (ObservablesGeneric.jl:44, 61-62); a launch continued from the files of an interrupted one
+    (overwrite = false, Launcher.jl:78-88) ends in the same states as an uninterrupted launch."""
+    Ts = [0.1, 0.5]
+    kw = dict(measurement_rate=10, seed=17, checkpoint_rate=50, precision=32)
+    full = scmc.launch_(str(tmp_path / "full.h5"), "nearest-neighbor", 1, None, "triangular", 6, [NOTEBOOK_J], Ts, 2.0, 100, 100, **kw)
+    one = scmc.readCheckpointH5(full["files"][1])
+    assert int(one["current_sweep"]) == 200 and one["energy"].shape == (20,) and one["βs"].shape == (20,)
+    n_anneal = 75
+    beta_expected = [1.0 / (2.0 * (0.5 / 2.0) ** ((q - 1) / (n_anneal - 1))) if q <= n_anneal else 2.0 for q in range(10, 101, 10)] + [2.0] * 10
+    assert np.allclose(one["βs"], beta_expected, rtol=1e-12)
+    assert np.array_equal(one["energy"], full["energy_series"][:, 1]) and abs(one["energy"][3] - full["therm_energy"][3, 1]) < 1e-12
+    assert abs(one["energy"][-1] - full["cfg"].energies()[1] / 36) < 1e-12      # the last entry is E/N of the final state
+    assert one["means"]["correlations"]["mean"].shape == (16, 36)
+    C0 = one["means"]["correlations"]["mean"]
+    assert np.allclose(C0[0], 36.0, rtol=1e-5)                                  # T^1 = 1 at every site: sum over the 36 pairs of every displacement
+    # an interrupted launch: stop after the thermalisation + 50 measurement sweeps (files written at sweep 150), then continue
+    part = scmc.launch_(str(tmp_path / "part.h5"), "nearest-neighbor", 1, None, "triangular", 6, [NOTEBOOK_J], Ts, 2.0, 100, 50, **kw)
+    mid = scmc.readCheckpointH5(part["files"][0])
+    assert int(mid["current_sweep"]) == 150 and mid["energy"].shape == (15,)
+    # the same files, now asked for 100 measurement sweeps: continued from sweep 150
+    cont = scmc.launch_(str(tmp_path / "part.h5"), "nearest-neighbor", 1, None, "triangular", 6, [NOTEBOOK_J], Ts, 2.0, 100, 100, overwrite=False, **kw)
+    assert np.array_equal(cont["cfg"].get_state(), full["cfg"].get_state())
+    end = scmc.readCheckpointH5(cont["files"][0])
+    ref = scmc.readCheckpointH5(full["files"][0])
+    assert int(end["current_sweep"]) == 200 and np.array_equal(end["energy"], ref["energy"]) and np.array_equal(end["βs"], ref["βs"])
+    assert float(end["σ"]) == float(ref["σ"])
+
+
+@pytest.mark.gpu
+def test_sigma_convention_reference_units(scmc, golden):
+    """σ_convention = "reference": cone widths cross the API in the reference's units (its proposal normals have variance 1/2, see
+    tests/test_oracle_physics.py::test_reference_sigma_trace_is_a_variance_half_convention).  The adapted sigma of the notebook's model at
+    T = 0.02 then lands in the range the notebook prints (0.0258 - 0.0289), and is sqrt(2) times the unit-convention value of the same chain."""
+    mk = lambda: scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 6, 1, n_replicas=64, precision=32, seed=8)
+    a, b = mk(), mk()
+    ra = scmc.run_(a, None, 0.02, 1.0, 20000, 0, measurement_rate=10, σ=60.0, σ_convention="reference")
+    rb = scmc.run_(b, None, 0.02, 1.0, 20000, 0, measurement_rate=10, σ=60.0 / np.sqrt(2.0))
+    assert np.allclose(ra["sigma"], rb["sigma"] * np.sqrt(2.0), rtol=1e-6) and np.array_equal(a.get_state(), b.get_state())
+    nb = [row["sigma"] for row in golden["metropolis"]["thermalization_log"] if row["sweep"] >= 80000]
+    assert min(nb) * 0.97 < ra["sigma"].mean() < max(nb) * 1.03, (ra["sigma"].mean(), nb)
+    assert rb["sigma"].mean() < min(nb) * 0.85
+
+
+@pytest.mark.gpu
+def test_C4_fp32_annealing_with_fp64_polish_reaches_1e8(scmc, golden):
+    """C4 in the precision it ships in: 512 restarts (one GPU's share of the 4096) annealed in FP32 with the notebook's schedule, optimisation
+    sweeps and energies finished in FP64 (polishFP64_): min E/N within 1e-8 of the exact -3.6 and never below it (an FP32 energy sum alone
+    gave -3.6000005 in round 1).  Consecutive fresh runs on one configuration use different stream keys."""
+    a = golden["annealing"]["params"]
+    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 36, 1, n_replicas=512, precision=32, seed=20230301)
+    res = scmc.runAnnealing_(cfg, a["T_i"], T_fac=a["T_fac"], N_max=int(a["N_max"]), N_o=400, N_per_T=int(a["N_per_T"]),
+                             min_acc_per_site=int(a["min_acc_per_site"]), min_accrate=a["min_accrate"], σ_min=a["σ_min"])
+    assert res["polished_fp64"]
+    e = res["E"] / cfg.nSites
+    assert abs(e.min() - golden["annealing"]["exact_E_per_site"]) < 1e-8, e.min()
+    assert np.all(e >= -3.6 - 1e-9) and np.all(e <= res["E_annealed"] / cfg.nSites + 1e-6)
+    # the polished states are back in the FP32 configuration: its own (FP32) energy agrees to FP32 accuracy
+    assert np.allclose(cfg.energies() / cfg.nSites, e, atol=2e-6)
+    assert cfg.stream_epoch == 0
+    scmc.runAnnealing_(cfg, 3.0, N_max=5, N_o=0, N_per_T=2)
+    assert cfg.stream_epoch == 1

@@ -23,6 +23,11 @@ def build(scmc, kind, precision, R=3, seed=1234, **kw):
         return scmc.initializeCfg("nearest-neighbor", "honeycomb", [Jon, random_symmetric_J(9)], 4, 2, n_replicas=R, precision=precision, seed=seed, **kw)
     if kind == "tghbn":              # 3 labels, 12 neighbours, on-site K, n = 2, 4 colours
         return scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.15, 0.8], 4, 2, n_replicas=R, precision=precision, seed=seed, **kw)
+    if kind == "honey_n2":           # n = 2 (d = 6), no on-site term (BASELINE config C3 couplings: J = 1_16 with J[1,1] = 0), honeycomb L = 4
+        Jc3 = np.eye(16); Jc3[0, 0] = 0.0
+        return scmc.initializeCfg("nearest-neighbor", "honeycomb", [Jc3], 4, 2, n_replicas=R, precision=precision, seed=seed, **kw)
+    if kind == "tghbn6":             # TG/h-BN model on triangular L = 6 (3 labels, 12 neighbours, on-site K, n = 2)
+        return scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.15, 0.8], 6, 2, n_replicas=R, precision=precision, seed=seed, **kw)
     if kind == "honey_heis":         # BASELINE config C1: su(4) Heisenberg on honeycomb 6x6
         return scmc.initializeCfg("nearest-neighbor", "honeycomb", [np.eye(16)], 6, 1, n_replicas=R, precision=precision, seed=seed, **kw)
     if kind == "tri_n3":
@@ -198,6 +203,35 @@ def test_thermal_statistics_match_reference_chain(scmc, oracle_mod, stream):
     assert abs(e_gpu - e_ref) < 4.5 * np.hypot(e_gpu_err, e_ref_err) + 1e-4, (e_gpu, e_gpu_err, e_ref, e_ref_err)
     assert abs(c_gpu - c_ref) < 4.5 * np.hypot(c_gpu_err, c_ref_err) + 0.02, (c_gpu, c_gpu_err, c_ref, c_ref_err)
     assert np.all(np.abs(res["acc_rate"] - 0.5) < 0.1)      # sigma adapted towards 50 % (MonteCarlo.jl:47-54)
+
+
+@pytest.mark.parametrize("kind,T,stream", [("honey_n2", 0.15, 1), ("honey_n2_onsite", 0.15, 2), ("tghbn6", 0.05, 1), ("tghbn6", 0.05, 2)])
+def test_fp32_production_statistics_n2_and_tghbn_match_sequential_chain(scmc, oracle_mod, kind, T, stream):
+    """The FP32 production kernels for d = 6 (n = 2: T-gather without, psi-gather with on-site term) and for the TG/h-BN model (three
+    coupling labels, 12 neighbours, label-major gather) against the oracle's sequential random-site FP64 chain (the reference's sweep,
+    src/MonteCarlo.jl:40-44): energy, specific heat and |m| agree within error bars."""
+    R = 48
+    cfg = build(scmc, kind, 32, R=R, seed=4711, stream=stream)
+    N = cfg.nSites
+    res = scmc.run_(cfg, None, T, 1.0, 2000, 6000, measurement_rate=10)
+    ser = res["series"]                                      # [rows, R, 21]
+    e_rep = ser[:, :, 0].mean(axis=0)
+    c_rep = (ser[:, :, 1].mean(axis=0) - e_rep ** 2) * N / T ** 2
+    m_rep = ser[:, :, 2:5].mean(axis=0)
+    es, cs, ms = [], [], []
+    for k in range(6):
+        o = make_oracle(cfg, oracle_mod)
+        o.seed(2000 + k); o.randomize()
+        s_ = o.run_metropolis(T, 1.0, 2000, 6000, 10)["series"]
+        es.append(s_[:, 0].mean()); cs.append((s_[:, 1].mean() - s_[:, 0].mean() ** 2) * N / T ** 2); ms.append(s_[:, 2:5].mean(axis=0))
+    def cmp(gpu, ref, floor):
+        g, ge = np.mean(gpu, axis=0), np.std(gpu, axis=0, ddof=1) / np.sqrt(len(gpu))
+        r, re_ = np.mean(ref, axis=0), np.std(ref, axis=0, ddof=1) / np.sqrt(len(ref))
+        assert np.all(np.abs(g - r) < 4.5 * np.hypot(ge, re_) + floor), (kind, g, ge, r, re_)
+    cmp(e_rep, es, 1e-4 * max(1.0, abs(np.mean(es))))
+    cmp(c_rep, cs, 0.03)
+    cmp(m_rep, np.array(ms), 2e-3)
+    assert np.all(np.abs(res["acc_rate"] - 0.5) < 0.12)
 
 
 @pytest.mark.parametrize("stream", [1, 2])
