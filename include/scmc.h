@@ -195,6 +195,37 @@ int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results*
  * minimiser of its local energy <psi|H_loc|psi> (the fixed point of the reference's per-site gradient descent). E [R] or NULL. */
 int32_t scmc_optimize(scmc_t* h, int64_t n_sweeps, double* E);
 
+/* ---- several GPUs of one box behind one object ------------------------------------------------------------------------
+ * Replaces the reference's only parallelism, one Slurm job step per temperature merged from files (Launcher.jl:239-345, IO.jl:64-143), for
+ * callers that are not one-process-per-GPU Python programs (the Julia shim, C).  Replicas / temperatures / restarts never interact: the
+ * object is one scmc_t per device, each owning a contiguous range of the n_replicas_total GLOBAL replica ids (device i: first_replica ..
+ * first_replica + n_replicas - 1; the ids enter the random stream, so a chain does not depend on the split).  Every array argument below is
+ * indexed by the global replica and lives on the host.  Calls fan out to the devices from one host thread per device; the only exchange
+ * between GPUs is in scmc_multi_measure: ONE ncclAllGather of the SCMC_NOBS-value measure! rows over NVLink (single process,
+ * ncclCommInitAll; NCCL is dlopen'ed at first use).  devices = NULL means 0 .. n_dev-1.  A per-device handle obtained from
+ * scmc_multi_handle can be used with every single-device entry point (structure factors, get/set_state, ...). */
+typedef struct scmc_multi scmc_multi_t;
+int32_t scmc_multi_create(scmc_multi_t** m, int32_t n_dev, const int32_t* devices, int32_t precision, int64_t n_sites, int32_t d,
+                          int64_t n_replicas_total, int64_t replica_offset, int32_t z_max, const int32_t* nbr_site, const int32_t* nbr_label,
+                          int32_t n_labels, const double* J, const double* K, const double* gen_re, const double* gen_im,
+                          const double* gensq_re, const double* gensq_im, const int32_t* colour);
+int32_t scmc_multi_destroy(scmc_multi_t* m);
+int32_t scmc_multi_count(scmc_multi_t* m, int32_t* n_dev, int64_t* n_replicas_total);
+int32_t scmc_multi_handle(scmc_multi_t* m, int32_t i, scmc_t** h, int64_t* first_replica, int64_t* n_replicas);
+int32_t scmc_multi_randomize(scmc_multi_t* m, uint64_t seed);
+int32_t scmc_multi_set_stream_version(scmc_multi_t* m, int32_t version);
+int32_t scmc_multi_set_sweep_mode(scmc_multi_t* m, int32_t mode, int64_t batch);
+int32_t scmc_multi_sweep(scmc_multi_t* m, int64_t n_sweeps, int32_t hits, const double* beta, const double* sigma, uint64_t seed,
+                         uint64_t sweep_counter, int64_t* accepted, int64_t* attempted);
+int32_t scmc_multi_energy(scmc_multi_t* m, double* E /* [R_total] */);
+int32_t scmc_multi_optimize(scmc_multi_t* m, int64_t n_sweeps, double* E /* [R_total] */);
+int32_t scmc_multi_get_state(scmc_multi_t* m, int64_t r0, int64_t count, double* re, double* im);
+/* measure! rows of all replicas [R_total][SCMC_NOBS]: per-device reductions + one ncclAllGather (the final observable reduction) */
+int32_t scmc_multi_measure(scmc_multi_t* m, double* obs);
+/* run! / runAnnealing! cooling loop on all devices at once; parameter and result arrays have R_total entries per row */
+int32_t scmc_multi_run_metropolis(scmc_multi_t* m, const scmc_run_params* p, scmc_run_results* out);
+int32_t scmc_multi_anneal(scmc_multi_t* m, const scmc_anneal_params* p, scmc_anneal_results* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,22 @@ SIGNATURES = {
     "scmc_run_metropolis": (C.c_int32, [C.c_void_p, C.POINTER(RunParams), C.POINTER(RunResults)]),
     "scmc_anneal": (C.c_int32, [C.c_void_p, C.POINTER(AnnealParams), C.POINTER(AnnealResults)]),
     "scmc_optimize": (C.c_int32, [C.c_void_p, C.c_int64, c_dp]),
+    # several GPUs of one box behind one object (single process, ncclAllGather of the measure! rows)
+    "scmc_multi_create": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int32, c_ip, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32,
+                                      c_ip, c_ip, C.c_int32, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip]),
+    "scmc_multi_destroy": (C.c_int32, [C.c_void_p]),
+    "scmc_multi_count": (C.c_int32, [C.c_void_p, c_ip, c_lp]),
+    "scmc_multi_handle": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), c_lp, c_lp]),
+    "scmc_multi_randomize": (C.c_int32, [C.c_void_p, C.c_uint64]),
+    "scmc_multi_set_stream_version": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "scmc_multi_set_sweep_mode": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64]),
+    "scmc_multi_sweep": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, c_dp, c_dp, C.c_uint64, C.c_uint64, c_lp, c_lp]),
+    "scmc_multi_energy": (C.c_int32, [C.c_void_p, c_dp]),
+    "scmc_multi_optimize": (C.c_int32, [C.c_void_p, C.c_int64, c_dp]),
+    "scmc_multi_get_state": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, c_dp, c_dp]),
+    "scmc_multi_measure": (C.c_int32, [C.c_void_p, c_dp]),
+    "scmc_multi_run_metropolis": (C.c_int32, [C.c_void_p, C.POINTER(RunParams), C.POINTER(RunResults)]),
+    "scmc_multi_anneal": (C.c_int32, [C.c_void_p, C.POINTER(AnnealParams), C.POINTER(AnnealResults)]),
 }
 
 _lib = None

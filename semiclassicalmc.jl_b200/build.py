@@ -8,7 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscmc_b200.so")
-SOURCES = ["scmc_core.cu", "scmc_drivers.cu", "scmc_resident.cu", "scmc_tma.cu"]
+SOURCES = ["scmc_core.cu", "scmc_drivers.cu", "scmc_resident.cu", "scmc_tma.cu", "scmc_multi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "--expt-relaxed-constexpr", "-use_fast_math",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
         for l in logs:
             sys.stderr.write(l)
     if jobs or force or _stale(LIB, objs):
-        r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs], capture_output=True, text=True)
+        r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-ldl"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
