@@ -259,6 +259,12 @@ def test_launch_writes_checkpoint_files_during_the_run_and_resumes(scmc, tmp_pat
     ref = scmc.readCheckpointH5(full["files"][0])
     assert int(end["current_sweep"]) == 200 and np.array_equal(end["energy"], ref["energy"]) and np.array_equal(end["βs"], ref["βs"])
     assert float(end["σ"]) == float(ref["σ"])
+    # the reference-layout file of a real launch passes the independent C reader (tests/h5_check.c, written from the HDF5 specification)
+    import os, subprocess
+    exe = str(tmp_path / "h5_check")
+    subprocess.check_call(["gcc", "-O1", "-o", exe, os.path.join(os.path.dirname(os.path.abspath(__file__)), "h5_check.c")])
+    out = subprocess.run([exe, full["files"][0]], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "/means/correlations/mean float64 [36,16]" in out.stdout and "/state complex128 [36,4]" in out.stdout, out.stdout + out.stderr
 
 
 @pytest.mark.gpu

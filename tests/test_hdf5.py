@@ -156,3 +156,61 @@ def test_result_file_names_of_a_packed_launch(scmc):
     assert f(lambda T: f"x{T}.h5", 2.0, None, 5) == "x2.0.h5"
     w = scmc.launcher._writes_files
     assert w("a.h5") and w("b.HDF5") and w(lambda T: "c") and not w("label") and not w(None)
+
+
+def _fnv(raw):
+    s = 0
+    for b in raw:
+        s = (s * 1099511628211 + b) & 0xFFFFFFFFFFFFFFFF
+    return f"{s:016x}"
+
+
+def test_files_pass_an_independent_c_reader(tmp_path):
+    """No libhdf5 / h5py / HDF5.jl exists in this image, so the written files are checked by a SECOND reader, written in C from the HDF5 File
+    Format Specification alone (tests/h5_check.c: superblock v0, v1 object headers, symbol-table groups through B-tree / SNOD / local heap,
+    dataspace, datatype and contiguous-layout messages, address and size consistency).  Its listing must name every object with the type,
+    shape, leading values and a checksum of the raw bytes that were written; a damaged file must fail its checks."""
+    import os
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    import scmc_b200 as scmc
+    exe = str(tmp_path / "h5_check")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "h5_check.c")])
+    state = (np.arange(24).reshape(6, 4) + 1j * np.arange(24).reshape(6, 4)[::-1]).astype(np.complex128)
+    tree = {"current_sweep": np.int64(200), "energy": np.linspace(-3.5, -3.4, 7), "σ": np.float64(0.0271), "βs": np.full(7, 50.0), "state": state,
+            "means/energy/mean": np.float64(-3.54), "means/energy/error": np.float64(9e-5), "means/magnetizationVec/mean": np.arange(16.0),
+            "means/correlations/mean": np.arange(16.0 * 36).reshape(36, 16), "rs": np.arange(72.0).reshape(36, 2), "seed": np.uint64(2 ** 63 + 5),
+            "small": np.arange(5, dtype=np.int32) - 2, "f32": np.arange(3, dtype=np.float32) / 3, "empty": np.zeros(0)}
+    tree.update({f"means/obs{k:02d}/mean": np.float64(k) for k in range(20)})          # a group larger than the default leaf K
+    fn = str(tmp_path / "t.h5")
+    scmc.hdf5.write(fn, tree)
+    out = subprocess.run([exe, fn], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and out.stdout.rstrip().endswith("h5_check ok"), out.stdout + out.stderr
+    lines = {l.split(" ", 1)[0]: l.split(" ", 1)[1] for l in out.stdout.splitlines()[1:-1]}
+    names = {"int64": "int64", "int32": "int32", "uint64": "uint64", "float64": "float64", "float32": "float32", "complex128": "complex128"}
+    n_sets = 0
+    for key, v in tree.items():
+        a = np.asarray(v)
+        got = lines["/" + key]
+        shape = "[" + ",".join(str(n) for n in a.shape) + "]"
+        assert got.startswith(f"{names[a.dtype.name]} {shape}"), (key, got)
+        assert got.endswith("fnv=" + _fnv(a.tobytes())), (key, got)
+        n_sets += 1
+    groups = [k for k, v in lines.items() if v == "group"]
+    assert sorted(groups) == sorted(["/", "/means/", "/means/energy/", "/means/magnetizationVec/", "/means/correlations/"] + [f"/means/obs{k:02d}/" for k in range(20)])
+    assert len(lines) == n_sets + len(groups)
+    assert lines["/state"].split()[2:4] == ["(0,20)", "(1,21)"] and lines["/small"].split()[2:7] == ["-2", "-1", "0", "1", "2"]
+    assert lines["/seed"].split()[2] == str(2 ** 63 + 5) and float(lines["/σ"].split()[2]) == 0.0271
+    # the reference's result file as launch_ writes it goes through the same checks on the GPU box (tests/test_gpu_configs.py); here: damage
+    raw = bytearray(open(fn, "rb").read())
+    raw[40] ^= 0x10                                                                     # end-of-file address in the superblock
+    bad = str(tmp_path / "bad.h5")
+    open(bad, "wb").write(raw)
+    assert subprocess.run([exe, bad], capture_output=True, text=True, timeout=60).returncode == 1
+    raw = bytearray(open(fn, "rb").read())
+    k = raw.find(b"SNOD")
+    raw[k + 8 + 40:k + 8 + 48], raw[k + 8:k + 16] = raw[k + 8:k + 16], raw[k + 8 + 40:k + 8 + 48]      # swap two link-name offsets: entries no longer sorted
+    open(bad, "wb").write(raw)
+    assert subprocess.run([exe, bad], capture_output=True, text=True, timeout=60).returncode == 1
