@@ -18,7 +18,7 @@ class Configuration:
     """struct Configuration (Configuration.jl:2-24) + constructor (Configuration.jl:27-77)."""
 
     def __init__(self, latticename, L, uc, interactions, onsiteInteraction, n, *, n_replicas=1, precision=64, device=0,
-                 replica_offset=0, seed=None, colour=None, stream=1):
+                 replica_offset=0, seed=None, colour=None, stream=1, generators=None):
         lat = getLatticePeriodic(uc, L)
         self.latticename, self.L, self.n = latticename, int(L), int(n)
         self.lattice = lat
@@ -31,8 +31,10 @@ class Configuration:
         self.interactionLabels = lat.nbr_label          # [N, z], 1-based
         self.interactions = [np.array(J, dtype=float).reshape(16, 16) for J in interactions]
         self.onsiteInteraction = np.array(onsiteInteraction, dtype=float).reshape(16)
-        self.generators = _gen.getGenerators(n)
-        self.generatorsSq = _gen.getGeneratorsSq(n)
+        # generators=: caller-supplied tables [16, d, d] (Hermitian, d = 4 or 6) instead of getGenerators(n) -- e.g. the n = 2 parton
+        # representation WITH the Jordan-Wigner sign the reference's f omits; they run on the library's dense-table path
+        self.generators = _gen.getGenerators(n) if generators is None else np.asarray(generators, dtype=np.complex128)
+        self.generatorsSq = _gen.getGeneratorsSq(n) if generators is None else np.stack([g @ g for g in self.generators])
         self.d = self.generators.shape[1]
         self.n_replicas, self.precision, self.device, self.replica_offset = int(n_replicas), int(precision), int(device), int(replica_offset)
         self.colour = np.ascontiguousarray(colourSites(lat) if colour is None else colour, dtype=np.int32)

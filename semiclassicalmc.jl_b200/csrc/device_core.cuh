@@ -64,6 +64,60 @@ template <> struct GenOps<3> {
     template <class R> static __device__ __forceinline__ R energy_from_state(const R* re, const R* im, const R* Hq) { return gen::energy_from_state_g3(re, im, Hq); }
 };
 
+// Caller-supplied generator tables (any 16 Hermitian d x d matrices, d = 4 or 6 -- e.g. a parton operator WITH the Jordan-Wigner sign the
+// reference's f omits): no unrolled sparse code exists for them, so T^a = Re psi^dagger G^a psi is the reference's dense
+// contraction (computeSpinExpectation!, src/Configuration.jl:166-194) over tables in constant memory.  One table set per translation unit
+// and device (set_custom_tables below); the kernels of the T-gather family use it, always with the on-site term and MAXL labels.
+struct CustomTables { double gre[NG * 36], gim[NG * 36], qre[NG * 36], qim[NG * 36]; };      // [a][j][k], row stride d
+static __constant__ CustomTables c_custom;
+template <int D_> struct GenOpsCustom {
+    static constexpr int D = D_;
+    static constexpr int NDENS = 0;            // no density basis: the psi-gather family is not offered
+    template <class R> static __device__ __forceinline__ void contract(const double* gr, const double* gi, const R* re, const R* im, R* T) {
+#pragma unroll 1
+        for (int a = 0; a < NG; a++) {
+            R acc = R(0);
+#pragma unroll
+            for (int j = 0; j < D; j++)
+#pragma unroll
+                for (int k = 0; k < D; k++) {
+                    const R g_r = (R)gr[(a * D + j) * D + k], g_i = (R)gi[(a * D + j) * D + k];
+                    acc += (re[j] * re[k] + im[j] * im[k]) * g_r - (re[j] * im[k] - im[j] * re[k]) * g_i;
+                }
+            T[a] = acc;
+        }
+    }
+    template <class R> static __device__ __forceinline__ void expect(const R* re, const R* im, R* T) { contract<R>(c_custom.gre, c_custom.gim, re, im, T); }
+    template <class R> static __device__ __forceinline__ void expect_sq(const R* re, const R* im, R* T) { contract<R>(c_custom.qre, c_custom.qim, re, im, T); }
+    // upper triangle of H_loc = sum_a h^a G^a + K^a (G^a)^2
+    template <class R, bool O> static __device__ __forceinline__ void hloc(const R* h, const R* K, R* Hr, R* Hi) {
+#pragma unroll
+        for (int j = 0; j < D; j++)
+#pragma unroll
+            for (int k = j; k < D; k++) {
+                R hr = R(0), hi = R(0);
+#pragma unroll 1
+                for (int a = 0; a < NG; a++) {
+                    hr += h[a] * (R)c_custom.gre[(a * D + j) * D + k]; hi += h[a] * (R)c_custom.gim[(a * D + j) * D + k];
+                    if (O) { hr += K[a] * (R)c_custom.qre[(a * D + j) * D + k]; hi += K[a] * (R)c_custom.qim[(a * D + j) * D + k]; }
+                }
+                Hr[j * D + k] = hr; Hi[j * D + k] = hi;
+            }
+    }
+};
+template <> struct GenOps<4> : GenOpsCustom<4> {};
+template <> struct GenOps<5> : GenOpsCustom<6> {};
+// host: make `t` the table set of the calling translation unit on the current device (synchronises the device when another handle's set is live)
+static inline cudaError_t set_custom_tables(const CustomTables& t, const void* owner, int device) {
+    static const void* live[64] = {nullptr};
+    if (live[device & 63] == owner) return cudaSuccess;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_custom, &t, sizeof(CustomTables));
+    if (e == cudaSuccess) live[device & 63] = owner;
+    return e;
+}
+
 // ------------------------------------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ void mulhilo(uint32_t m, uint32_t x, uint32_t& hi, uint32_t& lo) {
     // one IMAD.WIDE.U32; written in PTX so the 64-bit product is split without extra carry/IADD3 instructions

@@ -75,7 +75,8 @@ struct scmc_handle {
     std::vector<int32_t> colour, perm, orig;   // perm[orig site] = permuted index
     int32_t col_off[scmc::MAXC + 1] = {0};
     double J[scmc::MAXL][256] = {{0}}, K[16] = {0};
-    double e_const = 0.0;     // N * sum_a K^a when (G^a)^2 = 1 (n = 1, 3): constant on-site energy
+    double e_const = 0.0;     // N * sum_a K^a c_a when (G^a)^2 = c_a 1 (n = 1, 3): constant on-site energy
+    scmc::CustomTables* custom = nullptr;     // caller-supplied generator tables (gen_id 4: d = 4, 5: d = 6), else null
     // device memory
     void *psi = nullptr, *T = nullptr, *Tsq = nullptr;
     int32_t *nbr = nullptr, *d_orig = nullptr, *d_col_list = nullptr, *d_cls_site = nullptr, *d_cls_nbr = nullptr;

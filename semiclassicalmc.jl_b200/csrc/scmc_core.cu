@@ -1157,6 +1157,9 @@ static int32_t dispatch(const scmc_handle* h, F&& f) {
             case 1: return with_nl(rt, ic<1>{}, ic<0>{});
             case 2: return h->onsite ? with_nl(rt, ic<2>{}, ic<1>{}) : with_nl(rt, ic<2>{}, ic<0>{});
             case 3: return with_nl(rt, ic<3>{}, ic<0>{});
+            // caller-supplied tables: dense contraction, always MAXL labels and the on-site term (one instantiation per precision and d)
+            case 4: if (set_custom_tables(*h->custom, h, h->device) != cudaSuccess) break; return f(rt, ic<4>{}, ic<1>{}, ic<MAXL>{});
+            case 5: if (set_custom_tables(*h->custom, h, h->device) != cudaSuccess) break; return f(rt, ic<5>{}, ic<1>{}, ic<MAXL>{});
         }
         set_error("internal: bad generator id");
         return SCMC_ERR_ARG;
@@ -1186,9 +1189,9 @@ int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma) 
 // Which arithmetic family the production (stream-driven) sweeps of this handle use.  It depends on the model only -- never on
 // the replica count or the number of sweeps per call -- so that a replica's chain is identical however replicas are sharded.
 bool uses_psi_gather(const scmc_handle* h) {
-    if (h->sweep_mode == 3 || h->sweep_mode == 4 || h->sweep_mode == 5) return h->n_labels == 1;
+    if (h->sweep_mode == 3 || h->sweep_mode == 4 || h->sweep_mode == 5) return h->n_labels == 1 && h->gen_id <= 3;
     if (h->sweep_mode == 1 || h->sweep_mode == 2) return false;
-    return h->n_labels == 1 && (h->d == 4 || h->onsite) && !h->res_family_T;      // measured: d = 6 without on-site term is on par / slightly faster with T-gather
+    return h->gen_id <= 3 && h->n_labels == 1 && (h->d == 4 || h->onsite) && !h->res_family_T;      // measured: d = 6 without on-site term is on par / slightly faster with T-gather
 }
 
 // Where the replica-resident kernel is the better one (measured, profiles/README.md): clusters of up to 2 CTAs, or larger ones when they
@@ -1481,8 +1484,16 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     else if (d == 4 && table_matches(gen_re, gen_im, gen::G3_re, gen::G3_im, 256) && table_matches(gensq_re, gensq_im, gen::Gsq3_re, gen::Gsq3_im, 256)) gen_id = 3;
     else if (d == 6 && table_matches(gen_re, gen_im, gen::G2_re, gen::G2_im, 576) && table_matches(gensq_re, gensq_im, gen::Gsq2_re, gen::Gsq2_im, 576)) gen_id = 2;
     if (!gen_id) {
-        set_error("scmc_create: generator tables differ from getGenerators(n), n = 1, 2, 3 (custom generators are not supported)");
-        return SCMC_ERR_UNSUPPORTED;
+        // caller-supplied generators (e.g. the parton operator with its Jordan-Wigner sign): dense-table path, T-gather family
+        for (int a = 0; a < 16; a++)
+            for (int j = 0; j < d; j++)
+                for (int k = 0; k < d; k++) {
+                    const size_t jk = ((size_t)a * d + j) * d + k, kj = ((size_t)a * d + k) * d + j;
+                    SCMC_ARG(std::fabs(gen_re[jk] - gen_re[kj]) < 1e-12 && std::fabs(gen_im[jk] + gen_im[kj]) < 1e-12 &&
+                             std::fabs(gensq_re[jk] - gensq_re[kj]) < 1e-12 && std::fabs(gensq_im[jk] + gensq_im[kj]) < 1e-12,
+                             "scmc_create: generator tables must be Hermitian matrices");
+                }
+        gen_id = d == 4 ? 4 : 5;
     }
 
     const int64_t N = n_sites;
@@ -1527,8 +1538,19 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     bool anyK = false;
     double sumK = 0.0;
     for (int a = 0; a < 16; a++) { anyK |= (K[a] != 0.0); sumK += K[a]; }
-    h->onsite = anyK && gen_id == 2;
-    h->e_const = (gen_id == 2) ? 0.0 : sumK * (double)N;   // (G^a)^2 = 1 for d = 4  
+    h->onsite = (anyK && gen_id == 2) || gen_id >= 4;
+    // n = 1: (G^a)^2 = 1; n = 3: (G^a)^2 = c_a 1 with c_1 = 9 (S(0,0) = 3 1): the on-site energy is the constant N sum_a K^a c_a
+    h->e_const = 0.0;
+    if (gen_id == 1 || gen_id == 3)
+        for (int a = 0; a < 16; a++) h->e_const += K[a] * gensq_re[(size_t)a * d * d] * (double)N;
+    (void)sumK;
+    if (gen_id >= 4) {
+        h->custom = new CustomTables();
+        memset(h->custom, 0, sizeof(CustomTables));
+        const size_t nt = (size_t)16 * d * d;
+        memcpy(h->custom->gre, gen_re, nt * 8); memcpy(h->custom->gim, gen_im, nt * 8);
+        memcpy(h->custom->qre, gensq_re, nt * 8); memcpy(h->custom->qim, gensq_im, nt * 8);
+    }
 
     // --- colouring
     h->colour.assign(N, -1);
@@ -1574,7 +1596,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
         int cs = 0;
         const int cs_min = getenv("SCMC_CLUSTER_MIN") ? atoi(getenv("SCMC_CLUSTER_MIN")) : 1;      // experiments: larger clusters than needed
         for (int c : {1, 2, 4, 8}) {
-            if (c < cs_min) continue;
+            if (c < cs_min || gen_id >= 4) continue;      // caller-supplied generators: streaming kernels only
             const int64_t n_own = (N + c - 1) / c;
             const size_t cap = (size_t)(n_own + 1 + 7) / 8 * 8;
             if (cap * per_site + (size_t)MAXL * 256 * w + 1024 <= (size_t)226 * 1024 && n_own + 1 <= 8191 && N >= c) { cs = c; break; }
@@ -1719,6 +1741,7 @@ int32_t scmc_destroy(scmc_t* h) {
     for (void* p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < scmc_handle::N_SCRATCH; i++) if (h->scratch[i]) cudaFree(h->scratch[i]);
     if (h->pinned) cudaFreeHost(h->pinned);
+    delete h->custom;
     for (int l = 0; l < 2; l++) {
         if (h->lane_stream[l]) cudaStreamDestroy(h->lane_stream[l]);
         if (h->ev_join[l]) cudaEventDestroy(h->ev_join[l]);

@@ -398,6 +398,8 @@ static int32_t dispatch_d(const scmc_handle* h, F&& f) {
             case 1: return with_nl(rt, ic<1>{}, ic<0>{});
             case 2: return h->onsite ? with_nl(rt, ic<2>{}, ic<1>{}) : with_nl(rt, ic<2>{}, ic<0>{});
             case 3: return with_nl(rt, ic<3>{}, ic<0>{});
+            case 4: if (set_custom_tables(*h->custom, h, h->device) != cudaSuccess) break; return f(rt, ic<4>{}, ic<1>{}, ic<MAXL>{});
+            case 5: if (set_custom_tables(*h->custom, h, h->device) != cudaSuccess) break; return f(rt, ic<5>{}, ic<1>{}, ic<MAXL>{});
         }
         return SCMC_ERR_ARG;
     };

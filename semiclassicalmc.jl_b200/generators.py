@@ -47,6 +47,34 @@ def _one_body(M, states):
     return out
 
 
+def _one_body_signed(M, states):
+    """Second-quantised one-body operator sum_pq M_pq c_p^dagger c_q on the occupation-number basis WITH the Jordan-Wigner sign."""
+    idx = {m: i for i, m in enumerate(states)}
+    d = len(states)
+    out = np.zeros((d, d), dtype=np.complex128)
+    below = lambda m, q: bin(m & ((1 << q) - 1)).count("1")
+    for col, m in enumerate(states):
+        for q in range(4):
+            if not (m >> q) & 1:
+                continue
+            emptied = m & ~(1 << q)
+            s_q = (-1) ** below(m, q)
+            for p in range(4):
+                if M[p, q] == 0 or (emptied >> p) & 1:
+                    continue
+                out[idx[emptied | (1 << p)], col] += M[p, q] * s_q * (-1) ** below(emptied, p)
+    return out
+
+
+def getGeneratorsSigned(n):
+    """The 16 generators in the TRUE fermionic representation of filling n (parton operator with its Jordan-Wigner sign, which the
+    reference's f omits, Generators.jl:39-51 / SURVEY Q1): for n = 2 they span su(4) in the antisymmetric square of C^4 (closed under
+    commutation, unlike the reference's tables).  Not a built-in of the library: hand them to Configuration(..., generators=...) /
+    scmc_create, which then runs its dense-table path for caller-supplied generators."""
+    states = fock_states(n)
+    return np.stack([_one_body_signed(np.kron(_PAULI[mu], _PAULI[nu]), states) for mu in range(4) for nu in range(4)])
+
+
 def getGenerators(n):
     """[16, d, d] complex; G[a] = sigma^mu (x) tau^nu, a = 4 mu + nu (0-based).  Like the reference's two methods, getGenerators(n::Int)
     (Generators.jl:2) and getGenerators(cfg) (Configuration.jl:108), the argument may be a filling or a Configuration."""

@@ -45,7 +45,8 @@ def oracle_mod():
 
 def make_oracle(cfg, oracle_mod, replica=None):
     """An oracle chain with the same tables as a product Configuration (and optionally the state of one replica)."""
-    o = oracle_mod.Oracle(cfg.interactionSites, cfg.interactionLabels, np.stack(cfg.interactions), cfg.onsiteInteraction, cfg.n)
+    o = oracle_mod.Oracle(cfg.interactionSites, cfg.interactionLabels, np.stack(cfg.interactions), cfg.onsiteInteraction, cfg.n,
+                          generators=cfg.generators)
     if replica is not None:
         o.set_state(cfg.get_state(replica, 1)[0])
     return o

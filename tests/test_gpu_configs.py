@@ -4,7 +4,7 @@ covered at full lattice size by test_gpu_parity.py::test_invariants_after_sweeps
 import numpy as np
 import pytest
 
-from conftest import NOTEBOOK_J, make_oracle
+from conftest import NOTEBOOK_J, make_oracle, random_symmetric_J
 
 pytestmark = pytest.mark.gpu
 
@@ -300,3 +300,57 @@ def test_C4_fp32_annealing_with_fp64_polish_reaches_1e8(scmc, golden):
     assert cfg.stream_epoch == 0
     scmc.runAnnealing_(cfg, 3.0, N_max=5, N_o=0, N_per_T=2)
     assert cfg.stream_epoch == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["signed_n2", "rotated_n1"])
+def test_caller_supplied_generator_tables(scmc, oracle_mod, which):
+    """generators are input data.  Tables that are not getGenerators(n) -- the n = 2 representation WITH the Jordan-Wigner sign the
+    reference's parton operator omits (closed under commutation, unlike the reference's), or a unitarily rotated n = 1 set -- run on the
+    library's dense-table path: expectations, energies and local fields against the oracle's dense contraction (Configuration.jl:166-194),
+    the FP64 chain step by step for both random streams, FP32 to 1e-5, optimisation sweeps lowering the energy."""
+    from scmc_b200 import generators as G
+    rng = np.random.default_rng(5)
+    if which == "signed_n2":
+        gens = G.getGeneratorsSigned(2)
+        # closure: every commutator stays in the span of the 16 generators (48 of 256 leave it for the reference's sign-less tables)
+        B = np.stack([g.ravel() for g in gens], axis=1)
+        bad = 0
+        for a in range(16):
+            for b in range(16):
+                c = (gens[a] @ gens[b] - gens[b] @ gens[a]).ravel()
+                bad += np.linalg.norm(c - B @ np.linalg.lstsq(B, c, rcond=None)[0]) > 1e-10
+        assert bad == 0
+        n, lattice, L = 2, "honeycomb", 4
+        Jm = [np.diag(np.linspace(-0.3, 0.4, 16)), random_symmetric_J(9)]
+    else:
+        A = rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))
+        U = np.linalg.qr(A)[0]
+        gens = np.stack([U @ g @ U.conj().T for g in G.getGenerators(1)])
+        n, lattice, L = 1, "triangular", 6
+        Jm = [random_symmetric_J(4)]
+    for precision, stream in ((64, 1), (64, 2), (32, 1)):
+        cfg = scmc.initializeCfg("nearest-neighbor", lattice, Jm, L, n, n_replicas=3, precision=precision, seed=77, replica_offset=2, stream=stream,
+                                 generators=gens)
+        assert cfg.info()["generator_table"] in (4, 5) and not cfg.info()["resident"] and not cfg.info()["tma"]
+        tol = 1e-12 if precision == 64 else 2e-5
+        o = make_oracle(cfg, oracle_mod, replica=1)
+        T, Tsq = cfg.get_T(1, squared=True)
+        To, Tsqo = o.get_T()
+        assert np.allclose(T, To, atol=tol * 10) and np.allclose(Tsq, Tsqo, atol=tol * 10)
+        assert abs(cfg.energies()[1] - o.energy()) < tol * 10 * cfg.nSites
+        assert np.allclose(cfg.local_field(1), np.array([o.local_field(i) for i in range(cfg.nSites)]), atol=tol * 20)
+        beta, sigma = np.array([1.0, 3.0, 9.0]), np.array([0.6, 0.3, 0.15])
+        acc, att = cfg.sweep(3, beta, sigma)
+        if precision == 64:
+            oc = make_oracle(cfg, oracle_mod)
+            oc.randomize_v1(77, 3)
+            a = oc.sweeps_colour(stream, 3, 2, cfg.colour, beta[1], sigma[1], 77, 3, 0)
+            assert a == acc[1] and np.allclose(cfg.get_state(1, 1)[0], oc.get_state(), atol=1e-10)
+        o2 = make_oracle(cfg, oracle_mod, replica=2)
+        assert abs(cfg.energies()[2] - o2.energy()) < tol * 20 * cfg.nSites
+        assert np.allclose(cfg.measure()[2, 0], o2.energy() / cfg.nSites, atol=tol * 20)
+        E0 = cfg.energies()
+        E1 = scmc.localOptimization_(cfg, n_sweeps=5)
+        assert np.all(E1 <= E0 + 1e-6 * cfg.nSites)
+        cfg.close()

@@ -32,10 +32,13 @@ def build(scmc, kind, precision, R=3, seed=1234, **kw):
         return scmc.initializeCfg("nearest-neighbor", "honeycomb", [np.eye(16)], 6, 1, n_replicas=R, precision=precision, seed=seed, **kw)
     if kind == "tri_n3":
         return scmc.initializeCfg("nearest-neighbor", "triangular", [random_symmetric_J(3)], 4, 3, n_replicas=R, precision=precision, seed=seed, **kw)
+    if kind == "tri_n3_onsite":      # n = 3 with an on-site matrix: (G^1)^2 = 9 (S(0,0) = 3 1), the constant on-site energy is N sum_a K^a c_a
+        return scmc.initializeCfg("nearest-neighbor", "triangular", [np.diag(np.linspace(0.5, -0.4, 16)), random_symmetric_J(3)], 4, 3,
+                                  n_replicas=R, precision=precision, seed=seed, **kw)
     raise KeyError(kind)
 
 
-KINDS = ["tri_notebook", "tri_dense_odd", "honey_n2_onsite", "tghbn", "honey_heis", "tri_n3"]
+KINDS = ["tri_notebook", "tri_dense_odd", "honey_n2_onsite", "tghbn", "honey_heis", "tri_n3", "tri_n3_onsite"]
 
 
 @pytest.mark.parametrize("precision", [64, 32])
