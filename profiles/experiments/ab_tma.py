@@ -12,7 +12,7 @@ J = np.diag([0, 0.2, 0.2, 0.2, -1, 0.2, 0.2, 0.2, -1, 0.2, 0.2, 0.2, -1, 0.2, 0.
 T = np.tile(np.geomspace(0.02, 2.0, 64), R // 64)
 beta, sigma = 1 / T, np.clip(0.6 * np.sqrt(T), 0.02, 60)
 for mode in modes:
-    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [J], 128, 1, n_replicas=R, precision=32, seed=1)
+    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [J], 128, 1, n_replicas=R, precision=32, seed=1, stream=int(os.environ.get("STREAM", "1")))
     cfg.set_sweep_mode(mode)
     cfg.sweep(2, beta, sigma, hits=HITS, want_counts=False)          # warm-up (thermalises a little, loads the module)
     best = 0.0

@@ -25,6 +25,9 @@ namespace scmc {
 #ifndef SCMC_TMA_BLOCKS
 #define SCMC_TMA_BLOCKS 5        // CTAs per SM the kernel is compiled for (128 threads each)
 #endif
+#ifndef SCMC_TMA_ABLATE
+#define SCMC_TMA_ABLATE 0        // timing ablations (profiles/README.md, round 2); 0 = production.  1: no mat-vec, 2: one neighbour, 3: no random numbers
+#endif
 constexpr int TMA_GAP = 8;       // runs closer than this many unused states are merged into one copy
 
 // ------------------------------------------------------------------------------------------------ planning (host)
@@ -161,7 +164,7 @@ struct TmaArgs {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <class R, int GEN, int Z, int STREAM>
+template <class R, int GEN, int Z, int STREAM, int HITS>
 __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A, const TmaArgs T) {
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
     static_assert(NP == NG, "fused density basis (16 entries) only");
@@ -245,12 +248,21 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
             if (s < n_it) issue(s, s);
     }
 
+    // HITS = 2: a thread's accepted hits of replica `it` (0..2) go into bits 2 it, 2 it + 1 of one register (TMA_RC <= 16 replicas per CTA);
+    // the per-replica sums over the warp and the atomics happen once, after the loop, instead of a reduce -> branch -> atomic chain per visit
+    static_assert(TMA_RC <= 16, "packed acceptance counts: 2 bits per replica");
+    uint32_t packed = 0;
+    char* const own = reinterpret_cast<char*>(M.psi + rb * M.Ns + p);      // own state of the chunk's first replica (plane 0)
+    const uint32_t rep_bytes = (uint32_t)M.Ns * VB;
     for (int it = 0; it < n_it; it++) {
         const int s = it % TMA_STAGES;
         const uint32_t parity = (it / TMA_STAGES) & 1;
         const int rl = sRep[it];
         const int64_t r = rb + rl;
         const R sigma = sSigma[it], nbeta = neg_beta_scaled(sBeta[it]);
+#if SCMC_TMA_ABLATE == 4                                   // timing only: the first two replicas' states are consumed over and over, no refill, no wait
+        if (it < TMA_STAGES)
+#endif
         mbar_wait(bar0 + 8 * s, parity);
         const unsigned char* st = smem + s * stage_bytes;
         R re[D], im[D], P[NP];
@@ -262,7 +274,7 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
 #pragma unroll
         for (int t = 0; t < NP; t++) P[t] = R(0);
 #pragma unroll
-        for (int k = 0; k < Z; k++) {
+        for (int k = 0; k < (SCMC_TMA_ABLATE == 2 ? 1 : Z); k++) {
             R nr[D], ni[D];
 #pragma unroll
             for (int v = 0; v < NPV; v++) {
@@ -274,17 +286,30 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
         // this warp is done with the stage: release it; warp 0 refills it with the states of replica it + STAGES once all warps have
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + 8 * (TMA_STAGES + s));
-        if (warp == 0 && it + TMA_STAGES < n_it) {
+        if (SCMC_TMA_ABLATE != 4 && warp == 0 && it + TMA_STAGES < n_it) {
             mbar_wait(bar0 + 8 * (TMA_STAGES + s), parity);
             issue(it + TMA_STAGES, s);
         }
         R Hq[NG];
+#if SCMC_TMA_ABLATE == 1
+#pragma unroll
+        for (int t = 0; t < NG; t++) Hq[t] = P[t] + sJt[t];
+#else
         field_from_sums_smem<1>(sJt, (const R(*)[NG])P, Hq);       // Hq = Jq . Psum
+#endif
         R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
         unsigned mine = 0;
         uint32_t uw[4];                                            // stream v2: acceptance-uniform words of the current group of four visits
-        for (int hit = 0; hit < A.hits; hit++) {
+        const int n_hits = HITS ? HITS : A.hits;                   // HITS = 2: the two hits of the reference's 2N-update sweep, unrolled
+#pragma unroll
+        for (int hit = 0; hit < n_hits; hit++) {
             R xr[D], xi[D], u, dE;
+#if SCMC_TMA_ABLATE == 3
+#pragma unroll
+            for (int k = 0; k < D; k++) { xr[k] = Hq[k] * R(0.01) + R(hit); xi[k] = Hq[k + D] * R(0.01); }
+            u = R(0.5);
+            if (false)
+#endif
             if constexpr (STREAM == 2) {
                 const uint64_t visit = A.visit0 + hit;
                 stream_v2_normals<R, D>(A.seed, site, (uint32_t)(A.roff + r), visit, xr, xi);
@@ -296,9 +321,19 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
             mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
         }
         if (!valid) mine = 0;
-        if (mine) store_psi<R, D>(M.psi + r * M.Ns + p, ps, re, im);
-        const unsigned tot = __reduce_add_sync(0xffffffffu, mine);
-        if (lane == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
+        if (mine) store_psi<R, D>(reinterpret_cast<V*>(own + (size_t)rl * rep_bytes), ps, re, im);
+        if constexpr (HITS == 2) {
+            packed |= mine << (2 * it);
+        } else {
+            const unsigned tot = __reduce_add_sync(0xffffffffu, mine);
+            if (lane == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
+        }
+    }
+    if constexpr (HITS == 2) {
+        for (int it = 0; it < n_it; it++) {
+            const unsigned tot = __reduce_add_sync(0xffffffffu, (packed >> (2 * it)) & 3u);
+            if (lane == 0 && tot) atomicAdd(A.acc + rb + sRep[it], (unsigned long long)tot);
+        }
     }
 }
 
@@ -330,7 +365,7 @@ bool tma_pass_available(const scmc_handle* h, const SweepArgs& A) {
     return h->tma.cls[A.colour].ok != 0;
 }
 
-template <int GEN, int Z, int STREAM>
+template <int GEN, int Z, int STREAM, int HITS>
 static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t stream) {
     using R = float;
     auto M = make_model_t<R>(h);
@@ -345,7 +380,7 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
     const size_t smem = tma_smem_bytes(h);
     static size_t attr_set[64] = {0};      // per device: largest dynamic shared-memory size opted into so far
     if (attr_set[h->device & 63] < smem) {
-        SCMC_CK(cudaFuncSetAttribute(k_sweep_tma_psi<R, GEN, Z, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCMC_CK(cudaFuncSetAttribute(k_sweep_tma_psi<R, GEN, Z, STREAM, HITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[h->device & 63] = smem;
     }
     for (int64_t y0 = 0; y0 < A.rcount; y0 += (int64_t)65535 * rc) {
@@ -353,7 +388,7 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
         B.r0 = A.r0 + y0; B.rcount = std::min<int64_t>((int64_t)65535 * rc, A.rcount - y0);
         B.Jqt = h->d_Jqt; B.Jt = h->d_Jt;
         const dim3 grid((unsigned)C.n_tiles, (unsigned)((B.rcount + rc - 1) / rc));
-        k_sweep_tma_psi<R, GEN, Z, STREAM><<<grid, TMA_TILE, smem, stream>>>(M, B, T);
+        k_sweep_tma_psi<R, GEN, Z, STREAM, HITS><<<grid, TMA_TILE, smem, stream>>>(M, B, T);
         h->launches++;
     }
     SCMC_CK(cudaGetLastError());
@@ -363,12 +398,15 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
 
 int32_t launch_colour_pass_tma(scmc_handle* h, const SweepArgs& A, cudaStream_t stream) {
     if (A.rcount == 0) return SCMC_OK;
-    if (A.stream == 2) {
-        if (h->gen_id == 1) return h->z == 6 ? launch_one<1, 6, 2>(h, A, stream) : launch_one<1, 3, 2>(h, A, stream);
-        return h->z == 6 ? launch_one<3, 6, 2>(h, A, stream) : launch_one<3, 3, 2>(h, A, stream);
-    }
-    if (h->gen_id == 1) return h->z == 6 ? launch_one<1, 6, 1>(h, A, stream) : launch_one<1, 3, 1>(h, A, stream);
-    return h->z == 6 ? launch_one<3, 6, 1>(h, A, stream) : launch_one<3, 3, 1>(h, A, stream);
+    static const bool unroll2 = !(getenv("SCMC_TMA_UNROLL2") && atoi(getenv("SCMC_TMA_UNROLL2")) == 0);
+    auto go = [&](auto gen, auto zz) -> int32_t {
+        constexpr int GEN = decltype(gen)::value, Z = decltype(zz)::value;
+        if (A.hits == 2 && unroll2) return A.stream == 2 ? launch_one<GEN, Z, 2, 2>(h, A, stream) : launch_one<GEN, Z, 1, 2>(h, A, stream);
+        return A.stream == 2 ? launch_one<GEN, Z, 2, 0>(h, A, stream) : launch_one<GEN, Z, 1, 0>(h, A, stream);
+    };
+    using I1 = std::integral_constant<int, 1>; using I3 = std::integral_constant<int, 3>; using I6 = std::integral_constant<int, 6>;
+    if (h->gen_id == 1) return h->z == 6 ? go(I1{}, I6{}) : go(I1{}, I3{});
+    return h->z == 6 ? go(I3{}, I6{}) : go(I3{}, I3{});
 }
 
 }  // namespace scmc
