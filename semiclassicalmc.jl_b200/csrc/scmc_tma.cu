@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
             if constexpr (STREAM == 2) {
                 const uint64_t visit = A.visit0 + hit;
                 stream_v2_normals<R, D>(A.seed, site, (uint32_t)(A.roff + r), visit, xr, xi);
-                if (hit == 0 || ((uint32_t)visit & 3u) == 0) stream_v2_uniform_words(A.seed, site, (uint32_t)(A.roff + r), visit >> 2, uw);
+                // HITS = 2: visit0 = 2 x sweep is even, so the second hit never opens a new group of four visits
+                if (hit == 0 || (HITS != 2 && ((uint32_t)visit & 3u) == 0)) stream_v2_uniform_words(A.seed, site, (uint32_t)(A.roff + r), visit >> 2, uw);
                 u = unit_uniform(pick_word(uw, (uint32_t)visit & 3u), R(0));
             } else {
                 stream_v1<R, D>(A.seed, site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
