@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--restarts", type=int, default=512)
     ap.add_argument("--L", type=int, default=36)
     ap.add_argument("--N-max", type=int, default=16000)
-    ap.add_argument("--N-o", type=int, default=200)
+    ap.add_argument("--N-o", type=int, default=600)      # 300 in FP32 + 300 in FP64 (polishFP64_): |min E/N + 3.6| < 1e-8
     ap.add_argument("--precision", type=int, default=32)
     a = ap.parse_args()
     import torch
