@@ -178,7 +178,8 @@ typedef struct {
     double T_i, T_fac;          /* runAnnealing! kwargs (MonteCarlo.jl:112-129) */
     int64_t N_max, N_per_T, min_acc_per_site;
     double min_accrate, sigma_min, sigma0;
-    int32_t hits, reserved;
+    int32_t hits;
+    int32_t log_rate;           /* > 0: E/N and beta of every replica are logged every log_rate sweeps (energy_log / beta_log below) */
     uint64_t seed;
 } scmc_anneal_params;
 typedef struct {
@@ -186,6 +187,10 @@ typedef struct {
     double* beta;               /* [R] final inverse temperatures */
     double* sigma;              /* [R] final cone widths */
     int64_t* sweeps;            /* [R] annealing sweeps performed per replica */
+    double* energy_log;         /* [n_log_cap][R] E/N series (push!(energy, E / N), MonteCarlo.jl:158-159, on a grid of log_rate sweeps) or NULL */
+    double* beta_log;           /* [n_log_cap][R] beta series or NULL */
+    int64_t n_log_cap;          /* rows the two logs can hold */
+    int64_t n_log;              /* out: rows written (replicas that stopped earlier repeat their final values) */
 } scmc_anneal_results;
 /* cooling loop of runAnnealing! (MonteCarlo.jl:131-204), every replica with its own beta / sigma / stopping flag (device-side
  * inside the resident kernel where that kernel is the preferred one, one CTA or one cluster per replica, else one controller kernel

@@ -471,10 +471,11 @@ end
 
 struct AnnealParams
     T_i::Float64; T_fac::Float64; N_max::Int64; N_per_T::Int64; min_acc_per_site::Int64
-    min_accrate::Float64; sigma_min::Float64; sigma0::Float64; hits::Int32; reserved::Int32; seed::UInt64
+    min_accrate::Float64; sigma_min::Float64; sigma0::Float64; hits::Int32; log_rate::Int32; seed::UInt64
 end
 mutable struct AnnealResults
     E::Ptr{Float64}; beta::Ptr{Float64}; sigma::Ptr{Float64}; sweeps::Ptr{Int64}
+    energy_log::Ptr{Float64}; beta_log::Ptr{Float64}; n_log_cap::Int64; n_log::Int64
 end
 
 # runAnnealing!(cfg, T_i, filename; ...) (src/MonteCarlo.jl:112-238): cooling loop, N_o optimisation sweeps, checkpoint! + f["state"] at the
@@ -489,7 +490,7 @@ function runAnnealing!(cfg::Configuration, T_i, filename::String; T_fac = 0.98, 
     seed = newEpoch!(cfg, false)
     GC.@preserve E β σs sweeps begin
         p = AnnealParams(T_i, T_fac, N_max, N_per_T, min_acc_per_site, min_accrate, σ_min / SQRT2, σ / SQRT2, hits, 0, seed)
-        out = AnnealResults(pointer(E), pointer(β), pointer(σs), pointer(sweeps))
+        out = AnnealResults(pointer(E), pointer(β), pointer(σs), pointer(sweeps), C_NULL, C_NULL, 0, 0)
         check(ccall((:scmc_anneal, LIB), Int32, (Ptr{Cvoid}, Ref{AnnealParams}, Ref{AnnealResults}), cfg.handle, p, out))
         N_o > 0 && check(ccall((:scmc_optimize, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}), cfg.handle, N_o, E))
     end
@@ -622,7 +623,7 @@ function runAnnealing!(m::MultiConfiguration, T_i; T_fac = 0.98, N_max::Int = 10
     E = zeros(R); β = zeros(R); σs = zeros(R); sweeps = zeros(Int64, R)
     GC.@preserve E β σs sweeps begin
         p = AnnealParams(T_i, T_fac, N_max, N_per_T, min_acc_per_site, min_accrate, σ_min / SQRT2, σ / SQRT2, hits, 0, m.seed)
-        out = AnnealResults(pointer(E), pointer(β), pointer(σs), pointer(sweeps))
+        out = AnnealResults(pointer(E), pointer(β), pointer(σs), pointer(sweeps), C_NULL, C_NULL, 0, 0)
         check(ccall((:scmc_multi_anneal, LIB), Int32, (Ptr{Cvoid}, Ref{AnnealParams}, Ref{AnnealResults}), m.handle, p, out))
         N_o > 0 && check(ccall((:scmc_multi_optimize, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}), m.handle, N_o, E))
     end

@@ -31,11 +31,12 @@ class RunResults(C.Structure):
 class AnnealParams(C.Structure):
     _fields_ = [("T_i", C.c_double), ("T_fac", C.c_double), ("N_max", C.c_int64), ("N_per_T", C.c_int64),
                 ("min_acc_per_site", C.c_int64), ("min_accrate", C.c_double), ("sigma_min", C.c_double), ("sigma0", C.c_double),
-                ("hits", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64)]
+                ("hits", C.c_int32), ("log_rate", C.c_int32), ("seed", C.c_uint64)]
 
 
 class AnnealResults(C.Structure):
-    _fields_ = [("E", c_dp), ("beta", c_dp), ("sigma", c_dp), ("sweeps", c_lp)]
+    _fields_ = [("E", c_dp), ("beta", c_dp), ("sigma", c_dp), ("sweeps", c_lp), ("energy_log", c_dp), ("beta_log", c_dp), ("n_log_cap", C.c_int64),
+                ("n_log", C.c_int64)]
 
 
 # symbol -> argtypes; every symbol of include/scmc.h (checked by tests/test_abi.py)

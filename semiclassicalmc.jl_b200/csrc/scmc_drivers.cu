@@ -596,6 +596,21 @@ int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results*
     const unsigned gR = grid_for(R, 128);
     int n_active = (int)std::min<int64_t>(R, 1 << 30);
     const int check_every = 16;
+    // energy / beta log (push!(energy, E / N); push!(betas, beta), MonteCarlo.jl:158-159): every replica follows its own schedule on the device,
+    // so the series is taken on a fixed grid, every log_rate sweeps, for all replicas at once (stopped replicas repeat their final values)
+    const int64_t log_rate = (p->log_rate > 0 && out->energy_log && out->beta_log) ? p->log_rate : 0;
+    int64_t n_log = 0;
+    std::vector<char> blog(R * h->esz());
+    auto log_point = [&]() -> int32_t {
+        if (n_log >= out->n_log_cap) return SCMC_OK;
+        SCMC_TRY(launch_measure(h, h->obs));
+        SCMC_CK(cudaMemcpy2DAsync(out->energy_log + n_log * R, 8, h->obs, SCMC_NOBS * 8, 8, R, cudaMemcpyDeviceToHost, h->stream));
+        SCMC_CK(cudaMemcpyAsync(blog.data(), h->beta, blog.size(), cudaMemcpyDeviceToHost, h->stream));
+        SCMC_CK(cudaStreamSynchronize(h->stream));
+        for (int64_t r = 0; r < R; r++) out->beta_log[n_log * R + r] = h->prec == 64 ? ((double*)blog.data())[r] : (double)((float*)blog.data())[r];
+        n_log++;
+        return SCMC_OK;
+    };
     // Device-side driver: when every replica lives in ONE CTA of the psi-family resident kernel, the whole cooling loop
     // (acceptance window, beta / sigma updates, stop flag) runs inside the persistent kernel, `chunk` sweeps per launch.
     const bool psi_fam = uses_psi_gather(h);
@@ -603,13 +618,15 @@ int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results*
     if (device_side) {
         const int64_t n_total = p->N_max - 1;
         for (int64_t launched = 0; launched < n_total && n_active > 0;) {
-            const int64_t chunk = std::min<int64_t>(512, n_total - launched);
+            int64_t chunk = std::min<int64_t>(512, n_total - launched);
+            if (log_rate) chunk = std::min<int64_t>(chunk, log_rate - launched % log_rate);
             SCMC_CK(cudaMemsetAsync(dnact.p, 0, sizeof(int), h->stream));
             SCMC_TRY(launch_resident_anneal(h, chunk, p->hits, p->seed, att_per_sweep, min_accepted, 1.0 / p->T_fac, p->min_accrate, p->sigma_min,
                                             p->N_per_T, n_total, dsat.as<int64_t>(), ddone.as<int64_t>(), dnact.as<int>()));
             SCMC_CK(cudaMemcpyAsync(&n_active, dnact.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             SCMC_CK(cudaStreamSynchronize(h->stream));
             launched += chunk;
+            if (log_rate && launched % log_rate == 0) SCMC_TRY(log_point());
         }
     }
     for (int64_t sweep = 1; !device_side && sweep < p->N_max && n_active > 0; sweep++) {
@@ -631,7 +648,9 @@ int32_t scmc_anneal(scmc_t* h, const scmc_anneal_params* p, scmc_anneal_results*
             SCMC_CK(cudaMemcpyAsync(&n_active, dnact.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             SCMC_CK(cudaStreamSynchronize(h->stream));
         }
+        if (log_rate && sweep % log_rate == 0) SCMC_TRY(log_point());
     }
+    out->n_log = n_log;
     SCMC_CK(cudaMemsetAsync(h->active, 1, R, h->stream));
     if (out->E) SCMC_TRY(scmc_energy(h, out->E));
     std::vector<char> buf(R * h->esz());

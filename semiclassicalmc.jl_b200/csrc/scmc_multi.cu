@@ -284,13 +284,38 @@ int32_t scmc_multi_run_metropolis(scmc_multi_t* m, const scmc_run_params* p, scm
 // cooling loop of runAnnealing! on every device at once; result arrays [R_total]
 int32_t scmc_multi_anneal(scmc_multi_t* m, const scmc_anneal_params* p, scmc_anneal_results* out) {
     SCMC_ARG(m && p && out, "null argument");
-    return fan_out(m, [&](int i) {
-        const int64_t f = m->first[i];
+    const bool logs = p->log_rate > 0 && out->energy_log && out->beta_log && out->n_log_cap > 0;
+    std::vector<std::vector<double>> el(m->n_dev), bl(m->n_dev);
+    std::vector<int64_t> nl(m->n_dev, 0);
+    SCMC_TRY(fan_out(m, [&](int i) {
+        const int64_t f = m->first[i], c = m->count[i];
         scmc_anneal_results o{};
         o.E = out->E ? out->E + f : nullptr; o.beta = out->beta ? out->beta + f : nullptr;
         o.sigma = out->sigma ? out->sigma + f : nullptr; o.sweeps = out->sweeps ? out->sweeps + f : nullptr;
-        return scmc_anneal(m->h[i], p, &o);
-    });
+        if (logs) {
+            el[i].assign((size_t)out->n_log_cap * c, 0.0); bl[i].assign((size_t)out->n_log_cap * c, 0.0);
+            o.energy_log = el[i].data(); o.beta_log = bl[i].data(); o.n_log_cap = out->n_log_cap;
+        }
+        const int32_t st = scmc_anneal(m->h[i], p, &o);
+        nl[i] = o.n_log;
+        return st;
+    }));
+    out->n_log = 0;
+    if (logs) {
+        // devices whose replicas all stopped early wrote fewer rows: pad with their last row so that every replica has the same grid
+        for (int i = 0; i < m->n_dev; i++) out->n_log = std::max(out->n_log, nl[i]);
+        for (int i = 0; i < m->n_dev; i++) {
+            const int64_t f = m->first[i], c = m->count[i];
+            for (int64_t r = 0; r < out->n_log; r++) {
+                const int64_t src = nl[i] ? std::min(r, nl[i] - 1) : -1;
+                for (int64_t q = 0; q < c; q++) {
+                    out->energy_log[r * m->R_total + f + q] = src >= 0 ? el[i][(size_t)src * c + q] : 0.0;
+                    out->beta_log[r * m->R_total + f + q] = src >= 0 ? bl[i][(size_t)src * c + q] : 0.0;
+                }
+            }
+        }
+    }
+    return SCMC_OK;
 }
 
 }  // extern "C"

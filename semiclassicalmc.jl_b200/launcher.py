@@ -114,6 +114,8 @@ def launchAnnealing_(filename, model, n, latticename, L, J, T_i, *, T_fac=0.98, 
         for r in range(n_restarts):
             stem, _, ext = str(filename).rpartition(".")
             fn = filename(r) if callable(filename) else (str(filename) if n_restarts == 1 else f"{stem}_r{r}.{ext}")
-            _io.checkpointH5_(fn, cfg, int(res["sweeps"][r]), [float(res["beta"][r])], [float(res["E"][r] / cfg.nSites)], res["sigma"], replica=r)
+            k = int(res["series_length"][r])      # this restart's E/N and beta series (MonteCarlo.jl:158-159, on a grid of log_rate sweeps) + the final values
+            _io.checkpointH5_(fn, cfg, int(res["sweeps"][r]), np.append(res["beta_series"][:k, r], res["beta"][r]),
+                              np.append(res["energy_series"][:k, r], res["E"][r] / cfg.nSites), res["sigma"], replica=r)
             res["files"].append(fn)
     return res

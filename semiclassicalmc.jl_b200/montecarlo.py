@@ -221,19 +221,30 @@ def polishFP64_(cfg, n_sweeps, batch=1024, write_back=True):
 
 def runAnnealing_(cfg, T_i, filename=None, *, T_fac=0.98, N_max=10_000_000, N_o=0, N_per_T=10000, min_acc_per_site=100,
                   min_accrate=1e-5, checkpoint_rate=100000, σ_min=0.05, verbose=False, βs=None, energy=None, current_sweep=1,
-                  σ=60.0, σ_convention="unit", hits=2, polish_fp64="auto"):
+                  σ=60.0, σ_convention="unit", hits=2, polish_fp64="auto", log_rate="auto"):
     """runAnnealing! (MonteCarlo.jl:112-238): cooling loop then N_o optimisation sweeps, every replica independently.
     polish_fp64 ("auto": when cfg is FP32 and N_o > 0): the optimisation sweeps and the final energies are done in FP64 (polishFP64_), so that
-    an FP32 annealing run reaches the exact ground-state energy to 1e-8 as an FP64 one does.  `energy` / `βs` receive the final E/N and
-    beta of replica 0 (the per-sweep series of MonteCarlo.jl:158-159 is not kept: every replica follows its own schedule on the device)."""
+    an FP32 annealing run reaches the exact ground-state energy to 1e-8 as an FP64 one does.
+    log_rate: E/N and beta of every replica are logged every `log_rate` sweeps (the reference pushes them every sweep, MonteCarlo.jl:158-159;
+    every replica follows its own cooling schedule on the device, so the series is taken on a fixed grid; "auto" = max(N_per_T, N_max / 2048),
+    0 = off) -> `energy_series` / `beta_series` [n, R] in the result; the caller's `energy` / `βs` lists get replica 0's series and the final values."""
     R = cfg.n_replicas
     scale = sigma_scale(σ_convention)
     _new_epoch(cfg, resumed=False)
+    if log_rate == "auto":
+        log_rate = max(int(N_per_T), -(-int(N_max) // 2048))
+    log_rate = int(min(max(int(log_rate), 0), 2 ** 31 - 1))
+    n_cap = int(N_max) // log_rate + 1 if log_rate else 0
+    elog = np.zeros((max(n_cap, 1), R)); blog = np.zeros((max(n_cap, 1), R))
     p = _lib.AnnealParams(float(T_i), float(T_fac), int(N_max), int(N_per_T), int(min_acc_per_site), float(min_accrate),
-                          float(σ_min) / scale, float(σ) / scale, int(hits), 0, C.c_uint64(stream_seed(cfg)))
+                          float(σ_min) / scale, float(σ) / scale, int(hits), log_rate, C.c_uint64(stream_seed(cfg)))
     E = np.zeros(R); beta = np.zeros(R); sig = np.zeros(R); sweeps = np.zeros(R, dtype=np.int64)
-    out = _lib.AnnealResults(_lib.dptr(E), _lib.dptr(beta), _lib.dptr(sig), _lib.lptr(sweeps))
+    out = _lib.AnnealResults(_lib.dptr(E), _lib.dptr(beta), _lib.dptr(sig), _lib.lptr(sweeps), _lib.dptr(elog) if log_rate else None,
+                             _lib.dptr(blog) if log_rate else None, n_cap, 0)
     _lib.check(cfg._lib.scmc_anneal(cfg._h, C.byref(p), C.byref(out)))
+    n_log = int(out.n_log)
+    # the grid stops when the last replica stops; a replica's own series ends at its own last sweep
+    keep = [int(min(n_log, sweeps[r] // log_rate)) if log_rate else 0 for r in range(R)]
     cfg.sweep_counter = max(cfg.sweep_counter, int(sweeps.max()) + 1)
     E_sa = E.copy()
     polished = False
@@ -248,12 +259,13 @@ def runAnnealing_(cfg, T_i, filename=None, *, T_fac=0.98, N_max=10_000_000, N_o=
         else:
             _lib.check(cfg._lib.scmc_optimize(cfg._h, int(N_o), _lib.dptr(E)))
     if energy is not None:
-        energy.append(float(E[0] / cfg.nSites))
+        energy.extend(elog[:keep[0], 0].tolist()); energy.append(float(E[0] / cfg.nSites))
     if βs is not None:
-        βs.append(float(beta[0]))
+        βs.extend(blog[:keep[0], 0].tolist()); βs.append(float(beta[0]))
     if verbose and filename:
         print(f"{filename}: Finished calculation. E/N = {E[0] / cfg.nSites}", flush=True)
-    return dict(E=E, E_annealed=E_sa, beta=beta, sigma=sig * scale, sweeps=sweeps, polished_fp64=polished)
+    return dict(E=E, E_annealed=E_sa, beta=beta, sigma=sig * scale, sweeps=sweeps, polished_fp64=polished, log_rate=log_rate,
+                energy_series=elog[:n_log], beta_series=blog[:n_log], series_length=np.array(keep))
 
 
 def localOptimization_(cfg, E=None, i=None, n_sweeps=1):

@@ -31,7 +31,7 @@ def test_struct_layouts_match_header(scmc):
     assert ctypes.sizeof(L.RunParams) == 8 * 3 + 4 * 2 + 8 * 2 + 8 * 3
     assert ctypes.sizeof(L.RunResults) == 8 * 5
     assert ctypes.sizeof(L.AnnealParams) == 8 * 8 + 4 * 2 + 8
-    assert ctypes.sizeof(L.AnnealResults) == 8 * 4
+    assert ctypes.sizeof(L.AnnealResults) == 8 * 8
 
 
 def test_no_cpu_fallback(scmc):

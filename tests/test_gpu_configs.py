@@ -354,3 +354,33 @@ def test_caller_supplied_generator_tables(scmc, oracle_mod, which):
         E1 = scmc.localOptimization_(cfg, n_sweeps=5)
         assert np.all(E1 <= E0 + 1e-6 * cfg.nSites)
         cfg.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,precision", [(6, 64), (48, 32)])
+def test_annealing_energy_and_beta_series(scmc, tmp_path, L, precision):
+    """runAnnealing! logs E/N and beta while it cools (push!, MonteCarlo.jl:158-159).  Every replica follows its own schedule on the device, so the
+    series comes on a grid of log_rate sweeps for all replicas -- from the persistent kernel (L = 6: whole loop on the device) and from the
+    host-driven controller (L = 48) alike: beta is non-decreasing and ends at the final beta, the energy falls, the last logged energy of a replica
+    that stopped is its annealed energy, and launchAnnealing_ stores each restart's own series in its file."""
+    R = 6
+    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], L, 1, n_replicas=R, precision=precision, seed=12)
+    energy, betas = [], []
+    res = scmc.runAnnealing_(cfg, 3.0, T_fac=0.9, N_max=600, N_o=0, N_per_T=20, min_acc_per_site=4, min_accrate=0.02, σ_min=0.05, log_rate=10,
+                             energy=energy, βs=betas)
+    es, bs, n = res["energy_series"], res["beta_series"], res["series_length"]
+    assert es.shape == bs.shape and es.shape[1] == R and es.shape[0] >= n.max() and n.min() >= 3
+    for r in range(R):
+        k = n[r]
+        assert k == min(es.shape[0], res["sweeps"][r] // 10)
+        assert np.all(np.diff(bs[:k, r]) >= -1e-12) and bs[0, r] >= 1 / 3.0 - 1e-6 and bs[k - 1, r] <= res["beta"][r] * (1 + 1e-6)
+        assert es[k - 1, r] < es[0, r]
+        if res["sweeps"][r] % 10 == 0 and res["sweeps"][r] < 599:                 # stopped exactly on a grid point: the log holds the annealed energy
+            assert abs(es[k - 1, r] - res["E_annealed"][r] / cfg.nSites) < (1e-12 if precision == 64 else 1e-5)
+    assert len(energy) == n[0] + 1 and energy[-1] == res["E"][0] / cfg.nSites and betas[-1] == res["beta"][0]
+    if L == 6:
+        ann = scmc.launchAnnealing_(str(tmp_path / "sa.h5"), "nearest-neighbor", 1, "triangular", 6, [NOTEBOOK_J], 3.0, N_max=300, N_per_T=20,
+                                    min_acc_per_site=5, seed=5, n_restarts=2)
+        one = scmc.readCheckpointH5(ann["files"][1])
+        assert one["energy"].shape == one["βs"].shape and one["energy"].shape[0] == ann["series_length"][1] + 1
+        assert one["energy"][-1] == ann["E"][1] / 36
