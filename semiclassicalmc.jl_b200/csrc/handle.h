@@ -154,7 +154,7 @@ int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint
                                double beta_fac, double min_accrate, double sigma_min, int64_t n_per_T, int64_t n_total,
                                int64_t* d_sweeps_at_T, int64_t* d_sweeps_done, int* d_n_active);
 // implemented in scmc_tma.cu
-constexpr int TMA_TILE = 128, TMA_MAX_RUNS = 16, TMA_STAGES = 2, TMA_RC = 16;   // TMA_RC: replicas one CTA walks over (<= 32)
+constexpr int TMA_TILE = 128, TMA_MAX_RUNS = 16, TMA_STAGES = 2, TMA_RC = 128;   // TMA_RC: most replicas one CTA walks over
 void plan_tma(scmc_handle* h, const std::vector<int32_t>& col_list, const std::vector<int32_t>& nb /* [z][N] permuted neighbour by permuted site */);
 bool tma_pass_available(const scmc_handle* h, const SweepArgs& A);
 int32_t launch_colour_pass_tma(scmc_handle* h, const SweepArgs& A, cudaStream_t stream);

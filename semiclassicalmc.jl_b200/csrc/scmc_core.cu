@@ -1189,7 +1189,7 @@ int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma) 
 // Which arithmetic family the production (stream-driven) sweeps of this handle use.  It depends on the model only -- never on
 // the replica count or the number of sweeps per call -- so that a replica's chain is identical however replicas are sharded.
 bool uses_psi_gather(const scmc_handle* h) {
-    if (h->sweep_mode == 3 || h->sweep_mode == 4 || h->sweep_mode == 5) return h->n_labels == 1 && h->gen_id <= 3;
+    if (h->sweep_mode == 3 || h->sweep_mode == 4 || h->sweep_mode == 5 || h->sweep_mode == 6) return h->n_labels == 1 && h->gen_id <= 3;
     if (h->sweep_mode == 1 || h->sweep_mode == 2) return false;
     return h->gen_id <= 3 && h->n_labels == 1 && (h->d == 4 || h->onsite) && !h->res_family_T;      // measured: d = 6 without on-site term is on par / slightly faster with T-gather
 }
@@ -1779,7 +1779,7 @@ int32_t scmc_set_stream_version(scmc_t* h, int32_t version) {
 
 int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch) {
     SCMC_ARG(h, "null handle");
-    SCMC_ARG(mode >= 0 && mode <= 5 && batch >= 0, "scmc_set_sweep_mode: bad mode / batch");
+    SCMC_ARG(mode >= 0 && mode <= 6 && batch >= 0, "scmc_set_sweep_mode: bad mode / batch");
     h->sweep_mode = mode; h->batch = batch;
     return SCMC_OK;
 }

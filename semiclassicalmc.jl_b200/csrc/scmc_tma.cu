@@ -28,6 +28,9 @@ namespace scmc {
 #ifndef SCMC_TMA_ABLATE
 #define SCMC_TMA_ABLATE 0        // timing ablations (profiles/README.md, round 2); 0 = production.  1: no mat-vec, 2: one neighbour, 3: no random numbers
 #endif
+#ifndef SCMC_TC_PRE
+#define SCMC_TC_PRE 1            // tensor-core variant: generate both hits' random numbers between the MMA issue and the wait for its result
+#endif
 constexpr int TMA_GAP = 8;       // runs closer than this many unused states are merged into one copy
 
 // ------------------------------------------------------------------------------------------------ planning (host)
@@ -156,6 +159,53 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ tcgen05 primitives (TC variant)
+// The 16x16 mat-vec of a visit for the 128 sites of a tile is ONE tensor-core tile D[128x16] = A[128x16] B[16x16]^T (kind::tf32, 3xTF32 split,
+// FP32 accumulation in tensor memory).  A comes from TMEM (tcgen05.st: a thread's TMEM lane is its site), B = Jq from shared memory (K-major,
+// no swizzle, 8-row x 16-byte core matrices), D is read back with tcgen05.ld.  Every warp issues its own MMAs over the CTA's A region into
+// its own D columns and reads back only its 32 lanes, so the warps of a CTA never wait for each other (rows of other warps that a warp's
+// MMA reads may be half-written: they land in D lanes nobody reads).  A shared D region with the other warps' lanes masked out
+// (disable-output-lane mask) was measured slower: MMAs into one D region are ordered behind each other.  Checked stand-alone in profiles/microbench/tc_matvec.cu.
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+                 "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]),
+                   "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    return leader != 0;
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// shared-memory matrix descriptor: start address, leading (K chunk) and stride (8-row group) byte offsets, sm_100 descriptor version, no swizzle
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+constexpr uint32_t TC_LBO = 256, TC_SBO = 128;                       // Jq in core-matrix order: chunk (b / 4) * 256 + group (a / 8) * 128 + (a % 8) * 16 + (b % 4) * 4
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);      // D = F32, A = B = TF32, K-major, N = 16, M = 128
+// Tensor memory of a CTA: A_hi 16 + A_lo 16 + 4 warps x D 16 = 96 columns, taken as THREE allocations of 32 columns (allocations are powers of
+// two: one of 128 would cap the SM at 4 CTAs; equal-sized pieces cannot fragment the 512 columns, 5 CTAs x 3 = 15 of 16 pieces).
+constexpr int TC_TMEM_COLS = 32, TC_TMEM_ALLOCS = 3;
+#ifndef SCMC_TC_BLOCKS
+#define SCMC_TC_BLOCKS 5         // CTAs per SM the tensor-core variant is compiled for
+#endif
+
 struct TmaArgs {
     const uint4* meta;       // [tiles][128][2]
     const uint2* runs;       // [tiles][TMA_MAX_RUNS]
@@ -164,20 +214,22 @@ struct TmaArgs {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <class R, int GEN, int Z, int STREAM, int HITS>
-__global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A, const TmaArgs T) {
+template <class R, int GEN, int Z, int STREAM, int HITS, bool TC>
+__global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCKS) k_sweep_tma_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A, const TmaArgs T) {
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
     static_assert(NP == NG, "fused density basis (16 entries) only");
     using V = vec4<R>;
     constexpr uint32_t VB = sizeof(V);
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t plane_bytes = (uint32_t)T.cap * VB, stage_bytes = NPV * plane_bytes;
-    R* sJt = reinterpret_cast<R*>(smem + TMA_STAGES * stage_bytes);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sJt + NG * NG);      // full[0..S), empty[0..S)
-    int32_t* sRep = reinterpret_cast<int32_t*>(bars + 2 * TMA_STAGES);                    // replicas of this CTA that are alive
+    R* sJt = reinterpret_cast<R*>(smem + TMA_STAGES * stage_bytes);                      // TC: Jq_hi, Jq_lo in core-matrix order (2 x 1 KB)
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sJt + (TC ? 2 : 1) * NG * NG);      // full[0..S), empty[0..S), TC: one per warp
+    int32_t* sRep = reinterpret_cast<int32_t*>(bars + 2 * TMA_STAGES + TMA_TILE / 32);    // replicas of this CTA that are alive
     R* sBeta = reinterpret_cast<R*>(sRep + TMA_RC);
     R* sSigma = sBeta + TMA_RC;
     __shared__ int s_nit;
+    __shared__ uint32_t s_tmem[4];
+    static_assert(!TC || (std::is_same<R, float>::value && D == 4), "tensor-core mat-vec: FP32, d = 4");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = T.first + blockIdx.x;
@@ -199,7 +251,25 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
     const bool valid = (m0.w >> 16) != 0;
     const uint32_t site = m1.x, p = m1.y;
 
-    for (int t = tid; t < NG * NG; t += TMA_TILE) sJt[t] = ((const R*)A.Jqt)[t];
+    if constexpr (TC) {
+        if (warp == 0) {                                           // tensor memory of this CTA (freed by the same warp at the end)
+#pragma unroll
+            for (int q = 0; q < TC_TMEM_ALLOCS; q++)
+                asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem[q])), "n"(TC_TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        for (int t = tid; t < NG * NG; t += TMA_TILE) {            // Jqt[b][a] = Jq[a][b] -> B[n = a][k = b], split into TF32 head and tail
+            const int b = t / NG, a = t % NG;
+            const float j = (float)((const R*)A.Jqt)[t];
+            const float hi = __uint_as_float(__float_as_uint(j) & 0xFFFFE000u);
+            const uint32_t o = ((b / 4) * TC_LBO + (a / 8) * TC_SBO + (a % 8) * 16 + (b % 4) * 4) / 4;
+            reinterpret_cast<float*>(sJt)[o] = hi;
+            reinterpret_cast<float*>(sJt)[NG * NG + o] = j - hi;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // written by the generic proxy, read by the tensor core
+    } else {
+        for (int t = tid; t < NG * NG; t += TMA_TILE) sJt[t] = ((const R*)A.Jqt)[t];
+    }
     if (tid < NPV * TMA_STAGES) {                                  // the all-zero slot of every plane of every stage (never a copy target)
         V zv; zv.x = zv.y = zv.z = zv.w = R(0);
         *reinterpret_cast<V*>(smem + tid * plane_bytes + zero_off) = zv;
@@ -217,10 +287,19 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
             s_nit = __popc(mask);
 #pragma unroll
             for (int s = 0; s < TMA_STAGES; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + TMA_STAGES + s), TMA_TILE / 32); }
+            if (TC)
+                for (int w = 0; w < TMA_TILE / 32; w++) mbar_init(smem_u32(bars + 2 * TMA_STAGES + w), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
+    if (TC) tc_fence_before();
     __syncthreads();
+    if (TC) tc_fence_after();
+    // TC: TMEM columns of this CTA (A_hi, A_lo shared by the warps; D per warp), this warp's lanes, its completion barrier, the B descriptors
+    const uint32_t tm = TC ? s_tmem[0] : 0u, tm_lane = (uint32_t)(warp * 32) << 16;
+    const uint32_t tm_ahi = tm, tm_alo = tm + 16, tm_d = TC ? s_tmem[1 + (warp >> 1)] + 16 * (warp & 1) : 0u;
+    const uint32_t tc_bar = smem_u32(bars + 2 * TMA_STAGES + warp);
+    const uint64_t tc_bhi = tc_smem_desc(smem_u32(sJt), TC_LBO, TC_SBO), tc_blo = tc_smem_desc(smem_u32(sJt + NG * NG), TC_LBO, TC_SBO);
     const int n_it = s_nit;
     const size_t ps = (size_t)M.nrep * M.Ns;
 
@@ -248,10 +327,9 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
             if (s < n_it) issue(s, s);
     }
 
-    // HITS = 2: a thread's accepted hits of replica `it` (0..2) go into bits 2 it, 2 it + 1 of one register (TMA_RC <= 16 replicas per CTA);
-    // the per-replica sums over the warp and the atomics happen once, after the loop, instead of a reduce -> branch -> atomic chain per visit
-    static_assert(TMA_RC <= 16, "packed acceptance counts: 2 bits per replica");
-    uint32_t packed = 0;
+    // HITS = 2: the warp total of accepted hits of replica `it` comes from two ballots (bit 0, bit 1 of a thread's count 0..2) and stays in lane
+    // it % 32; one atomic instruction per warp and 32 replicas instead of a reduce -> branch -> atomic chain per visit
+    unsigned tot_mine = 0;
     char* const own = reinterpret_cast<char*>(M.psi + rb * M.Ns + p);      // own state of the chunk's first replica (plane 0)
     const uint32_t rep_bytes = (uint32_t)M.Ns * VB;
     for (int it = 0; it < n_it; it++) {
@@ -291,16 +369,63 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
             issue(it + TMA_STAGES, s);
         }
         R Hq[NG];
-#if SCMC_TMA_ABLATE == 1
-#pragma unroll
-        for (int t = 0; t < NG; t++) Hq[t] = P[t] + sJt[t];
-#else
-        field_from_sums_smem<1>(sJt, (const R(*)[NG])P, Hq);       // Hq = Jq . Psum
-#endif
-        R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
+        R eloc;
         unsigned mine = 0;
         uint32_t uw[4];                                            // stream v2: acceptance-uniform words of the current group of four visits
         const int n_hits = HITS ? HITS : A.hits;                   // HITS = 2: the two hits of the reference's 2N-update sweep, unrolled
+        constexpr bool PRE = TC && HITS == 2 && STREAM == 2 && SCMC_TC_PRE;       // both hits' random numbers are generated while the tensor core works
+        R pxr[PRE ? 2 : 1][D], pxi[PRE ? 2 : 1][D];
+        if constexpr (TC) {
+            uint32_t hi[NG], lo[NG];
+#pragma unroll
+            for (int t = 0; t < NG; t++) {
+                hi[t] = __float_as_uint(P[t]) & 0xFFFFE000u;
+                lo[t] = __float_as_uint(P[t] - __uint_as_float(hi[t]));
+            }
+            tmem_st16(tm_lane | tm_ahi, hi);
+            tmem_st16(tm_lane | tm_alo, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (elect_one()) {                                  // elect.sync: ptxas then emits the MMAs straight, without a loop over the active lanes
+                tc_fence_after();
+                constexpr uint32_t KS = (2 * TC_LBO) >> 4;          // descriptor step of one K = 8 slice
+                tc_mma_tf32_ts(tm_d, tm_alo, tc_bhi, TC_IDESC, 0);
+                tc_mma_tf32_ts(tm_d, tm_alo + 8, tc_bhi + KS, TC_IDESC, 1);
+                tc_mma_tf32_ts(tm_d, tm_ahi, tc_blo, TC_IDESC, 1);
+                tc_mma_tf32_ts(tm_d, tm_ahi + 8, tc_blo + KS, TC_IDESC, 1);
+                tc_mma_tf32_ts(tm_d, tm_ahi, tc_bhi, TC_IDESC, 1);
+                tc_mma_tf32_ts(tm_d, tm_ahi + 8, tc_bhi + KS, TC_IDESC, 1);
+                tc_commit(tc_bar);
+            }
+            __syncwarp();
+            uint32_t tc_dep = 0;
+            if constexpr (PRE) {
+#pragma unroll
+                for (int hit = 0; hit < 2; hit++) stream_v2_normals<R, D>(A.seed, site, (uint32_t)(A.roff + r), A.visit0 + hit, pxr[hit], pxi[hit]);
+                stream_v2_uniform_words(A.seed, site, (uint32_t)(A.roff + r), A.visit0 >> 2, uw);
+                // ptxas would hoist the (possibly suspending) try_wait above this arithmetic: make the wait's parity operand depend on the
+                // last numbers computed, through a mask that is zero at run time but not at compile time (tile indices are non-negative)
+                tc_dep = uw[3];
+#pragma unroll
+                for (int hit = 0; hit < 2; hit++)
+#pragma unroll
+                    for (int k = 0; k < D; k++) tc_dep ^= __float_as_uint(pxr[hit][k]);
+                tc_dep &= (uint32_t)T.first >> 31;
+            }
+            mbar_wait(tc_bar, ((uint32_t)it & 1u) ^ tc_dep);
+            tc_fence_after();
+            tmem_ld16(tm_lane | tm_d, Hq);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#if SCMC_TMA_ABLATE == 1
+#pragma unroll
+            for (int t = 0; t < NG; t++) Hq[t] = P[t] + sJt[t];
+#else
+            field_from_sums_smem<1>(sJt, (const R(*)[NG])P, Hq);       // Hq = Jq . Psum
+#endif
+        }
+        eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
 #pragma unroll
         for (int hit = 0; hit < n_hits; hit++) {
             R xr[D], xi[D], u, dE;
@@ -310,7 +435,11 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
             u = R(0.5);
             if (false)
 #endif
-            if constexpr (STREAM == 2) {
+            if constexpr (PRE) {
+#pragma unroll
+                for (int k = 0; k < D; k++) { xr[k] = pxr[hit][k]; xi[k] = pxi[hit][k]; }
+                u = unit_uniform(pick_word(uw, ((uint32_t)A.visit0 + hit) & 3u), R(0));
+            } else if constexpr (STREAM == 2) {
                 const uint64_t visit = A.visit0 + hit;
                 stream_v2_normals<R, D>(A.seed, site, (uint32_t)(A.roff + r), visit, xr, xi);
                 // HITS = 2: visit0 = 2 x sweep is even, so the second hit never opens a new group of four visits
@@ -324,16 +453,23 @@ __global__ void __launch_bounds__(TMA_TILE, SCMC_TMA_BLOCKS) k_sweep_tma_psi(con
         if (!valid) mine = 0;
         if (mine) store_psi<R, D>(reinterpret_cast<V*>(own + (size_t)rl * rep_bytes), ps, re, im);
         if constexpr (HITS == 2) {
-            packed |= mine << (2 * it);
+            const unsigned b0 = __ballot_sync(0xffffffffu, mine & 1u), b1 = __ballot_sync(0xffffffffu, mine & 2u);
+            if (lane == (it & 31)) tot_mine = __popc(b0) + 2 * __popc(b1);
+            if ((it & 31) == 31 || it == n_it - 1) {
+                const int j = (it & ~31) + lane;
+                if (j <= it && tot_mine) atomicAdd(A.acc + rb + sRep[j], (unsigned long long)tot_mine);
+            }
         } else {
             const unsigned tot = __reduce_add_sync(0xffffffffu, mine);
             if (lane == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
         }
     }
-    if constexpr (HITS == 2) {
-        for (int it = 0; it < n_it; it++) {
-            const unsigned tot = __reduce_add_sync(0xffffffffu, (packed >> (2 * it)) & 3u);
-            if (lane == 0 && tot) atomicAdd(A.acc + rb + sRep[it], (unsigned long long)tot);
+    if constexpr (TC) {
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int q = 0; q < TC_TMEM_ALLOCS; q++) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s_tmem[q]), "n"(TC_TMEM_COLS) : "memory");
         }
     }
 }
@@ -352,9 +488,19 @@ static DevModel<R, 1> make_model_t(const scmc_handle* h) {
     return M;
 }
 
-static size_t tma_smem_bytes(const scmc_handle* h) {
+static size_t tma_smem_bytes(const scmc_handle* h, bool tc = true) {
     const size_t VB = 4 * h->esz();
-    return (size_t)TMA_STAGES * (h->d / 2) * h->tma.cap * VB + 256 * h->esz() + 2 * TMA_STAGES * 8 + TMA_RC * (4 + 2 * h->esz()) + 16;
+    return (size_t)TMA_STAGES * (h->d / 2) * h->tma.cap * VB + (tc ? 2 : 1) * 256 * h->esz() + (2 * TMA_STAGES + TMA_TILE / 32) * 8 + TMA_RC * (4 + 2 * h->esz()) + 16;
+}
+
+// Tensor-core mat-vec variant (mode 6; auto unless SCMC_TC=0): rounding of the 16x16 mat-vec differs from the FFMA order of the other psi-gather
+// kernels (3xTF32 products, FP32 accumulation in the tensor core), so its chains agree with theirs to rounding, not bit for bit; mode 5 keeps
+// the bit-identical FFMA2 form.
+static bool tma_use_tc(const scmc_handle* h) {
+    static const int env = getenv("SCMC_TC") ? atoi(getenv("SCMC_TC")) : -1;
+    if (h->sweep_mode == 6) return true;
+    if (h->sweep_mode == 5) return false;
+    return env != 0;
 }
 
 // The pipelined kernel serves FP32, d = 4 (n = 1, 3), one coupling label, no on-site term, z = 3 or 6 neighbour slots, single-class passes.
@@ -366,7 +512,7 @@ bool tma_pass_available(const scmc_handle* h, const SweepArgs& A) {
     return h->tma.cls[A.colour].ok != 0;
 }
 
-template <int GEN, int Z, int STREAM, int HITS>
+template <int GEN, int Z, int STREAM, int HITS, bool TC>
 static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t stream) {
     using R = float;
     auto M = make_model_t<R>(h);
@@ -375,13 +521,14 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
     T.meta = (const uint4*)h->tma.d_meta; T.runs = (const uint2*)h->tma.d_runs; T.tile = h->tma.d_tile;
     T.first = C.first; T.cap = h->tma.cap;
     // replicas per CTA: TMA_RC, fewer when that leaves the chip with less than a few waves of CTAs (small shards)
-    int rc = TMA_RC;
-    while (rc > 2 && (int64_t)C.n_tiles * ((A.rcount + rc - 1) / rc) < 3000) rc /= 2;
+    static const int rc_env = getenv("SCMC_TMA_RC") ? atoi(getenv("SCMC_TMA_RC")) : 0, min_ctas = getenv("SCMC_TMA_MINCTAS") ? atoi(getenv("SCMC_TMA_MINCTAS")) : 3000;
+    int rc = rc_env > 0 && rc_env <= TMA_RC ? rc_env : TMA_RC;
+    while (rc > 2 && (int64_t)C.n_tiles * ((A.rcount + rc - 1) / rc) < min_ctas) rc /= 2;
     T.rc = rc;
-    const size_t smem = tma_smem_bytes(h);
+    const size_t smem = tma_smem_bytes(h, TC);
     static size_t attr_set[64] = {0};      // per device: largest dynamic shared-memory size opted into so far
     if (attr_set[h->device & 63] < smem) {
-        SCMC_CK(cudaFuncSetAttribute(k_sweep_tma_psi<R, GEN, Z, STREAM, HITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCMC_CK(cudaFuncSetAttribute(k_sweep_tma_psi<R, GEN, Z, STREAM, HITS, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[h->device & 63] = smem;
     }
     for (int64_t y0 = 0; y0 < A.rcount; y0 += (int64_t)65535 * rc) {
@@ -389,7 +536,7 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
         B.r0 = A.r0 + y0; B.rcount = std::min<int64_t>((int64_t)65535 * rc, A.rcount - y0);
         B.Jqt = h->d_Jqt; B.Jt = h->d_Jt;
         const dim3 grid((unsigned)C.n_tiles, (unsigned)((B.rcount + rc - 1) / rc));
-        k_sweep_tma_psi<R, GEN, Z, STREAM, HITS><<<grid, TMA_TILE, smem, stream>>>(M, B, T);
+        k_sweep_tma_psi<R, GEN, Z, STREAM, HITS, TC><<<grid, TMA_TILE, smem, stream>>>(M, B, T);
         h->launches++;
     }
     SCMC_CK(cudaGetLastError());
@@ -400,10 +547,15 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
 int32_t launch_colour_pass_tma(scmc_handle* h, const SweepArgs& A, cudaStream_t stream) {
     if (A.rcount == 0) return SCMC_OK;
     static const bool unroll2 = !(getenv("SCMC_TMA_UNROLL2") && atoi(getenv("SCMC_TMA_UNROLL2")) == 0);
+    const bool tc = tma_use_tc(h);
     auto go = [&](auto gen, auto zz) -> int32_t {
         constexpr int GEN = decltype(gen)::value, Z = decltype(zz)::value;
-        if (A.hits == 2 && unroll2) return A.stream == 2 ? launch_one<GEN, Z, 2, 2>(h, A, stream) : launch_one<GEN, Z, 1, 2>(h, A, stream);
-        return A.stream == 2 ? launch_one<GEN, Z, 2, 0>(h, A, stream) : launch_one<GEN, Z, 1, 0>(h, A, stream);
+        if (tc) {
+            if (A.hits == 2 && unroll2) return A.stream == 2 ? launch_one<GEN, Z, 2, 2, true>(h, A, stream) : launch_one<GEN, Z, 1, 2, true>(h, A, stream);
+            return A.stream == 2 ? launch_one<GEN, Z, 2, 0, true>(h, A, stream) : launch_one<GEN, Z, 1, 0, true>(h, A, stream);
+        }
+        if (A.hits == 2 && unroll2) return A.stream == 2 ? launch_one<GEN, Z, 2, 2, false>(h, A, stream) : launch_one<GEN, Z, 1, 2, false>(h, A, stream);
+        return A.stream == 2 ? launch_one<GEN, Z, 2, 0, false>(h, A, stream) : launch_one<GEN, Z, 1, 0, false>(h, A, stream);
     };
     using I1 = std::integral_constant<int, 1>; using I3 = std::integral_constant<int, 3>; using I6 = std::integral_constant<int, 6>;
     if (h->gen_id == 1) return h->z == 6 ? go(I1{}, I6{}) : go(I1{}, I3{});
