@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--hits", type=int, default=2)
     ap.add_argument("--precision", type=int, default=32)
     ap.add_argument("--coupling", default="notebook", choices=["notebook", "dense"])
-    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1/2 streaming/resident T-gather, 3/4 streaming/resident psi-gather")
+    ap.add_argument("--mode", type=int, default=0, help="0 auto, 1/2 streaming/resident T-gather, 3/4 streaming/resident psi-gather, 5/6 TMA-pipelined psi-gather without / with the tensor-core mat-vec")
     ap.add_argument("--stream", type=int, default=2, choices=[1, 2], help="random stream version (DESIGN.md section 5): 1 = Philox4x32-10, 2 = Philox4x32-7")
     ap.add_argument("--batch", type=int, default=0, help="replicas per L2 batch (streaming path)")
     ap.add_argument("--colouring", default="auto", choices=["auto", "few", "balanced"], help="few = 3 large + seam classes, balanced = 2x2 parity (4 equal classes)")
@@ -373,9 +373,11 @@ def run_ours(args):
         psi_family = args.mode in (3, 4) or (args.mode == 0 and cfg.d == 4)
         small = 1 <= info["cluster"] <= 2 and (args.sweeps >= 4 or R * N / info["n_colours"] < 300000)
         uses_resident = args.mode in (2, 4) or (args.mode == 0 and small and (info["resident_psi"] if psi_family else info["resident"]))
-        uses_tma = (not uses_resident) and psi_family and info.get("tma") and args.mode in (0, 5) and args.precision == 32
+        uses_tma = (not uses_resident) and psi_family and info.get("tma") and args.mode in (0, 5, 6) and args.precision == 32
+        uses_tc = uses_tma and info.get("tma_tc")
         kernel_name = (f"replica-resident cluster({info['cluster']})" if uses_resident else "streaming colour-pass") + (", psi-gather" if psi_family else ", T-gather") + \
-                      (", TMA-pipelined (cp.async.bulk + mbarrier ring; seam classes: direct gather)" if uses_tma else "")
+                      (", TMA-pipelined (cp.async.bulk + mbarrier ring; seam classes: direct gather)" if uses_tma else "") + \
+                      (", 16x16 mat-vec on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, A in TMEM)" if uses_tc else "")
         # algorithmic bytes per kernel launch: state in + state out (4 d w bytes) of every site the launch visits
         sites_per_launch = R * N * args.sweeps * intervals * args.steps / n_launch_local
         alg_bytes = sites_per_launch * 4 * d * w
@@ -405,7 +407,7 @@ def run_ours(args):
                            "acceptance_rate": acc_rate, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                              "updates_per_site_per_launch": args.hits, "launch_us": launch_s * 1e6,
-                             "note": "issue / FMA-pipe bound, not HBM bound: see profiles/README.md (round 2) for the ncu summary of this kernel"},
+                             "note": "issue / latency bound, not HBM bound: see profiles/README.md (round 2) for the ncu summary of this kernel"},
                 "e2e": {"value": e2e_value, "unit": "site-updates/s", "h2d_bytes_per_step": int(2 * R * 8) * world * intervals,      # beta and sigma cross the ABI as FP64 tables
                         "d2h_bytes_per_step": int(2 * R * 8 + R * _lib.NOBS * 8) * world * intervals, "ms_per_step": ms_e2e / args.steps,
                         "collective": (f"all_gather of the {_lib.NOBS}-value measure! rows of all {R_total} replicas over NCCL, once per interval" if world > 1 else None)},

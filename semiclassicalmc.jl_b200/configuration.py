@@ -118,7 +118,7 @@ class Configuration:
     def info(self):
         a = np.zeros(8, dtype=np.int64)
         _lib.check(self._lib.scmc_info(self._h, _lib.lptr(a)))
-        return dict(n_colours=int(a[0]), generator_table=int(a[1]), device_bytes=int(a[2]), resident=bool(a[3] & 1), resident_psi=bool(a[3] & 2), tma=bool(a[3] & 4), cluster=int(a[4]),
+        return dict(n_colours=int(a[0]), generator_table=int(a[1]), device_bytes=int(a[2]), resident=bool(a[3] & 1), resident_psi=bool(a[3] & 2), tma=bool(a[3] & 4), tma_tc=bool(a[3] & 8), cluster=int(a[4]),
                     launches=int(a[5]), n_sites=int(a[6]), n_replicas=int(a[7]))
 
     def set_sweep_mode(self, mode=0, batch=0):

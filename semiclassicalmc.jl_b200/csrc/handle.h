@@ -154,9 +154,13 @@ int32_t launch_resident_anneal(scmc_handle* h, int64_t chunk, int32_t hits, uint
                                double beta_fac, double min_accrate, double sigma_min, int64_t n_per_T, int64_t n_total,
                                int64_t* d_sweeps_at_T, int64_t* d_sweeps_done, int* d_n_active);
 // implemented in scmc_tma.cu
-constexpr int TMA_TILE = 128, TMA_MAX_RUNS = 16, TMA_STAGES = 2, TMA_RC = 128;   // TMA_RC: most replicas one CTA walks over
+#ifndef SCMC_TMA_STAGES
+#define SCMC_TMA_STAGES 2
+#endif
+constexpr int TMA_TILE = 128, TMA_MAX_RUNS = 16, TMA_STAGES = SCMC_TMA_STAGES, TMA_RC = 128;   // TMA_RC: most replicas one CTA walks over
 void plan_tma(scmc_handle* h, const std::vector<int32_t>& col_list, const std::vector<int32_t>& nb /* [z][N] permuted neighbour by permuted site */);
 bool tma_pass_available(const scmc_handle* h, const SweepArgs& A);
+bool tma_use_tc(const scmc_handle* h);      // the handle's TMA passes run the tensor-core mat-vec variant (mode 6, auto unless SCMC_TC=0)
 int32_t launch_colour_pass_tma(scmc_handle* h, const SweepArgs& A, cudaStream_t stream);
 // implemented in scmc_resident.cu
 void plan_resident(scmc_handle* h, const std::vector<int>& owner_of_perm);

@@ -1766,7 +1766,7 @@ int32_t scmc_set_lanes(scmc_t* h, int32_t lanes) {
 
 int32_t scmc_info(scmc_t* h, int64_t* info) {
     SCMC_ARG(h && info, "null argument");
-    info[0] = h->n_col; info[1] = h->gen_id; info[2] = h->bytes; info[3] = h->res.eligible | (h->res.eligible_psi << 1) | (h->tma.ready << 2); info[4] = h->res.cs; info[5] = h->launches; info[6] = h->N; info[7] = h->R;
+    info[0] = h->n_col; info[1] = h->gen_id; info[2] = h->bytes; info[3] = h->res.eligible | (h->res.eligible_psi << 1) | (h->tma.ready << 2) | ((h->tma.ready && h->prec == 32 && tma_use_tc(h)) ? 8 : 0); info[4] = h->res.cs; info[5] = h->launches; info[6] = h->N; info[7] = h->R;
     return SCMC_OK;
 }
 

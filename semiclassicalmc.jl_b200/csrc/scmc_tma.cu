@@ -28,10 +28,20 @@ namespace scmc {
 #ifndef SCMC_TMA_ABLATE
 #define SCMC_TMA_ABLATE 0        // timing ablations (profiles/README.md, round 2); 0 = production.  1: no mat-vec, 2: one neighbour, 3: no random numbers
 #endif
+#ifndef SCMC_TMA_PREFETCH
+#define SCMC_TMA_PREFETCH 0      // replicas ahead of a stage refill whose runs are prefetched into L2 (0: off)
+#endif
+#ifndef SCMC_TC_PACKED
+#define SCMC_TC_PACKED 1         // tensor-core variant: density sums as packed fma.rn.f32x2 (its own summation order; the variant is not bit-identical anyway)
+#endif
 #ifndef SCMC_TC_PRE
 #define SCMC_TC_PRE 1            // tensor-core variant: generate both hits' random numbers between the MMA issue and the wait for its result
 #endif
-constexpr int TMA_GAP = 8;       // runs closer than this many unused states are merged into one copy
+#ifndef SCMC_TMA_GAP
+#define SCMC_TMA_GAP 32
+#endif
+// measured on C5 (A/B harness, 8192 replicas): 8 -> 5.49e10, 32 -> 5.55e10, 96 -> 5.32e10 updates/s (fewer, longer copies against unused bytes)
+constexpr int TMA_GAP = SCMC_TMA_GAP;       // runs closer than this many unused states are merged into one copy
 
 // ------------------------------------------------------------------------------------------------ planning (host)
 void plan_tma(scmc_handle* h, const std::vector<int32_t>& col_list, const std::vector<int32_t>& nb) {
@@ -206,6 +216,46 @@ constexpr int TC_TMEM_COLS = 32, TC_TMEM_ALLOCS = 3;
 #define SCMC_TC_BLOCKS 5         // CTAs per SM the tensor-core variant is compiled for
 #endif
 
+// Packed density sums of the tensor-core variant (d = 4; basis order of gen::density_acc_g1 / _g3): with the pairs c_m = (re_m, im_m) as they come out
+// of the 128-bit loads, c_m * c_m = (re_m^2, im_m^2), c_m * c_n = (re_m re_n, im_m im_n) and c_m * swap(c_n) = (re_m im_n, im_m re_n) are one
+// fma.rn.f32x2 each: 16 FFMA2 + 6 moves per neighbour instead of 32 FFMA; the two halves are combined once per visit (sum linear in the neighbours).
+__device__ __forceinline__ unsigned long long pk2(float x, float y) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ void fma2(unsigned long long& d, unsigned long long a, unsigned long long b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+__device__ __forceinline__ float2 up2(unsigned long long v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+struct PackedDensity {
+    unsigned long long dg[4], a[6], b[6];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 4; i++) dg[i] = 0ull;
+#pragma unroll
+        for (int i = 0; i < 6; i++) { a[i] = 0ull; b[i] = 0ull; }
+    }
+    __device__ __forceinline__ void add(const float4 q0, const float4 q1) {
+        const unsigned long long c[4] = {pk2(q0.x, q0.y), pk2(q0.z, q0.w), pk2(q1.x, q1.y), pk2(q1.z, q1.w)};
+        const unsigned long long sw[4] = {0ull, pk2(q0.w, q0.z), pk2(q1.y, q1.x), pk2(q1.w, q1.z)};
+#pragma unroll
+        for (int m = 0; m < 4; m++) fma2(dg[m], c[m], c[m]);
+        int i = 0;
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+#pragma unroll
+            for (int n = m + 1; n < 4; n++, i++) { fma2(a[i], c[m], c[n]); fma2(b[i], c[m], sw[n]); }
+    }
+    __device__ __forceinline__ void finish(float* P) const {
+        constexpr int DIAG[4] = {0, 7, 12, 15}, OFF[6] = {1, 3, 5, 8, 10, 13};      // P index of |psi_m|^2 and of Re(conj(psi_m) psi_n); Im follows Re
+#pragma unroll
+        for (int m = 0; m < 4; m++) { const float2 v = up2(dg[m]); P[DIAG[m]] = v.x + v.y; }
+#pragma unroll
+        for (int i = 0; i < 6; i++) { const float2 u = up2(a[i]), w = up2(b[i]); P[OFF[i]] = u.x + u.y; P[OFF[i] + 1] = w.x - w.y; }
+    }
+};
+
+// L2 prefetch of a run (TMA engine, no shared-memory destination), SCMC_TMA_PREFETCH replicas ahead of the copy that will consume it.
+// Measured on C5 (profiles/README.md, round 2): 5.50e10 -> 5.05e10 updates/s with a distance of 2 or 4 -- off by default.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 struct TmaArgs {
     const uint4* meta;       // [tiles][128][2]
     const uint2* runs;       // [tiles][TMA_MAX_RUNS]
@@ -319,7 +369,10 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
     auto issue = [&](int it, int s) {
         if (lane == 0) mbar_expect_tx(bar0 + 8 * s, tile_bytes);
         __syncwarp();
-        if (c_bytes) bulk_g2s(smem0 + s * stage_bytes + c_dst, c_src + (size_t)sRep[it] * M.Ns * VB, c_bytes, bar0 + 8 * s);
+        if (c_bytes) {
+            bulk_g2s(smem0 + s * stage_bytes + c_dst, c_src + (size_t)sRep[it] * M.Ns * VB, c_bytes, bar0 + 8 * s);
+            if (SCMC_TMA_PREFETCH && it + SCMC_TMA_PREFETCH < n_it) bulk_prefetch_l2(c_src + (size_t)sRep[it + SCMC_TMA_PREFETCH] * M.Ns * VB, c_bytes);
+        }
     };
     if (warp == 0) {
 #pragma unroll
@@ -349,17 +402,26 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
             const V q = *reinterpret_cast<const V*>(st + v * plane_bytes + off[0]);
             re[2 * v] = q.x; im[2 * v] = q.y; re[2 * v + 1] = q.z; im[2 * v + 1] = q.w;
         }
+        if constexpr (TC && SCMC_TC_PACKED) {
+            PackedDensity pd;
+            pd.clear();
 #pragma unroll
-        for (int t = 0; t < NP; t++) P[t] = R(0);
+            for (int k = 0; k < Z; k++)
+                pd.add(*reinterpret_cast<const float4*>(st + off[1 + k]), *reinterpret_cast<const float4*>(st + plane_bytes + off[1 + k]));
+            pd.finish(P);
+        } else {
 #pragma unroll
-        for (int k = 0; k < (SCMC_TMA_ABLATE == 2 ? 1 : Z); k++) {
-            R nr[D], ni[D];
+            for (int t = 0; t < NP; t++) P[t] = R(0);
 #pragma unroll
-            for (int v = 0; v < NPV; v++) {
-                const V q = *reinterpret_cast<const V*>(st + v * plane_bytes + off[1 + k]);
-                nr[2 * v] = q.x; ni[2 * v] = q.y; nr[2 * v + 1] = q.z; ni[2 * v + 1] = q.w;
+            for (int k = 0; k < (SCMC_TMA_ABLATE == 2 ? 1 : Z); k++) {
+                R nr[D], ni[D];
+#pragma unroll
+                for (int v = 0; v < NPV; v++) {
+                    const V q = *reinterpret_cast<const V*>(st + v * plane_bytes + off[1 + k]);
+                    nr[2 * v] = q.x; ni[2 * v] = q.y; nr[2 * v + 1] = q.z; ni[2 * v + 1] = q.w;
+                }
+                GenOps<GEN>::density_acc(nr, ni, P);
             }
-            GenOps<GEN>::density_acc(nr, ni, P);
         }
         // this warp is done with the stage: release it; warp 0 refills it with the states of replica it + STAGES once all warps have
         __syncwarp();
@@ -496,7 +558,7 @@ static size_t tma_smem_bytes(const scmc_handle* h, bool tc = true) {
 // Tensor-core mat-vec variant (mode 6; auto unless SCMC_TC=0): rounding of the 16x16 mat-vec differs from the FFMA order of the other psi-gather
 // kernels (3xTF32 products, FP32 accumulation in the tensor core), so its chains agree with theirs to rounding, not bit for bit; mode 5 keeps
 // the bit-identical FFMA2 form.
-static bool tma_use_tc(const scmc_handle* h) {
+bool tma_use_tc(const scmc_handle* h) {
     static const int env = getenv("SCMC_TC") ? atoi(getenv("SCMC_TC")) : -1;
     if (h->sweep_mode == 6) return true;
     if (h->sweep_mode == 5) return false;
@@ -522,7 +584,7 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
     T.first = C.first; T.cap = h->tma.cap;
     // replicas per CTA: TMA_RC, fewer when that leaves the chip with less than a few waves of CTAs (small shards)
     static const int rc_env = getenv("SCMC_TMA_RC") ? atoi(getenv("SCMC_TMA_RC")) : 0, min_ctas = getenv("SCMC_TMA_MINCTAS") ? atoi(getenv("SCMC_TMA_MINCTAS")) : 3000;
-    int rc = rc_env > 0 && rc_env <= TMA_RC ? rc_env : TMA_RC;
+    int rc = rc_env > 0 && rc_env <= TMA_RC ? rc_env : 64;      // measured on C5: 16 -> 5.18e10, 32 -> 5.38e10, 64 -> 5.40e10, 128 -> 5.39e10 (tensor-core variant)
     while (rc > 2 && (int64_t)C.n_tiles * ((A.rcount + rc - 1) / rc) < min_ctas) rc /= 2;
     T.rc = rc;
     const size_t smem = tma_smem_bytes(h, TC);

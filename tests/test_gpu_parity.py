@@ -414,7 +414,7 @@ def test_device_side_annealing_equals_host_driven_loop(scmc, precision):
     """runAnnealing!'s cooling loop inside the persistent resident kernel (one CTA per replica) vs the same loop driven from the
     host one sweep at a time: identical final beta, sigma, sweep counts and bit-identical states for every replica."""
     mk = lambda: scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 12, 1, n_replicas=24, precision=precision, seed=4321)
-    kw = dict(T_fac=0.9, N_max=700, N_o=0, N_per_T=20, min_acc_per_site=3, min_accrate=0.02, σ_min=0.05)
+    kw = dict(T_fac=0.9, N_max=700, N_o=0, N_per_T=20, min_acc_per_site=3, min_accrate=0.02, σ_min=0.05, log_rate=0)      # no E / beta series: launches are not cut at log points
     a = mk(); a.set_sweep_mode(3)                  # streaming psi-gather kernel, host-driven controller
     ra = scmc.runAnnealing_(a, 2.0, **kw)
     b = mk()                                       # auto: psi family, single-CTA resident kernel, device-side controller
@@ -616,7 +616,7 @@ def test_device_side_annealing_in_clusters_equals_host_driven_loop(scmc, monkeyp
     def mk(c):
         monkeypatch.setenv("SCMC_CLUSTER_MIN", str(c))
         return scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 12, 1, n_replicas=10, precision=precision, seed=4321)
-    kw = dict(T_fac=0.9, N_max=700, N_o=0, N_per_T=20, min_acc_per_site=3, min_accrate=0.02, σ_min=0.05)
+    kw = dict(T_fac=0.9, N_max=700, N_o=0, N_per_T=20, min_acc_per_site=3, min_accrate=0.02, σ_min=0.05, log_rate=0)      # no E / beta series: launches are not cut at log points
     a = mk(1); a.set_sweep_mode(3)                 # streaming psi-gather kernel, host-driven controller
     ra = scmc.runAnnealing_(a, 2.0, **kw)
     b = mk(cmin)
@@ -684,7 +684,7 @@ def test_t_family_device_side_annealing_equals_host_driven_loop(scmc, monkeypatc
     def mk(c):
         monkeypatch.setenv("SCMC_CLUSTER_MIN", str(c))
         return _t_family_model(scmc, kind, 8, precision, 777)
-    kw = dict(T_fac=0.9, N_max=500, N_o=0, N_per_T=20, min_acc_per_site=3, min_accrate=0.02, σ_min=0.05)
+    kw = dict(T_fac=0.9, N_max=500, N_o=0, N_per_T=20, min_acc_per_site=3, min_accrate=0.02, σ_min=0.05, log_rate=0)
     a = mk(1); a.set_sweep_mode(1)
     ra = scmc.runAnnealing_(a, 2.0, **kw)
     b = mk(cmin)
