@@ -832,3 +832,61 @@ def test_tma_pipelined_kernel_is_bit_identical(scmc, case, stream):
     assert np.array_equal(a.energies(), b.energies())
     assert acc_a.min() > 0
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("case", [
+    ("triangular", 128, 37, 1),  # BASELINE C5 lattice, ragged replica chunks
+    ("triangular", 48, 19, 1),   # L % 3 == 0
+    ("honeycomb", 24, 21, 1),    # z = 3
+    ("square", 32, 18, 1),       # z = 4, padded to 6 slots
+    ("triangular", 48, 9, 3),    # n = 3 (d = 4, second generator table of the density basis)
+])
+@pytest.mark.parametrize("stream", [1, 2])
+@pytest.mark.parametrize("coupling", ["notebook", "dense"])
+def test_tensor_core_variant_follows_the_ffma_chain(scmc, case, stream, coupling):
+    """Mode 6 (what auto runs for streaming psi-gather passes in FP32): the TMA-pipelined kernel with the 16x16 mat-vec of a visit on the
+    tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, FP32 accumulation in TMEM) and packed FFMA2 density sums.  Its rounding differs from the
+    FFMA order of mode 5, so the chains agree to rounding: from identical states, after whole sweeps almost every site holds the same
+    state (a near-tie in an accept test may flip a handful), accept counts agree to a few, energies to 1e-5.  localUpdate!, MonteCarlo.jl:263-286."""
+    lattice, L, R, n = case
+    J = NOTEBOOK_J if coupling == "notebook" else random_symmetric_J(11)
+    mk = lambda: scmc.initializeCfg("nearest-neighbor", lattice, [J], L, n, n_replicas=R, precision=32, seed=777, replica_offset=5, stream=stream)
+    beta = np.geomspace(0.5, 50.0, R); sigma = np.geomspace(0.8, 0.03, R)
+    a = mk(); a.set_sweep_mode(5)
+    b = mk(); b.set_sweep_mode(6)
+    assert b.info()["tma"] and b.info()["tma_tc"] and not a.info()["tma_tc"]
+    for hits in (2, 3):                                   # 2: unrolled hits, random numbers generated under the MMA; 3: run-time hit loop
+        acc_a, att_a = a.sweep(1, beta, sigma, hits=hits)
+        acc_b, att_b = b.sweep(1, beta, sigma, hits=hits)
+        assert np.array_equal(att_a, att_b)
+        assert np.abs(acc_a.astype(np.int64) - acc_b.astype(np.int64)).max() <= 3
+        sa, sb = a.get_state(), b.get_state()
+        differing = np.abs(sa - sb).reshape(R, a.nSites, -1).max(axis=2) > 1e-4
+        assert differing.mean() < 1e-4, differing.sum()
+        Ea, Eb = a.energies(), b.energies()
+        same = ~differing.any(axis=1)                     # replicas without a flipped near-tie: the energies agree to rounding
+        assert same.sum() >= R - 3 and np.allclose(Ea[same], Eb[same], rtol=2e-5, atol=2e-6 * a.nSites)
+        b.set_state(sa)                                   # continue both from the same states: differences do not accumulate in the test
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("mode", [5, 6])
+@pytest.mark.parametrize("stream", [1, 2])
+def test_fp32_tma_kernels_follow_the_oracle_chain(scmc, oracle_mod, mode, stream):
+    """The FP32 production kernels of the headline workload (mode 5: TMA-pipelined, mode 6: + tensor-core mat-vec) against the oracle's FP64
+    restatement of the same colour-ordered counter-based chain, directly: same accept decisions (a near-tie may flip one), states to FP32 rounding."""
+    R, off, seed = 2, 11, 24680
+    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [random_symmetric_J(5)], 48, 1, n_replicas=R, precision=32, seed=seed, replica_offset=off, stream=stream)
+    cfg.set_sweep_mode(mode)
+    assert cfg.info()["tma"] and cfg.info()["tma_tc"] == (mode == 6)
+    beta, sigma = np.array([2.0, 15.0]), np.array([0.5, 0.1])
+    acc, att = cfg.sweep(1, beta, sigma, hits=2)
+    for r in range(R):
+        o = make_oracle(cfg, oracle_mod)
+        o.randomize_v1(seed, off + r)
+        a1 = o.sweeps_colour(stream, 1, 2, cfg.colour, beta[r], sigma[r], seed, off + r, 0)
+        assert abs(int(acc[r]) - a1) <= 2, (acc[r], a1)
+        d = np.abs(cfg.get_state(r, 1)[0] - o.get_state()).max(axis=1)          # per site
+        assert (d > 1e-4).sum() <= 4, (d > 1e-4).sum()
+        assert np.median(d) < 5e-6
+    cfg.close()
