@@ -211,7 +211,10 @@ constexpr uint32_t TC_LBO = 256, TC_SBO = 128;                       // Jq in co
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);      // D = F32, A = B = TF32, K-major, N = 16, M = 128
 // Tensor memory of a CTA: A_hi 16 + A_lo 16 + 4 warps x D 16 = 96 columns, taken as THREE allocations of 32 columns (allocations are powers of
 // two: one of 128 would cap the SM at 4 CTAs; equal-sized pieces cannot fragment the 512 columns, 5 CTAs x 3 = 15 of 16 pieces).
-constexpr int TC_TMEM_COLS = 32, TC_TMEM_ALLOCS = 3;
+#ifndef SCMC_TC_CTA
+#define SCMC_TC_CTA 1            // 1: ONE set of MMAs per tile visit, issued by one warp once all four have stored their rows (a quarter of the tensor work);
+#endif                           // 0: every warp issues its own MMAs into its own D columns (no rendezvous inside the CTA)
+constexpr int TC_TMEM_COLS = SCMC_TC_CTA ? 64 : 32, TC_TMEM_ALLOCS = SCMC_TC_CTA ? 1 : 3;
 #ifndef SCMC_TC_BLOCKS
 #define SCMC_TC_BLOCKS 5         // CTAs per SM the tensor-core variant is compiled for
 #endif
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
 #pragma unroll
             for (int s = 0; s < TMA_STAGES; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + TMA_STAGES + s), TMA_TILE / 32); }
             if (TC)
-                for (int w = 0; w < TMA_TILE / 32; w++) mbar_init(smem_u32(bars + 2 * TMA_STAGES + w), 1);
+                for (int w = 0; w < TMA_TILE / 32; w++) mbar_init(smem_u32(bars + 2 * TMA_STAGES + w), (SCMC_TC_CTA && w == 1) ? TMA_TILE / 32 : 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -347,8 +350,9 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
     if (TC) tc_fence_after();
     // TC: TMEM columns of this CTA (A_hi, A_lo shared by the warps; D per warp), this warp's lanes, its completion barrier, the B descriptors
     const uint32_t tm = TC ? s_tmem[0] : 0u, tm_lane = (uint32_t)(warp * 32) << 16;
-    const uint32_t tm_ahi = tm, tm_alo = tm + 16, tm_d = TC ? s_tmem[1 + (warp >> 1)] + 16 * (warp & 1) : 0u;
-    const uint32_t tc_bar = smem_u32(bars + 2 * TMA_STAGES + warp);
+    const uint32_t tm_ahi = tm, tm_alo = tm + 16, tm_d = !TC ? 0u : SCMC_TC_CTA ? tm + 32 : s_tmem[1 + (warp >> 1)] + 16 * (warp & 1);
+    // completion barrier of the MMAs: per warp, or (CTA-wide MMAs) barrier 0 = "D ready", barrier 1 = "all four warps stored their A rows"
+    const uint32_t tc_bar = smem_u32(bars + 2 * TMA_STAGES + (SCMC_TC_CTA ? 0 : warp)), tc_abar = smem_u32(bars + 2 * TMA_STAGES + 1);
     const uint64_t tc_bhi = tc_smem_desc(smem_u32(sJt), TC_LBO, TC_SBO), tc_blo = tc_smem_desc(smem_u32(sJt + NG * NG), TC_LBO, TC_SBO);
     const int n_it = s_nit;
     const size_t ps = (size_t)M.nrep * M.Ns;
@@ -449,6 +453,23 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
+#if SCMC_TC_CTA
+            if (lane == 0) mbar_arrive(tc_abar);                // this warp's rows of A are in tensor memory
+            if (warp == 1) {                                    // (warp 0 carries the stage refills)
+                mbar_wait(tc_abar, (uint32_t)it & 1u);
+                if (elect_one()) {                              // elect.sync: ptxas then emits the MMAs straight, without a loop over the active lanes
+                    tc_fence_after();
+                    constexpr uint32_t KS = (2 * TC_LBO) >> 4;  // descriptor step of one K = 8 slice
+                    tc_mma_tf32_ts(tm_d, tm_alo, tc_bhi, TC_IDESC, 0);
+                    tc_mma_tf32_ts(tm_d, tm_alo + 8, tc_bhi + KS, TC_IDESC, 1);
+                    tc_mma_tf32_ts(tm_d, tm_ahi, tc_blo, TC_IDESC, 1);
+                    tc_mma_tf32_ts(tm_d, tm_ahi + 8, tc_blo + KS, TC_IDESC, 1);
+                    tc_mma_tf32_ts(tm_d, tm_ahi, tc_bhi, TC_IDESC, 1);
+                    tc_mma_tf32_ts(tm_d, tm_ahi + 8, tc_bhi + KS, TC_IDESC, 1);
+                    tc_commit(tc_bar);
+                }
+            }
+#else
             if (elect_one()) {                                  // elect.sync: ptxas then emits the MMAs straight, without a loop over the active lanes
                 tc_fence_after();
                 constexpr uint32_t KS = (2 * TC_LBO) >> 4;          // descriptor step of one K = 8 slice
@@ -460,6 +481,7 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
                 tc_mma_tf32_ts(tm_d, tm_ahi + 8, tc_bhi + KS, TC_IDESC, 1);
                 tc_commit(tc_bar);
             }
+#endif
             __syncwarp();
             uint32_t tc_dep = 0;
             if constexpr (PRE) {
