@@ -370,7 +370,7 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         d, w = cfg.d, args.precision // 8
         n_launch_local = max(1, launches // world)
-        psi_family = args.mode in (3, 4) or (args.mode == 0 and cfg.d == 4)
+        psi_family = args.mode in (3, 4, 5, 6) or (args.mode == 0 and cfg.d == 4)
         small = 1 <= info["cluster"] <= 2 and (args.sweeps >= 4 or R * N / info["n_colours"] < 300000)
         uses_resident = args.mode in (2, 4) or (args.mode == 0 and small and (info["resident_psi"] if psi_family else info["resident"]))
         uses_tma = (not uses_resident) and psi_family and info.get("tma") and args.mode in (0, 5, 6) and args.precision == 32

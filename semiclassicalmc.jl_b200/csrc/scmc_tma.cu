@@ -327,17 +327,22 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
         V zv; zv.x = zv.y = zv.z = zv.w = R(0);
         *reinterpret_cast<V*>(smem + tid * plane_bytes + zero_off) = zv;
     }
-    if (warp == 0) {                                               // alive replicas of this chunk, in order
-        const bool al = lane < rcnt && (A.active == nullptr || A.active[rb + lane]);
-        const unsigned mask = __ballot_sync(0xffffffffu, al);
-        if (al) {
-            const int at = __popc(mask & ((1u << lane) - 1));
-            sRep[at] = lane;
-            sBeta[at] = ((const R*)A.beta)[rb + lane];
-            sSigma[at] = ((const R*)A.sigma)[rb + lane];
+    if (warp == 0) {                                               // alive replicas of this chunk, in order (32 at a time)
+        int n_alive = 0;
+        for (int c0 = 0; c0 < rcnt; c0 += 32) {
+            const int j = c0 + lane;
+            const bool al = j < rcnt && (A.active == nullptr || A.active[rb + j]);
+            const unsigned mask = __ballot_sync(0xffffffffu, al);
+            if (al) {
+                const int at = n_alive + __popc(mask & ((1u << lane) - 1));
+                sRep[at] = j;
+                sBeta[at] = ((const R*)A.beta)[rb + j];
+                sSigma[at] = ((const R*)A.sigma)[rb + j];
+            }
+            n_alive += __popc(mask);
         }
         if (lane == 0) {
-            s_nit = __popc(mask);
+            s_nit = n_alive;
 #pragma unroll
             for (int s = 0; s < TMA_STAGES; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + TMA_STAGES + s), TMA_TILE / 32); }
             if (TC)
@@ -605,7 +610,7 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
     T.meta = (const uint4*)h->tma.d_meta; T.runs = (const uint2*)h->tma.d_runs; T.tile = h->tma.d_tile;
     T.first = C.first; T.cap = h->tma.cap;
     // replicas per CTA: TMA_RC, fewer when that leaves the chip with less than a few waves of CTAs (small shards)
-    static const int rc_env = getenv("SCMC_TMA_RC") ? atoi(getenv("SCMC_TMA_RC")) : 0, min_ctas = getenv("SCMC_TMA_MINCTAS") ? atoi(getenv("SCMC_TMA_MINCTAS")) : 3000;
+    const int rc_env = getenv("SCMC_TMA_RC") ? atoi(getenv("SCMC_TMA_RC")) : 0, min_ctas = getenv("SCMC_TMA_MINCTAS") ? atoi(getenv("SCMC_TMA_MINCTAS")) : 3000;      // (read per launch: tests switch them)
     int rc = rc_env > 0 && rc_env <= TMA_RC ? rc_env : 64;      // measured on C5: 16 -> 5.18e10, 32 -> 5.38e10, 64 -> 5.40e10, 128 -> 5.39e10 (tensor-core variant)
     while (rc > 2 && (int64_t)C.n_tiles * ((A.rcount + rc - 1) / rc) < min_ctas) rc /= 2;
     T.rc = rc;

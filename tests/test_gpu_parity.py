@@ -890,3 +890,27 @@ def test_fp32_tma_kernels_follow_the_oracle_chain(scmc, oracle_mod, mode, stream
         assert (d > 1e-4).sum() <= 4, (d > 1e-4).sum()
         assert np.median(d) < 5e-6
     cfg.close()
+
+
+@pytest.mark.parametrize("rc", [8, 64, 128])
+def test_tma_replicas_per_cta_do_not_change_chains(scmc, monkeypatch, rc):
+    """A CTA of the TMA-pipelined kernel walks over up to 128 replicas (alive replicas compacted 32 at a time, acceptance counts flushed every
+    32 visits): whatever the chunking (ragged last chunk included), mode 5 realises the direct-gather chain bit for bit and mode 6 its own."""
+    monkeypatch.setenv("SCMC_TMA_MINCTAS", "1")           # keep the requested chunk although the grid is small
+    R = 150
+    mk = lambda: scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 48, 1, n_replicas=R, precision=32, seed=99, stream=2)
+    beta = np.geomspace(0.5, 50.0, R); sigma = np.geomspace(0.8, 0.03, R)
+    ref = mk(); ref.set_sweep_mode(3); ref.set_lanes(1)
+    acc_r, _ = ref.sweep(2, beta, sigma, hits=2)
+    monkeypatch.setenv("SCMC_TMA_RC", "16")
+    tc_ref = mk(); tc_ref.set_sweep_mode(6); tc_ref.set_lanes(1)
+    acc_t, _ = tc_ref.sweep(2, beta, sigma, hits=2)
+    monkeypatch.setenv("SCMC_TMA_RC", str(rc))
+    a = mk(); a.set_sweep_mode(5); a.set_lanes(1)
+    acc_a, att_a = a.sweep(2, beta, sigma, hits=2)
+    assert np.array_equal(acc_a, acc_r) and np.all(att_a == 2 * 2 * a.nSites) and np.array_equal(a.get_state(), ref.get_state())
+    b = mk(); b.set_sweep_mode(6); b.set_lanes(1)
+    acc_b, _ = b.sweep(2, beta, sigma, hits=2)
+    assert np.array_equal(acc_b, acc_t) and np.array_equal(b.get_state(), tc_ref.get_state())
+    for c in (ref, tc_ref, a, b):
+        c.close()
