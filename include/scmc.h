@@ -94,9 +94,11 @@ int32_t scmc_sweep_async(scmc_t* h, int64_t n_sweeps, int32_t hits, uint64_t see
  * 1 = streaming colour-pass kernel, 2 = replica-resident cluster kernel; psi-gather family (neighbours enter through their
  * states via density-matrix sums, one coupling label only): 3 = streaming with a per-thread gather, 4 = replica-resident,
  * 5 = streaming, TMA-pipelined (cp.async.bulk + mbarrier ring; classes that do not decompose into bulk copies fall back to the
- * gather of mode 3; this is what auto uses for streaming passes of the psi family).  Kernels of one family produce
- * bit-identical chains; the two families differ by rounding.  Auto picks the family from the model alone (never from the replica
- * count), so sharding replicas over GPUs cannot change a chain.  batch = replicas per batch for the streaming path (0 = all). */
+ * gather of mode 3), 6 = mode 5 with the 16x16 mat-vec of a site visit on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split,
+ * accumulator in tensor memory; FP32 only -- this is what auto uses for streaming FP32 passes of the psi family unless SCMC_TC=0).
+ * Kernels of one family produce bit-identical chains, except that mode 6 follows the psi-family chain to rounding (different
+ * summation order in the mat-vec); the two families differ by rounding.  Auto picks the family from the model alone (never from
+ * the replica count).  batch = replicas per batch for the streaming path (0 = all). */
 int32_t scmc_set_sweep_mode(scmc_t* h, int32_t mode, int64_t batch);
 /* Random stream of the stream-driven sweeps (the chain definition; stands in for randn!(local_rng(), ...) and rand(),
  * MonteCarlo.jl:255-256, 278): 1 (default) = Philox4x32-10, two calls and 24-bit Box-Muller pairs per update; 2 = Philox4x32-7, one call
