@@ -15,8 +15,11 @@
 namespace scmc {
 
 constexpr int NG = 16;        // number of generators
-constexpr int MAXC = 8;       // max colours
-constexpr int MAXL = 3;       // max coupling labels handled by the unrolled kernels
+#ifndef SCMC_MAXL
+#define SCMC_MAXL 3           // build-time: most coupling labels of a model (kernels are unrolled over the labels; -DSCMC_MAXL=6 builds a six-label library)
+#endif
+constexpr int MAXC = 16;      // max colours (colour-class offsets travel in the kernel parameters)
+constexpr int MAXL = SCMC_MAXL;
 constexpr uint64_t VISIT_INIT = (1ull << 60) - 1;  // reserved visit number of scmc_randomize
 
 template <class R> struct V4;

@@ -1475,7 +1475,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     SCMC_ARG(n_sites > 0 && n_sites <= (1ll << 27), "scmc_create: n_sites out of range (1 .. 2^27)");
     SCMC_ARG(n_replicas > 0, "scmc_create: n_replicas must be positive");
     SCMC_ARG(z_max > 0 && nbr_site && nbr_label, "scmc_create: neighbour tables required");
-    SCMC_ARG(n_labels >= 1 && n_labels <= MAXL, "scmc_create: 1..3 coupling labels supported");
+    SCMC_ARG(n_labels >= 1 && n_labels <= MAXL, "scmc_create: more coupling labels than this build supports (1..SCMC_MAXL, default 3; rebuild with -DSCMC_MAXL=<n>)");
     SCMC_ARG(J && K && gen_re && gen_im && gensq_re && gensq_im, "scmc_create: null coupling / generator table");
     SCMC_ARG(d == 4 || d == 6, "scmc_create: local dimension d must be 4 (n=1,3) or 6 (n=2)");
 
@@ -1573,7 +1573,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     }
     int ncol = 0;
     for (int64_t i = 0; i < N; i++) {
-        if (h->colour[i] < 0 || h->colour[i] >= MAXC) { delete h; set_error("scmc_create: colour outside 0..7 (too many colours)"); return SCMC_ERR_ARG; }
+        if (h->colour[i] < 0 || h->colour[i] >= MAXC) { delete h; set_error("scmc_create: colour outside 0..15 (too many colours)"); return SCMC_ERR_ARG; }
         ncol = std::max(ncol, h->colour[i] + 1);
     }
     for (int64_t i = 0; i < N; i++)

@@ -914,3 +914,30 @@ def test_tma_replicas_per_cta_do_not_change_chains(scmc, monkeypatch, rc):
     assert np.array_equal(acc_b, acc_t) and np.array_equal(b.get_state(), tc_ref.get_state())
     for c in (ref, tc_ref, a, b):
         c.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_more_than_eight_colours(scmc, oracle_mod, mode):
+    """Up to 16 colour classes (the reference visits random sites, so any proper colouring is a legitimate order here): a 12-class refinement of
+    the triangular 3-colouring; the FP64 chain of every sweep kernel follows the oracle's chain in the same class order."""
+    seed = 2718
+    base = scmc.initializeCfg("nearest-neighbor", "triangular", [random_symmetric_J(5)], 12, 1, n_replicas=1, precision=64, seed=seed)
+    colour = base.colour + 3 * (np.arange(base.nSites) % 4)         # proper: neighbours already differ mod 3
+    base.close()
+    assert len(set(colour.tolist())) == 12
+    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [random_symmetric_J(5)], 12, 1, n_replicas=2, precision=64, seed=seed, replica_offset=3, colour=colour, stream=2)
+    info = cfg.info()
+    assert info["n_colours"] == 12
+    if (mode == 2 and not info["resident"]) or (mode == 4 and not info["resident_psi"]):
+        pytest.skip("resident kernel of this family not available for the model")
+    cfg.set_sweep_mode(mode)
+    o = make_oracle(cfg, oracle_mod)
+    o.randomize_v1(seed, 4)
+    acc, _ = cfg.sweep(3, np.array([1.0, 3.0]), np.array([0.5, 0.3]))
+    a = o.sweeps_colour(2, 3, 2, cfg.colour, 3.0, 0.3, seed, 4, 0)
+    assert acc[1] == a
+    assert np.allclose(cfg.get_state(1, 1)[0], o.get_state(), atol=1e-10)
+    assert abs(cfg.energies()[1] - o.energy()) < 1e-9 * cfg.nSites
+    with pytest.raises(scmc._lib.ScmcError, match="colour"):
+        scmc.initializeCfg("nearest-neighbor", "triangular", [random_symmetric_J(5)], 12, 1, n_replicas=1, precision=64, seed=seed,
+                           colour=base.colour + 3 * (np.arange(base.nSites) % 6))      # 18 classes: over the limit
