@@ -211,10 +211,13 @@ constexpr uint32_t TC_LBO = 256, TC_SBO = 128;                       // Jq in co
 constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);      // D = F32, A = B = TF32, K-major, N = 16, M = 128
 // Tensor memory of a CTA: A_hi 16 + A_lo 16 + 4 warps x D 16 = 96 columns, taken as THREE allocations of 32 columns (allocations are powers of
 // two: one of 128 would cap the SM at 4 CTAs; equal-sized pieces cannot fragment the 512 columns, 5 CTAs x 3 = 15 of 16 pieces).
-#ifndef SCMC_TC_CTA
-#define SCMC_TC_CTA 1            // 1: ONE set of MMAs per tile visit, issued by one warp once all four have stored their rows (a quarter of the tensor work);
-#endif                           // 0: every warp issues its own MMAs into its own D columns (no rendezvous inside the CTA)
-constexpr int TC_TMEM_COLS = SCMC_TC_CTA ? 64 : 32, TC_TMEM_ALLOCS = SCMC_TC_CTA ? 1 : 3;
+#ifndef SCMC_TC_PIPE
+#define SCMC_TC_PIPE 0           // 1: the MMAs of visit it + 1 run during the hits of visit it (two A / D buffers: three allocations of 32 columns);
+#endif                           // 0: MMAs, random numbers and hits of a visit in sequence (one allocation of 64 columns).  Measured on C5 (profiles/README.md):
+                                 // pipelined 5.45e10 burst / 5.16e10 sustained against 5.57e10 / 5.24e10 -- the wait on the commit barrier moves, it does not go away
+// ONE set of MMAs per tile visit, issued by one warp once all four have stored their rows.  (Every warp its own MMAs into its own D columns -- no
+// rendezvous inside the CTA, four times the tensor work -- was 5.5 % slower under the power cap: profiles/README.md.)
+constexpr int TC_TMEM_COLS = SCMC_TC_PIPE ? 32 : 64, TC_TMEM_ALLOCS = SCMC_TC_PIPE ? 3 : 1;
 #ifndef SCMC_TC_BLOCKS
 #define SCMC_TC_BLOCKS 5         // CTAs per SM the tensor-core variant is compiled for
 #endif
@@ -346,18 +349,20 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
 #pragma unroll
             for (int s = 0; s < TMA_STAGES; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + TMA_STAGES + s), TMA_TILE / 32); }
             if (TC)
-                for (int w = 0; w < TMA_TILE / 32; w++) mbar_init(smem_u32(bars + 2 * TMA_STAGES + w), (SCMC_TC_CTA && w == 1) ? TMA_TILE / 32 : 1);
+                for (int w = 0; w < 4; w++) mbar_init(smem_u32(bars + 2 * TMA_STAGES + w), w >= 2 ? TMA_TILE / 32 : 1);      // D ready 0 / 1, A stored 0 / 1
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
     if (TC) tc_fence_before();
     __syncthreads();
     if (TC) tc_fence_after();
-    // TC: TMEM columns of this CTA (A_hi, A_lo shared by the warps; D per warp), this warp's lanes, its completion barrier, the B descriptors
-    const uint32_t tm = TC ? s_tmem[0] : 0u, tm_lane = (uint32_t)(warp * 32) << 16;
-    const uint32_t tm_ahi = tm, tm_alo = tm + 16, tm_d = !TC ? 0u : SCMC_TC_CTA ? tm + 32 : s_tmem[1 + (warp >> 1)] + 16 * (warp & 1);
-    // completion barrier of the MMAs: per warp, or (CTA-wide MMAs) barrier 0 = "D ready", barrier 1 = "all four warps stored their A rows"
-    const uint32_t tc_bar = smem_u32(bars + 2 * TMA_STAGES + (SCMC_TC_CTA ? 0 : warp)), tc_abar = smem_u32(bars + 2 * TMA_STAGES + 1);
+    // TC: tensor-memory columns of this CTA.  In-visit MMAs (SCMC_TC_PIPE = 0): one allocation of 64 columns = A_hi 16 | A_lo 16 | D 16.  Pipelined by one
+    // visit (SCMC_TC_PIPE = 1): three allocations of 32 columns = A buffer 0 (hi | lo), A buffer 1, D buffers 0 | 1.  Barriers: "D ready" 0 / 1, "A stored
+    // by all four warps" 0 / 1 (buffer = visit & 1; each completes once per two visits, so nobody can run a whole phase ahead of a waiter).
+    const uint32_t tm_lane = (uint32_t)(warp * 32) << 16;
+    auto tm_a = [&](int buf) -> uint32_t { return SCMC_TC_PIPE ? s_tmem[buf] : s_tmem[0]; };
+    auto tm_d = [&](int buf) -> uint32_t { return SCMC_TC_PIPE ? s_tmem[2] + 16 * buf : s_tmem[0] + 32; };
+    const uint32_t tc_bar0 = smem_u32(bars + 2 * TMA_STAGES);      // + 8 * buf: D ready; + 16 + 8 * buf: A stored
     const uint64_t tc_bhi = tc_smem_desc(smem_u32(sJt), TC_LBO, TC_SBO), tc_blo = tc_smem_desc(smem_u32(sJt + NG * NG), TC_LBO, TC_SBO);
     const int n_it = s_nit;
     const size_t ps = (size_t)M.nrep * M.Ns;
@@ -394,18 +399,18 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
     unsigned tot_mine = 0;
     char* const own = reinterpret_cast<char*>(M.psi + rb * M.Ns + p);      // own state of the chunk's first replica (plane 0)
     const uint32_t rep_bytes = (uint32_t)M.Ns * VB;
-    for (int it = 0; it < n_it; it++) {
+    constexpr bool PRE = TC && HITS == 2 && STREAM == 2 && SCMC_TC_PRE;    // both hits' random numbers are generated while the tensor core works
+    constexpr bool PIPE = TC && SCMC_TC_PIPE;                              // the MMAs of visit it + 1 are in flight during the hits of visit it
+
+    // ---- front half of a visit: wait for the stage, own state -> re / im, density sums of the neighbours -> P, release the stage, (warp 0) refill it
+    auto gather = [&](int it, R* re, R* im, R* P) {
         const int s = it % TMA_STAGES;
         const uint32_t parity = (it / TMA_STAGES) & 1;
-        const int rl = sRep[it];
-        const int64_t r = rb + rl;
-        const R sigma = sSigma[it], nbeta = neg_beta_scaled(sBeta[it]);
 #if SCMC_TMA_ABLATE == 4                                   // timing only: the first two replicas' states are consumed over and over, no refill, no wait
         if (it < TMA_STAGES)
 #endif
         mbar_wait(bar0 + 8 * s, parity);
         const unsigned char* st = smem + s * stage_bytes;
-        R re[D], im[D], P[NP];
 #pragma unroll
         for (int v = 0; v < NPV; v++) {
             const V q = *reinterpret_cast<const V*>(st + v * plane_bytes + off[0]);
@@ -439,55 +444,52 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
             mbar_wait(bar0 + 8 * (TMA_STAGES + s), parity);
             issue(it + TMA_STAGES, s);
         }
+    };
+    // ---- tensor-core mat-vec, part 1: this thread's 16 sums, split into TF32 head and tail, to its lane of A buffer `buf`; arrive on "A stored"
+    auto tc_store = [&](const R* P, int buf) {
+        uint32_t hi[NG], lo[NG];
+#pragma unroll
+        for (int t = 0; t < NG; t++) {
+            hi[t] = __float_as_uint(P[t]) & 0xFFFFE000u;
+            lo[t] = __float_as_uint(P[t] - __uint_as_float(hi[t]));
+        }
+        tmem_st16(tm_lane | tm_a(buf), hi);
+        tmem_st16(tm_lane | (tm_a(buf) + 16), lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tc_bar0 + 16 + 8 * buf);
+    };
+    // ---- part 2 (warp 1; warp 0 carries the stage refills): once all four warps have stored their rows of visit `it`, one elected thread issues
+    //      P_lo Jq_hi + P_hi Jq_lo + P_hi Jq_hi into D buffer `buf` and commits to "D ready"
+    auto tc_issue = [&](int it, int buf) {
+        mbar_wait(tc_bar0 + 16 + 8 * buf, (uint32_t)(PIPE ? it >> 1 : it) & 1u);
+        if (elect_one()) {                                      // elect.sync: ptxas then emits the MMAs straight, without a loop over the active lanes
+            tc_fence_after();
+            constexpr uint32_t KS = (2 * TC_LBO) >> 4;          // descriptor step of one K = 8 slice
+            const uint32_t ahi = tm_a(buf), alo = ahi + 16, d = tm_d(buf);
+            tc_mma_tf32_ts(d, alo, tc_bhi, TC_IDESC, 0);
+            tc_mma_tf32_ts(d, alo + 8, tc_bhi + KS, TC_IDESC, 1);
+            tc_mma_tf32_ts(d, ahi, tc_blo, TC_IDESC, 1);
+            tc_mma_tf32_ts(d, ahi + 8, tc_blo + KS, TC_IDESC, 1);
+            tc_mma_tf32_ts(d, ahi, tc_bhi, TC_IDESC, 1);
+            tc_mma_tf32_ts(d, ahi + 8, tc_bhi + KS, TC_IDESC, 1);
+            tc_commit(tc_bar0 + 8 * buf);
+        }
+        __syncwarp();
+    };
+    // ---- back half of a visit: (random numbers,) energy coefficients, the hits, store, acceptance counts
+    auto finish_visit = [&](int it, R* re, R* im, const R* P, int next_to_issue) {
+        const int rl = sRep[it];
+        const int64_t r = rb + rl;
+        const R sigma = sSigma[it], nbeta = neg_beta_scaled(sBeta[it]);
         R Hq[NG];
-        R eloc;
         unsigned mine = 0;
         uint32_t uw[4];                                            // stream v2: acceptance-uniform words of the current group of four visits
         const int n_hits = HITS ? HITS : A.hits;                   // HITS = 2: the two hits of the reference's 2N-update sweep, unrolled
-        constexpr bool PRE = TC && HITS == 2 && STREAM == 2 && SCMC_TC_PRE;       // both hits' random numbers are generated while the tensor core works
         R pxr[PRE ? 2 : 1][D], pxi[PRE ? 2 : 1][D];
         if constexpr (TC) {
-            uint32_t hi[NG], lo[NG];
-#pragma unroll
-            for (int t = 0; t < NG; t++) {
-                hi[t] = __float_as_uint(P[t]) & 0xFFFFE000u;
-                lo[t] = __float_as_uint(P[t] - __uint_as_float(hi[t]));
-            }
-            tmem_st16(tm_lane | tm_ahi, hi);
-            tmem_st16(tm_lane | tm_alo, lo);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-#if SCMC_TC_CTA
-            if (lane == 0) mbar_arrive(tc_abar);                // this warp's rows of A are in tensor memory
-            if (warp == 1) {                                    // (warp 0 carries the stage refills)
-                mbar_wait(tc_abar, (uint32_t)it & 1u);
-                if (elect_one()) {                              // elect.sync: ptxas then emits the MMAs straight, without a loop over the active lanes
-                    tc_fence_after();
-                    constexpr uint32_t KS = (2 * TC_LBO) >> 4;  // descriptor step of one K = 8 slice
-                    tc_mma_tf32_ts(tm_d, tm_alo, tc_bhi, TC_IDESC, 0);
-                    tc_mma_tf32_ts(tm_d, tm_alo + 8, tc_bhi + KS, TC_IDESC, 1);
-                    tc_mma_tf32_ts(tm_d, tm_ahi, tc_blo, TC_IDESC, 1);
-                    tc_mma_tf32_ts(tm_d, tm_ahi + 8, tc_blo + KS, TC_IDESC, 1);
-                    tc_mma_tf32_ts(tm_d, tm_ahi, tc_bhi, TC_IDESC, 1);
-                    tc_mma_tf32_ts(tm_d, tm_ahi + 8, tc_bhi + KS, TC_IDESC, 1);
-                    tc_commit(tc_bar);
-                }
-            }
-#else
-            if (elect_one()) {                                  // elect.sync: ptxas then emits the MMAs straight, without a loop over the active lanes
-                tc_fence_after();
-                constexpr uint32_t KS = (2 * TC_LBO) >> 4;          // descriptor step of one K = 8 slice
-                tc_mma_tf32_ts(tm_d, tm_alo, tc_bhi, TC_IDESC, 0);
-                tc_mma_tf32_ts(tm_d, tm_alo + 8, tc_bhi + KS, TC_IDESC, 1);
-                tc_mma_tf32_ts(tm_d, tm_ahi, tc_blo, TC_IDESC, 1);
-                tc_mma_tf32_ts(tm_d, tm_ahi + 8, tc_blo + KS, TC_IDESC, 1);
-                tc_mma_tf32_ts(tm_d, tm_ahi, tc_bhi, TC_IDESC, 1);
-                tc_mma_tf32_ts(tm_d, tm_ahi + 8, tc_bhi + KS, TC_IDESC, 1);
-                tc_commit(tc_bar);
-            }
-#endif
-            __syncwarp();
+            const int buf = PIPE ? (it & 1) : 0;
             uint32_t tc_dep = 0;
             if constexpr (PRE) {
 #pragma unroll
@@ -502,9 +504,11 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
                     for (int k = 0; k < D; k++) tc_dep ^= __float_as_uint(pxr[hit][k]);
                 tc_dep &= (uint32_t)T.first >> 31;
             }
-            mbar_wait(tc_bar, ((uint32_t)it & 1u) ^ tc_dep);
+            // pipelined: the MMAs of the NEXT visit are issued here, after this warp's random numbers (the other warps have stored their rows by then)
+            if (PIPE && warp == 1 && next_to_issue >= 0) tc_issue(next_to_issue, next_to_issue & 1);
+            mbar_wait(tc_bar0 + 8 * buf, ((uint32_t)(PIPE ? it >> 1 : it) & 1u) ^ tc_dep);
             tc_fence_after();
-            tmem_ld16(tm_lane | tm_d, Hq);
+            tmem_ld16(tm_lane | tm_d(buf), Hq);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         } else {
 #if SCMC_TMA_ABLATE == 1
@@ -514,7 +518,7 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
             field_from_sums_smem<1>(sJt, (const R(*)[NG])P, Hq);       // Hq = Jq . Psum
 #endif
         }
-        eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
+        R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
 #pragma unroll
         for (int hit = 0; hit < n_hits; hit++) {
             R xr[D], xi[D], u, dE;
@@ -551,6 +555,40 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
         } else {
             const unsigned tot = __reduce_add_sync(0xffffffffu, mine);
             if (lane == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
+        }
+    };
+
+    if constexpr (PIPE) {
+        // software pipeline, one visit deep: gather + tcgen05.st of visit it + 1, then the hits of visit it; the MMAs of a visit have a whole visit
+        // of slack before their result is needed, so a warp never waits for the slowest warp of its CTA plus the MMA latency
+        R re[D], im[D];
+        if (n_it > 0) {
+            R P[NP];
+            gather(0, re, im, P);
+            tc_store(P, 0);
+            if (warp == 1) tc_issue(0, 0);
+        }
+        for (int it = 0; it < n_it; it++) {
+            R nre[D], nim[D];
+            const bool more = it + 1 < n_it;
+            if (more) {
+                R P[NP];
+                gather(it + 1, nre, nim, P);
+                tc_store(P, (it + 1) & 1);
+            }
+            finish_visit(it, re, im, nullptr, more ? it + 1 : -1);
+#pragma unroll
+            for (int k = 0; k < D; k++) { re[k] = nre[k]; im[k] = nim[k]; }
+        }
+    } else {
+        for (int it = 0; it < n_it; it++) {
+            R re[D], im[D], P[NP];
+            gather(it, re, im, P);
+            if constexpr (TC) {
+                tc_store(P, 0);
+                if (warp == 1) tc_issue(it, 0);
+            }
+            finish_visit(it, re, im, P, -1);
         }
     }
     if constexpr (TC) {
