@@ -647,8 +647,9 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
     TmaArgs T;
     T.meta = (const uint4*)h->tma.d_meta; T.runs = (const uint2*)h->tma.d_runs; T.tile = h->tma.d_tile;
     T.first = C.first; T.cap = h->tma.cap;
-    // replicas per CTA: TMA_RC, fewer when that leaves the chip with less than a few waves of CTAs (small shards)
-    const int rc_env = getenv("SCMC_TMA_RC") ? atoi(getenv("SCMC_TMA_RC")) : 0, min_ctas = getenv("SCMC_TMA_MINCTAS") ? atoi(getenv("SCMC_TMA_MINCTAS")) : 3000;      // (read per launch: tests switch them)
+    // replicas per CTA: up to 64, fewer when that leaves the chip with less than about one wave of CTAs (small shards).  Measured (bench.py, sustained):
+    // a threshold of 650 against 3000 CTAs per launch: 256 replicas 4.74 against 4.28e10, 1024 replicas (the 8-GPU shard) 5.21 against 4.94e10, 8192 equal
+    const int rc_env = getenv("SCMC_TMA_RC") ? atoi(getenv("SCMC_TMA_RC")) : 0, min_ctas = getenv("SCMC_TMA_MINCTAS") ? atoi(getenv("SCMC_TMA_MINCTAS")) : 650;       // (read per launch: tests switch them)
     int rc = rc_env > 0 && rc_env <= TMA_RC ? rc_env : 64;      // measured on C5: 16 -> 5.18e10, 32 -> 5.38e10, 64 -> 5.40e10, 128 -> 5.39e10 (tensor-core variant)
     while (rc > 2 && (int64_t)C.n_tiles * ((A.rcount + rc - 1) / rc) < min_ctas) rc /= 2;
     T.rc = rc;
