@@ -8,10 +8,10 @@ import torch
 
 Jtg = [1.0, 0.3, 0.2, 0.1, 0.5]
 for L, n, R in ((48, 2, 1024), (48, 1, 1024), (12, 2, 4096), (96, 2, 256)):
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 3):
         cfg = scmc.initializeCfg("tg-hbn", "triangular", Jtg, L, n, n_replicas=R, precision=32, seed=1)
         info = cfg.info()
-        if mode == 2 and not info["resident"]:
+        if (mode == 2 and not info["resident"]) or (mode == 3 and n == 2):
             cfg.close()
             continue
         cfg.set_sweep_mode(mode)

@@ -84,12 +84,13 @@ struct scmc_handle {
     int8_t* lab = nullptr;
     void *beta = nullptr, *sigma = nullptr;      // [R] reals of the handle's precision
     void* d_Jt = nullptr;                        // [MAXL][16][16] transposed couplings (kernel stages them into shared memory)
-    void* d_Jqt = nullptr;                       // [16][16] transposed couplings in the density basis, Jq = C^T J C (psi family, 16 density entries)
+    void* d_Jqt = nullptr;                       // [MAXL][16][16] transposed couplings in the density basis, Jq_l = C^T J_l C (psi family, 16 density entries)
     // several labels: neighbour slots are stably sorted by label at create; when every site has the same number of bonds per label,
     // label l owns slots [lab_off[l], lab_off[l+1]) at every site and the kernels accumulate one label at a time in registers
     int32_t lab_off[scmc::MAXL + 1] = {0};
     bool label_major = false;
     bool fused_density = false;                  // psi kernels go straight from density sums to energy coefficients (d_Jqt valid)
+    bool psi_labels = false;                     // several labels, d = 4, label-major slots: the psi-gather family is available through k_sweep_colour_psi_nl (d_Jqt holds one table per label)
     unsigned long long* acc = nullptr;           // [R] accepted-update counters
     uint8_t* active = nullptr;                   // [R] replica still running (annealing) -- nullptr semantics handled by callers
     double* obs = nullptr;                       // [R][SCMC_NOBS] scratch rows

@@ -521,6 +521,97 @@ __global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEE
     if ((threadIdx.x & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
 }
 
+// psi-gather colour pass for SEVERAL coupling labels (d = 4, 16 density entries, no on-site term, label-major neighbour slots: TG/h-BN at n = 1, 3).
+// Neighbours enter through their states (32 B instead of a 64-B T vector), one label at a time: the label's density sums in 16 registers, then that
+// label's share Jq_l . P_l of the energy coefficients (field_accumulate_smem); the hits are those of the one-label psi family (metropolis_hit_psi:
+// e(psi) = sum_n Hq[n] P_n(psi)), nothing but psi is written and the T planes become the lazily refreshed cache (T_stale / ensure_T).
+// Reference work unit: localUpdate! with getEnergyDifference!'s per-bond mat-vecs (src/MonteCarlo.jl:263-286, src/Configuration.jl:278-298).
+template <class R, int GEN, int NL>
+__global__ void __launch_bounds__(SCMC_SWEEP_THREADS, sizeof(R) == 8 ? SCMC_SWEEP_PSI_BLOCKS_F64 : SCMC_SWEEP_BLOCKS) k_sweep_colour_psi_nl(const __grid_constant__ DevModel<R, NL> M, const SweepArgs A) {
+    constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
+    static_assert(NP == NG && D == 4, "16 density entries, d = 4");
+    constexpr bool F32 = sizeof(R) == 4;
+    const int64_t r = A.r0 + blockIdx.y;
+    __shared__ __align__(16) R sJq[NL * NG * NG];
+    for (int t = threadIdx.x; t < NL * NG * NG; t += blockDim.x) sJq[t] = ((const R*)A.Jqt)[t];
+    const bool alive = (A.active == nullptr || A.active[r]);
+    const R beta = ((const R*)A.beta)[r], sigma = ((const R*)A.sigma)[r];
+    const R nbeta = neg_beta_scaled(beta);
+    const size_t ps = (size_t)M.nrep * M.Ns;
+    const int64_t rbase = r * M.Ns;
+    unsigned long long Pq[NPV];               // opaque bases of the replica's psi planes (one mad.wide per gather load)
+#pragma unroll
+    for (int v = 0; v < NPV; v++) {
+        Pq[v] = (unsigned long long)(M.psi + rbase + v * ps);
+        asm volatile("" : "+l"(Pq[v]));
+    }
+    const unsigned stride = (unsigned)M.N;
+    __syncthreads();
+    unsigned nacc = 0;
+    for (int colour = A.colour; colour <= A.colour_last; colour++) {
+        const int nc = M.col_off[colour + 1] - M.col_off[colour];
+        for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nc && alive; s += gridDim.x * blockDim.x) {
+            const int cp = M.col_off[colour] + s;
+            const int p = M.col_list[cp];
+            const int site = M.cls_site[cp];
+            R re[D], im[D], Hq[NG];
+            load_psi<R, D>(M.psi + rbase + p, ps, re, im);
+            const int32_t* nb = M.cls_nbr + cp;
+            unsigned long long hp[NG / 2];
+            if constexpr (F32) {
+#pragma unroll
+                for (int i = 0; i < NG / 2; i++) hp[i] = 0ull;
+            } else {
+#pragma unroll
+                for (int a = 0; a < NG; a++) Hq[a] = R(0);
+            }
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+                const int k1 = A.lab_off[l + 1];
+                if (A.lab_off[l] == k1) continue;              // label without bonds (fewer labels than the build's maximum)
+                R P[NP];
+#pragma unroll
+                for (int t = 0; t < NP; t++) P[t] = R(0);
+                for (int k = A.lab_off[l]; k < k1; k += 3) {
+                    unsigned j[3];
+#pragma unroll
+                    for (int t = 0; t < 3; t++) j[t] = (k + t < k1) ? (unsigned)nb[(unsigned)(k + t) * stride] : stride;      // past the label's range: zero site
+                    vec4<R> v[3][NPV];
+#pragma unroll
+                    for (int t = 0; t < 3; t++)
+#pragma unroll
+                        for (int q = 0; q < NPV; q++) v[t][q] = *reinterpret_cast<const vec4<R>*>(Pq[q] + (unsigned long long)j[t] * sizeof(vec4<R>));
+#pragma unroll
+                    for (int t = 0; t < 3; t++) {
+                        R nr[D], ni[D];
+#pragma unroll
+                        for (int q = 0; q < NPV; q++) { nr[2 * q] = v[t][q].x; ni[2 * q] = v[t][q].y; nr[2 * q + 1] = v[t][q].z; ni[2 * q + 1] = v[t][q].w; }
+                        GenOps<GEN>::density_acc(nr, ni, P);
+                    }
+                }
+                if constexpr (F32) field_accumulate_smem((const float*)sJq + l * NG * NG, (const float*)P, hp);
+                else field_accumulate_smem((const double*)sJq + l * NG * NG, (const double*)P, (double*)Hq);
+            }
+            if constexpr (F32) {
+#pragma unroll
+                for (int i = 0; i < NG / 2; i++) asm("mov.b64 {%0, %1}, %2;" : "=f"(Hq[2 * i]), "=f"(Hq[2 * i + 1]) : "l"(hp[i]));
+            }
+            R eloc = GenOps<GEN>::energy_from_state(re, im, Hq);
+            unsigned mine = 0;
+            for (int hit = 0; hit < A.hits; hit++) {
+                R xr[D], xi[D], u, dE;
+                stream_any<R, D>(A.stream, A.seed, (uint32_t)site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
+                mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+            }
+            if (mine) store_psi<R, D>(M.psi + rbase + p, ps, re, im);
+            nacc += mine;
+        }
+        if (colour < A.colour_last) __syncthreads();
+    }
+    const unsigned tot = __reduce_add_sync(0xffffffffu, nacc);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(A.acc + r, (unsigned long long)tot);
+}
+
 // cp.async-pipelined form of k_sweep_colour_psi (FP32): the next visit's neighbour states and own state are staged in shared
 // memory (14 x 16 B per thread for d = 4, z = 6 -> 28 KB per CTA, 5 CTAs/SM), indices two visits ahead in registers.
 template <int GEN, bool ONSITE>
@@ -1189,8 +1280,12 @@ int32_t upload_scalars(scmc_handle* h, const double* beta, const double* sigma) 
 // Which arithmetic family the production (stream-driven) sweeps of this handle use.  It depends on the model only -- never on
 // the replica count or the number of sweeps per call -- so that a replica's chain is identical however replicas are sharded.
 bool uses_psi_gather(const scmc_handle* h) {
-    if (h->sweep_mode == 3 || h->sweep_mode == 4 || h->sweep_mode == 5 || h->sweep_mode == 6) return h->n_labels == 1 && h->gen_id <= 3;
+    if (h->sweep_mode == 3 || h->sweep_mode == 4 || h->sweep_mode == 5 || h->sweep_mode == 6) return (h->n_labels == 1 && h->gen_id <= 3) || h->psi_labels;
     if (h->sweep_mode == 1 || h->sweep_mode == 2) return false;
+    // several labels with d = 4 (TG/h-BN at n = 1, 3): the streaming psi-gather kernel moves half the bytes per neighbour and has the cheap hits (measured on
+    // 48x48 x 1024: 2.24e10 updates/s against 1.78e10 for the streaming and 1.39e10 for the resident T-gather kernel); colour passes too small to fill the chip
+    // (launch-bound) stay with the replica-resident T-gather kernel where that one is eligible
+    if (h->psi_labels) return !(h->res.eligible && resident_preferred(h) && h->R * h->N / std::max(1, h->n_col) < 300000);
     return h->gen_id <= 3 && h->n_labels == 1 && (h->d == 4 || h->onsite) && !h->res_family_T;      // measured: d = 6 without on-site term is on par / slightly faster with T-gather
 }
 
@@ -1298,6 +1393,9 @@ static int32_t launch_colour_pass(scmc_handle* h, const SweepArgs& A, cudaStream
                         }
                     }
                     if (!launched) k_sweep_colour_psi<R, GEN, ONS><<<grid, SCMC_SWEEP_THREADS, 0, stream>>>(M, B);
+                } else if constexpr (!ONS && GenOps<GEN>::NDENS == NG) {
+                    B.Jqt = h->d_Jqt;                              // one table per label
+                    k_sweep_colour_psi_nl<R, GEN, NL><<<grid, SCMC_SWEEP_THREADS, 0, stream>>>(M, B);
                 }
                 h->T_stale = true;
             } else if constexpr (std::is_same<R, float>::value && NL == 1) {
@@ -1393,7 +1491,7 @@ int32_t launch_sweeps(scmc_handle* h, int64_t n_sweeps, int32_t hits, uint64_t s
 }
 
 int32_t launch_measure(scmc_handle* h, double* d_rows, double* d_Etot) {
-    const bool psi = uses_psi_gather(h);
+    const bool psi = uses_psi_gather(h) && h->n_labels == 1;      // several labels: the T-family measurement kernel on the (refreshed) T planes
     if (!psi) SCMC_TRY(ensure_T(h));
     // CTAs per replica: SCMC_SWEEP_TILES site tiles each, at most 64, and enough CTAs over all replicas to fill the chip
     const int64_t tiles = (h->N + SCMC_MEASURE_THREADS - 1) / SCMC_MEASURE_THREADS;
@@ -1668,7 +1766,7 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     A((void**)&h->d_cls_site, N * sizeof(int32_t));
     A((void**)&h->d_cls_nbr, (size_t)h->z * N * sizeof(int32_t));
     A(&h->d_Jt, (size_t)MAXL * 256 * h->esz());
-    A(&h->d_Jqt, (size_t)256 * h->esz());
+    A(&h->d_Jqt, (size_t)MAXL * 256 * h->esz());
     A(&h->beta, h->R * h->esz());
     A(&h->sigma, h->R * h->esz());
     A((void**)&h->acc, h->R * sizeof(unsigned long long));
@@ -1702,19 +1800,22 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
                 }
         C(cudaMemcpy(h->d_Jt, jt.data(), jt.size(), cudaMemcpyHostToDevice));
     }
-    if (n_labels == 1 && (gen_id == 1 || gen_id == 3)) {     // 16 density entries: fuse map, couplings and transpose map into one 16x16 matrix
+    if (gen_id == 1 || gen_id == 3) {     // 16 density entries: fuse map, couplings and transpose map into one 16x16 matrix per label
         const int8_t* Cm = gen_id == 1 ? gen::DENSMAP1 : gen::DENSMAP3;
-        std::vector<char> jq((size_t)256 * h->esz(), 0);
-        for (int n = 0; n < 16; n++)
-            for (int m = 0; m < 16; m++) {
-                double v = 0.0;
-                for (int a = 0; a < 16; a++)
-                    for (int b = 0; b < 16; b++) v += (double)Cm[a * 16 + n] * h->J[0][a * 16 + b] * (double)Cm[b * 16 + m];
-                if (precision == 64) ((double*)jq.data())[m * 16 + n] = v;      // transposed: [m][n] = Jq[n][m]
-                else ((float*)jq.data())[m * 16 + n] = (float)v;
-            }
+        std::vector<char> jq((size_t)MAXL * 256 * h->esz(), 0);
+        for (int l = 0; l < n_labels; l++)
+            for (int n = 0; n < 16; n++)
+                for (int m = 0; m < 16; m++) {
+                    double v = 0.0;
+                    for (int a = 0; a < 16; a++)
+                        for (int b = 0; b < 16; b++) v += (double)Cm[a * 16 + n] * h->J[l][a * 16 + b] * (double)Cm[b * 16 + m];
+                    if (precision == 64) ((double*)jq.data())[(l * 16 + m) * 16 + n] = v;      // transposed: [l][m][n] = Jq_l[n][m]
+                    else ((float*)jq.data())[(l * 16 + m) * 16 + n] = (float)v;
+                }
         C(cudaMemcpy(h->d_Jqt, jq.data(), jq.size(), cudaMemcpyHostToDevice));
-        h->fused_density = true;
+        h->fused_density = n_labels == 1;
+        // several labels (TG/h-BN at n = 1, 3): neighbours enter through their states, one density sum and one 16x16 mat-vec per label
+        h->psi_labels = n_labels > 1 && h->label_major && !h->onsite && !(getenv("SCMC_PSI_LABELS") && atoi(getenv("SCMC_PSI_LABELS")) == 0);
     }
     C(cudaMemset(h->psi, 0, plane * (d / 2)));
     C(cudaMemset(h->T, 0, plane * 4));

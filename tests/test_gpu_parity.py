@@ -23,6 +23,8 @@ def build(scmc, kind, precision, R=3, seed=1234, **kw):
         return scmc.initializeCfg("nearest-neighbor", "honeycomb", [Jon, random_symmetric_J(9)], 4, 2, n_replicas=R, precision=precision, seed=seed, **kw)
     if kind == "tghbn":              # 3 labels, 12 neighbours, on-site K, n = 2, 4 colours
         return scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.15, 0.8], 4, 2, n_replicas=R, precision=precision, seed=seed, **kw)
+    if kind == "tghbn_n1":           # TG/h-BN couplings at filling 1: 3 labels, 12 neighbours, d = 4, no on-site term in the dynamics (several-label psi-gather kernel)
+        return scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.15, 0.8], 6, 1, n_replicas=R, precision=precision, seed=seed, **kw)
     if kind == "honey_n2":           # n = 2 (d = 6), no on-site term (BASELINE config C3 couplings: J = 1_16 with J[1,1] = 0), honeycomb L = 4
         Jc3 = np.eye(16); Jc3[0, 0] = 0.0
         return scmc.initializeCfg("nearest-neighbor", "honeycomb", [Jc3], 4, 2, n_replicas=R, precision=precision, seed=seed, **kw)
@@ -121,7 +123,7 @@ def test_sweep_deterministic_bit_exact_masks(scmc, oracle_mod, kind):
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("stream", [1, 2])
-@pytest.mark.parametrize("kind", ["tri_notebook", "honey_n2_onsite"])
+@pytest.mark.parametrize("kind", ["tri_notebook", "honey_n2_onsite", "tghbn_n1"])
 def test_philox_chain_follows_oracle_fp64(scmc, oracle_mod, kind, stream, mode):
     """Counter-based streams v1 / v2: the FP64 device chain of EVERY sweep kernel (auto, streaming / resident T-gather, streaming /
     resident psi-gather) equals the oracle's restatement of the same colour-ordered chain, step results included."""
@@ -941,3 +943,38 @@ def test_more_than_eight_colours(scmc, oracle_mod, mode):
     with pytest.raises(scmc._lib.ScmcError, match="colour"):
         scmc.initializeCfg("nearest-neighbor", "triangular", [random_symmetric_J(5)], 12, 1, n_replicas=1, precision=64, seed=seed,
                            colour=base.colour + 3 * (np.arange(base.nSites) % 6))      # 18 classes: over the limit
+
+
+@pytest.mark.parametrize("n", [1, 3])
+@pytest.mark.parametrize("precision", [32, 64])
+def test_several_label_psi_gather_kernel(scmc, oracle_mod, n, precision):
+    """TG/h-BN couplings at d = 4 (fillings 1, 3): the streaming psi-gather kernel for several coupling labels (k_sweep_colour_psi_nl: neighbours enter through
+    their states, one density sum and one 16x16 mat-vec per label) is what auto runs on lattices too large for the resident T-gather kernel; mode 3 selects it
+    anywhere.  Its chain equals the T-gather chain (mode 1) to rounding (FP64: 1e-9 after whole sweeps), energies / T vectors / measurement rows of the state it
+    leaves agree with the oracle, and the lazily refreshed T cache is consistent."""
+    mk = lambda R, L: scmc.initializeCfg("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.15, 0.8], L, n, n_replicas=R, precision=precision, seed=4711, stream=2)
+    a = mk(3, 12); a.set_sweep_mode(1)
+    b = mk(3, 12); b.set_sweep_mode(3)
+    beta, sigma = np.array([1.0, 4.0, 20.0]), np.array([0.6, 0.3, 0.1])
+    acc_a, _ = a.sweep(3, beta, sigma, hits=2)
+    acc_b, _ = b.sweep(3, beta, sigma, hits=2)
+    if precision == 64:
+        assert np.array_equal(acc_a, acc_b)
+        assert np.allclose(a.get_state(), b.get_state(), atol=1e-9)
+    else:
+        assert np.abs(acc_a.astype(np.int64) - acc_b.astype(np.int64)).max() <= 3
+    tol = 1e-10 if precision == 64 else 2e-5
+    for r in range(3):
+        o = make_oracle(b, oracle_mod)
+        o.set_state(b.get_state(r, 1)[0])
+        assert abs(o.energy() - b.energies()[r]) < tol * b.nSites * 10
+        assert np.allclose(b.get_T(r), o.get_T()[0], atol=tol * 10)          # T planes refreshed on demand after psi-gather sweeps
+    rows = b.measure()
+    assert np.allclose(rows[:, 0] * b.nSites, b.energies(), rtol=0, atol=tol * b.nSites * 10)
+    # auto: large lattice / many replicas -> the several-label psi-gather kernel (launch count of a streaming call), same chain as mode 3
+    c = mk(600, 48); d = mk(600, 48); d.set_sweep_mode(3)
+    bt, sg = np.geomspace(0.5, 20.0, 600), np.geomspace(0.6, 0.05, 600)
+    acc_c, _ = c.sweep(1, bt, sg, hits=2); acc_d, _ = d.sweep(1, bt, sg, hits=2)
+    assert np.array_equal(acc_c, acc_d) and np.array_equal(c.get_state(), d.get_state())
+    for x in (a, b, c, d):
+        x.close()
