@@ -92,7 +92,7 @@ int32_t scmc_sweep(scmc_t* h, int64_t n_sweeps, int32_t hits, const double* beta
 int32_t scmc_sweep_async(scmc_t* h, int64_t n_sweeps, int32_t hits, uint64_t seed, uint64_t sweep_counter);
 /* kernel selection for the stream-driven sweeps: 0 = auto; T-gather family (neighbours enter through the cached T vectors):
  * 1 = streaming colour-pass kernel, 2 = replica-resident cluster kernel; psi-gather family (neighbours enter through their
- * states via density-matrix sums, one coupling label only): 3 = streaming with a per-thread gather, 4 = replica-resident,
+ * states via density-matrix sums; one coupling label, or several at d = 4 for mode 3): 3 = streaming with a per-thread gather, 4 = replica-resident,
  * 5 = streaming, TMA-pipelined (cp.async.bulk + mbarrier ring; classes that do not decompose into bulk copies fall back to the
  * gather of mode 3), 6 = mode 5 with the 16x16 mat-vec of a site visit on the tensor cores (tcgen05.mma kind::tf32, 3xTF32 split,
  * accumulator in tensor memory; FP32 only -- this is what auto uses for streaming FP32 passes of the psi family unless SCMC_TC=0).
