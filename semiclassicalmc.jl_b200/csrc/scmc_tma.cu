@@ -626,7 +626,7 @@ static size_t tma_smem_bytes(const scmc_handle* h, bool tc = true) {
 bool tma_use_tc(const scmc_handle* h) {
     static const int env = getenv("SCMC_TC") ? atoi(getenv("SCMC_TC")) : -1;
     if (h->sweep_mode == 6) return true;
-    if (h->sweep_mode == 5) return false;
+    if (h->sweep_mode != 0) return false;      // 5: the FFMA2 form; 1 - 4 never reach the TMA pass
     return env != 0;
 }
 

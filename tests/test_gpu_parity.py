@@ -857,6 +857,8 @@ def test_tensor_core_variant_follows_the_ffma_chain(scmc, case, stream, coupling
     a = mk(); a.set_sweep_mode(5)
     b = mk(); b.set_sweep_mode(6)
     assert b.info()["tma"] and b.info()["tma_tc"] and not a.info()["tma_tc"]
+    a.set_sweep_mode(3); assert not a.info()["tma_tc"]
+    a.set_sweep_mode(5)
     for hits in (2, 3):                                   # 2: unrolled hits, random numbers generated under the MMA; 3: run-time hit loop
         acc_a, att_a = a.sweep(1, beta, sigma, hits=hits)
         acc_b, att_b = b.sweep(1, beta, sigma, hits=hits)
