@@ -33,17 +33,29 @@ def gather_replicas(local, n_total, group=None, device=None):
         return local
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     per = -(-int(n_total) // world)                                   # padded shard size: all_gather needs equal shapes
-    buf = np.zeros((per,) + local.shape[1:], dtype=local.dtype)
-    buf[:local.shape[0]] = local
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    t = torch.from_numpy(buf).to(device)
-    out = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(out, t, group=group)
+    if local.shape[0] == per:
+        t = torch.from_numpy(local).to(device)
+    else:
+        buf = np.zeros((per,) + local.shape[1:], dtype=local.dtype)
+        buf[:local.shape[0]] = local
+        t = torch.from_numpy(buf).to(device)
+    # one collective into one tensor and ONE copy back to the host (a list of per-rank tensors costs a copy and a synchronisation per rank)
+    full = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=t.dtype, device=device)
+    try:
+        dist.all_gather_into_tensor(full, t, group=group)
+    except (RuntimeError, NotImplementedError, AttributeError):      # backend without the single-tensor form
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t, group=group)
+        full = torch.cat(out, dim=0)
+    host = full.cpu().numpy()
+    if n_total == world * per:
+        return host
     parts = []
-    for r, o in enumerate(out):
+    for r in range(world):
         _, cnt = shard_range(n_total, world, r)
-        parts.append(o.cpu().numpy()[:cnt])
+        parts.append(host[r * per:r * per + cnt])
     return np.concatenate(parts, axis=0)
 
 
