@@ -980,3 +980,23 @@ def test_several_label_psi_gather_kernel(scmc, oracle_mod, n, precision):
     assert np.array_equal(acc_c, acc_d) and np.array_equal(c.get_state(), d.get_state())
     for x in (a, b, c, d):
         x.close()
+
+
+def test_annealing_on_a_tiled_lattice_with_stopped_replicas(scmc):
+    """runAnnealing!'s host-driven cooling loop on a lattice whose colour classes run through the TMA-pipelined kernel: replicas stop one by one (the `active`
+    mask compacts the replica chunk of a CTA), so the kernels see ragged chunks of alive replicas.  Mode 5 = mode 3 bit for bit; the tensor-core variant
+    (mode 6) reaches the same sweep counts within a few sweeps and the same energies within the spread of the restarts."""
+    mk = lambda: scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 48, 1, n_replicas=40, precision=32, seed=1357, stream=2)
+    kw = dict(T_fac=0.8, N_max=260, N_o=0, N_per_T=8, min_acc_per_site=2, min_accrate=0.25, σ_min=0.05, log_rate=0)
+    out = {}
+    for mode in (3, 5, 6):
+        c = mk(); c.set_sweep_mode(mode)
+        assert c.info()["tma"]
+        out[mode] = scmc.runAnnealing_(c, 2.0, **kw)
+        out[mode]["state"] = c.get_state()
+        c.close()
+    a, b, t = out[3], out[5], out[6]
+    assert len(set(a["sweeps"].tolist())) >= 2 and a["sweeps"].min() < 250         # replicas really stop at different times
+    assert np.array_equal(a["sweeps"], b["sweeps"]) and np.array_equal(a["E"], b["E"]) and np.array_equal(a["state"], b["state"])
+    assert np.abs(a["sweeps"] - t["sweeps"]).max() <= 2 * 8                          # at most a temperature step apart
+    assert abs(np.mean(a["E"]) - np.mean(t["E"])) < 4 * np.std(a["E"]) / np.sqrt(40) + 1e-3 * abs(np.mean(a["E"]))
