@@ -39,12 +39,16 @@ def test_C1_heisenberg_honeycomb_full_run(scmc, oracle_mod):
     assert np.isclose(m["magnetizationVec"][0][0], 1.0, atol=1e-5)          # T^1 = identity expectation
 
 
-def test_C2_temperature_sweep_48x48(scmc):
+@pytest.mark.parametrize("mode", [0, 5, 6])
+def test_C2_temperature_sweep_48x48(scmc, mode):
     """C2: spin-valley couplings, n = 1, triangular 48x48, 64 temperatures in one launch.  Started from the exact ground state;
-    low-T equipartition e = -3.6 + (d - 1) T (CP^3 has 6 real modes per site), e(T) monotone, sigma adapts to ~50 % acceptance."""
+    low-T equipartition e = -3.6 + (d - 1) T (CP^3 has 6 real modes per site), e(T) monotone, sigma adapts to ~50 % acceptance.
+    mode 0: what auto picks here (the replica-resident kernel with the schedule on the device); 5 / 6: the TMA-pipelined streaming kernel without / with the
+    tensor-core mat-vec (the production kernel of the headline workload) under the host-driven schedule: same physics."""
     Ts = np.geomspace(0.02, 2.0, 64)
-    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 48, 1, n_replicas=64, precision=32, seed=5)
-    assert cfg.info()["n_colours"] == 3
+    cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 48, 1, n_replicas=64, precision=32, seed=5, stream=2 if mode else 1)
+    cfg.set_sweep_mode(mode)
+    assert cfg.info()["n_colours"] == 3 and cfg.info()["tma"] and cfg.info()["tma_tc"] == (mode in (0, 6))
     cfg.set_state(np.tile(ground_state_triangular(48)[None], (64, 1, 1)))
     assert np.allclose(cfg.energies() / cfg.nSites, -3.6, atol=1e-5)
     res = scmc.run_(cfg, None, Ts, Ts, 400, 600, measurement_rate=10, σ=0.3 * np.sqrt(Ts))
