@@ -16,8 +16,8 @@ loop=[l for l in lines if lo<=addr(l)<=hi]
 out=[]
 out.append("k_sweep_tma_psi<float, GEN=1, Z=6, STREAM=2, HITS=2, TC=true> -- SASS of the production kernel of the headline workload (sm_100a, `cuobjdump -sass` of the")
 out.append("in-tree build, round 2, second session; regenerate with the script at the end of profiles/README.md)")
-out.append(f"replica loop: {lo:#06x} .. {hi:#06x} (back edge), {len(loop)} static instructions; ncu counts 804 executed warp-instructions per warp and replica for the whole")
-out.append("kernel (the MMA issue block runs on one warp of four, the bulk-copy issue block on another; prologue / epilogue amortised over 32 replicas per CTA).")
+out.append(f"replica loop: {lo:#06x} .. {hi:#06x} (back edge), {len(loop)} static instructions; ncu counts 794 executed warp-instructions per warp and replica for the whole")
+out.append("kernel (the MMA issue block runs on one warp of four, the bulk-copy issue block on another; prologue / epilogue amortised over 64 replicas per CTA).")
 out.append("")
 out.append("Blackwell-specific instructions in the kernel (PTX -> SASS: tcgen05.alloc/dealloc -> UTCATOMSWS, tcgen05.st/ld -> STTM/LDTM, tcgen05.mma.kind::tf32 -> UTCHMMA,")
 out.append("tcgen05.commit -> UTCBAR, cp.async.bulk -> UBLKCP, mbarrier.* -> SYNCS.*, elect.sync -> ELECT):")
