@@ -59,6 +59,10 @@ int32_t scmc_set_stream(scmc_t* h, void* cuda_stream);
 /* info[0]=n_colours, [1]=generator table id (1,2,3), [2]=device bytes allocated, [3]=resident-kernel eligibility bits (1: T-gather family, 2: psi-gather family),
  * [4]=cluster size of the resident kernel, [5]=kernel launches issued so far, [6]=n_sites, [7]=n_replicas */
 int32_t scmc_info(scmc_t* h, int64_t* info8);
+/* Self-check of the DEVICE copies of the tables the sweep kernels read (no counterpart in the reference; stands in for a race checker): no bond inside
+ * a colour class, every bond has its reverse, per-class tables and the bulk-copy tile plan resolve to exactly the neighbour table.  *n_errors = number of
+ * violations (0 for every handle scmc_create returns). */
+int32_t scmc_verify_tables(scmc_t* h, int64_t* n_errors);
 
 /* cfg.state (Configuration.jl:17); layout [count][N][d], the d x N complex matrix of IO.jl:146-150 per replica */
 int32_t scmc_set_state(scmc_t* h, int64_t replica0, int64_t count, const double* re, const double* im);

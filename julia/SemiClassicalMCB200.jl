@@ -194,6 +194,12 @@ end
 setSweepMode!(cfg::Configuration, mode::Int, batch::Int = 0) = check(ccall((:scmc_set_sweep_mode, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), cfg.handle, mode, batch))
 setStreamVersion!(cfg::Configuration, v::Int) = check(ccall((:scmc_set_stream_version, LIB), Int32, (Ptr{Cvoid}, Int32), cfg.handle, v))
 setLanes!(cfg::Configuration, lanes::Int) = check(ccall((:scmc_set_lanes, LIB), Int32, (Ptr{Cvoid}, Int32), cfg.handle, lanes))
+"Number of violations found by the on-device self-check of colouring, neighbour tables and tile plan (0 = consistent)."
+function verifyTables(cfg::Configuration)
+    n = Ref{Int64}(0)
+    check(ccall((:scmc_verify_tables, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), cfg.handle, n))
+    return n[]
+end
 
 ## ------------------------------------------------------------------------------------------------ observables (src/Observables/*.jl)
 # measure! rows of all replicas, NOBS x R: E/N, (E/N)^2, |m_σ|, |m_τ|, |m_στ|, m[1:16]
@@ -634,5 +640,5 @@ export Configuration, MultiConfiguration, initializeCfg, getPosition, getBasis, 
        getOnsiteInteraction, getGeneratorsSq, getState, getStateMatrix, setStateMatrix!, getSpinExpectation, getSpinSqExpectation, getEnergy,
        getEnergies, initializeObservables, measure!, measureRows, getMagnetization, getCorrelations, getRs, getProject, structureFactor,
        structureFactorGrid, getSublatticeMagnetization, getChirality, saveMeans!, checkpoint!, readCheckpoint, readCheckpointSA, run!,
-       runAnnealing!, localUpdate!, localOptimization!, launch!, launchAnnealing!, setSweepMode!, setStreamVersion!, setLanes!
+       runAnnealing!, localUpdate!, localOptimization!, launch!, launchAnnealing!, setSweepMode!, setStreamVersion!, setLanes!, verifyTables
 end

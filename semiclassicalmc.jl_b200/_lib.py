@@ -49,6 +49,7 @@ SIGNATURES = {
     "scmc_destroy": (C.c_int32, [C.c_void_p]),
     "scmc_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "scmc_info": (C.c_int32, [C.c_void_p, c_lp]),
+    "scmc_verify_tables": (C.c_int32, [C.c_void_p, c_lp]),
     "scmc_set_state": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, c_dp, c_dp]),
     "scmc_get_state": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, c_dp, c_dp]),
     "scmc_randomize": (C.c_int32, [C.c_void_p, C.c_uint64]),

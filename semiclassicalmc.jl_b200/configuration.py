@@ -121,6 +121,12 @@ class Configuration:
         return dict(n_colours=int(a[0]), generator_table=int(a[1]), device_bytes=int(a[2]), resident=bool(a[3] & 1), resident_psi=bool(a[3] & 2), tma=bool(a[3] & 4), tma_tc=bool(a[3] & 8), cluster=int(a[4]),
                     launches=int(a[5]), n_sites=int(a[6]), n_replicas=int(a[7]))
 
+    def verify_tables(self):
+        """Number of violations found by the on-device self-check of the colouring, neighbour tables and bulk-copy tile plan (0 = consistent)."""
+        n = np.zeros(1, dtype=np.int64)
+        _lib.check(self._lib.scmc_verify_tables(self._h, _lib.lptr(n)))
+        return int(n[0])
+
     def set_sweep_mode(self, mode=0, batch=0):
         """0 auto | 1 streaming T-gather | 2 resident T-gather | 3 streaming psi-gather, direct gather | 4 resident psi-gather |
         5 streaming psi-gather, TMA-pipelined where the class decomposes into bulk copies (include/scmc.h)."""

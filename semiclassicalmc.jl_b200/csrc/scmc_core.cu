@@ -1221,6 +1221,69 @@ __global__ void k_single_update(const __grid_constant__ DevModel<R, NL> M, int64
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
+// ------------------------------------------------------------------------------------------------ self-check of the device tables
+// compute-sanitizer / racecheck are closed on the GPU pool this was developed on, so the library carries its own check of what the sweep kernels
+// rely on, run ON THE DEVICE COPIES the kernels read: (1) no bond joins two sites of one colour class (sites of a class are updated concurrently:
+// this is the race-freedom condition of a colour pass) and every bond has its reverse; (2) the per-class-position tables repeat the neighbour
+// table; (3) every thread slot of the bulk-copy tile plan (scmc_tma.cu) resolves, through the tile's runs, to the thread's own site and to exactly
+// its neighbours.  scmc_verify_tables returns the number of violations (0 for every handle scmc_create accepts; the host validates the same
+// properties before upload, this re-derives them from device memory).
+__global__ void k_verify_class_of(int n_col, const int32_t* col_off9, const int32_t* col_list, int32_t* cls_of) {
+    const int cp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cp >= col_off9[n_col]) return;
+    int c = 0;
+    while (c + 1 < n_col && cp >= col_off9[c + 1]) c++;
+    cls_of[col_list[cp]] = c;
+}
+__global__ void k_verify_tables(int N, int z, int n_col, const int32_t* col_off9, const int32_t* nbr, const int32_t* col_list, const int32_t* cls_nbr,
+                                const int32_t* cls_site, const int32_t* orig, const int32_t* cls_of, unsigned long long* err) {
+    const int cp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cp >= N) return;
+    unsigned bad = 0;
+    const int p = col_list[cp];
+    if (p < 0 || p >= N) { atomicAdd(err, 1ull); return; }
+    if (cls_site[cp] != orig[p]) bad++;
+    for (int k = 0; k < z; k++) {
+        const int j = nbr[(size_t)k * N + p];
+        if (cls_nbr[(size_t)k * N + cp] != j) bad++;
+        if (j < 0 || j > N) { bad++; continue; }
+        if (j == N) continue;                                   // no bond in this slot (zero site)
+        if (cls_of[j] == cls_of[p]) bad++;                      // a colour pass would update both ends of a bond at once
+        bool back = false;
+        for (int k2 = 0; k2 < z; k2++) back = back || nbr[(size_t)k2 * N + j] == p;
+        if (!back) bad++;
+    }
+    if (bad) atomicAdd(err, (unsigned long long)bad);
+}
+__global__ void k_verify_tma_plan(int N, int z, int cap, const uint4* meta, const uint2* runs, const int32_t* tile_info, const int32_t* nbr, const int32_t* orig,
+                                  const int32_t* col_list, unsigned long long* err) {
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const uint4 m0 = meta[((size_t)tile * TMA_TILE + tid) * 2], m1 = meta[((size_t)tile * TMA_TILE + tid) * 2 + 1];
+    const int cnt = tile_info[tile * 4 + 0], nruns = tile_info[tile * 4 + 1], slots = tile_info[tile * 4 + 2], cp0 = tile_info[tile * 4 + 3];
+    const bool valid = (m0.w >> 16) != 0;
+    unsigned bad = 0;
+    if (valid != (tid < cnt)) bad++;
+    if (nruns < 1 || nruns > TMA_MAX_RUNS || slots + 1 > cap) bad++;
+    if (valid) {
+        const uint32_t w[4] = {m0.x, m0.y, m0.z, m0.w};
+        const int p = (int)m1.y;
+        if (p != col_list[cp0 + tid] || (int)m1.x != orig[p]) bad++;
+        for (int k = 0; k < 7; k++) {
+            const uint32_t l = (w[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            const int want = k == 0 ? p : (k - 1 < z ? nbr[(size_t)(k - 1) * N + p] : N);
+            if (want == N) { if (l != 0xFFFFu) bad++; continue; }       // no bond: the all-zero slot
+            int src = -1;
+            for (int q = 0; q < nruns; q++) {
+                const uint2 rd = runs[(size_t)tile * TMA_MAX_RUNS + q];
+                const uint32_t s0 = rd.y & 0xFFFFu, len = rd.y >> 16;
+                if (l >= s0 && l < s0 + len) src = (int)rd.x + (int)(l - s0);
+            }
+            if (src != want) bad++;
+        }
+    }
+    if (bad) atomicAdd(err, (unsigned long long)bad);
+}
+
 template <class R, int NL>
 static DevModel<R, NL> make_model(const scmc_handle* h) {
     DevModel<R, NL> M;
@@ -1855,6 +1918,47 @@ int32_t scmc_destroy(scmc_t* h) {
 int32_t scmc_set_stream(scmc_t* h, void* s) {
     SCMC_ARG(h, "null handle");
     h->stream = (cudaStream_t)s;
+    return SCMC_OK;
+}
+
+int32_t scmc_verify_tables(scmc_t* h, int64_t* n_errors) {
+    SCMC_ARG(h && n_errors, "null argument");
+    SCMC_CK(cudaSetDevice(h->device));
+    void *d_cls = nullptr, *d_err = nullptr, *d_off = nullptr;
+    SCMC_CK(scratch_get(h, 0, (size_t)(h->N + 1) * sizeof(int32_t), &d_cls));
+    SCMC_CK(scratch_get(h, 1, sizeof(unsigned long long), &d_err));
+    SCMC_CK(scratch_get(h, 2, sizeof(h->col_off), &d_off));
+    SCMC_CK(cudaMemsetAsync(d_err, 0, sizeof(unsigned long long), h->stream));
+    SCMC_CK(cudaMemcpyAsync(d_off, h->col_off, sizeof(h->col_off), cudaMemcpyHostToDevice, h->stream));
+    const int N = (int)h->N;
+    // self-test of the checker (tests only): SCMC_VERIFY_PLANT=1 points slot 0 of permuted site 0 at that site itself for the duration of the check
+    // (a bond inside a colour class without a reverse bond, which also breaks the class-position table and the tile plan), then restores the entry
+    const bool plant = getenv("SCMC_VERIFY_PLANT") && atoi(getenv("SCMC_VERIFY_PLANT")) != 0;
+    int32_t saved = 0;
+    if (plant) {
+        SCMC_CK(cudaStreamSynchronize(h->stream));
+        SCMC_CK(cudaMemcpy(&saved, h->nbr, sizeof saved, cudaMemcpyDeviceToHost));
+        const int32_t self = 0;
+        SCMC_CK(cudaMemcpy(h->nbr, &self, sizeof self, cudaMemcpyHostToDevice));
+    }
+    k_verify_class_of<<<grid_for(N), 256, 0, h->stream>>>(h->n_col, (const int32_t*)d_off, h->d_col_list, (int32_t*)d_cls);
+    k_verify_tables<<<grid_for(N), 256, 0, h->stream>>>(N, h->z, h->n_col, (const int32_t*)d_off, h->nbr, h->d_col_list, h->d_cls_nbr, h->d_cls_site, h->d_orig,
+                                                        (const int32_t*)d_cls, (unsigned long long*)d_err);
+    if (h->tma.ready) {
+        int n_tiles = 0;
+        for (int c = 0; c < h->n_col; c++)
+            if (h->tma.cls[c].ok) n_tiles = std::max(n_tiles, h->tma.cls[c].first + h->tma.cls[c].n_tiles);
+        if (n_tiles > 0)
+            k_verify_tma_plan<<<n_tiles, TMA_TILE, 0, h->stream>>>(N, h->z, h->tma.cap, (const uint4*)h->tma.d_meta, (const uint2*)h->tma.d_runs, h->tma.d_tile, h->nbr,
+                                                                   h->d_orig, h->d_col_list, (unsigned long long*)d_err);
+    }
+    h->launches += 3;
+    SCMC_CK(cudaGetLastError());
+    unsigned long long e = 0;
+    SCMC_CK(cudaMemcpyAsync(&e, d_err, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+    SCMC_CK(cudaStreamSynchronize(h->stream));
+    if (plant) SCMC_CK(cudaMemcpy(h->nbr, &saved, sizeof saved, cudaMemcpyHostToDevice));
+    *n_errors = (int64_t)e;
     return SCMC_OK;
 }
 

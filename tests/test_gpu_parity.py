@@ -1000,3 +1000,27 @@ def test_annealing_on_a_tiled_lattice_with_stopped_replicas(scmc):
     assert np.array_equal(a["sweeps"], b["sweeps"]) and np.array_equal(a["E"], b["E"]) and np.array_equal(a["state"], b["state"])
     assert np.abs(a["sweeps"] - t["sweeps"]).max() <= 2 * 8                          # at most a temperature step apart
     assert abs(np.mean(a["E"]) - np.mean(t["E"])) < 4 * np.std(a["E"]) / np.sqrt(40) + 1e-3 * abs(np.mean(a["E"]))
+
+
+@pytest.mark.parametrize("case", [
+    ("nearest-neighbor", "triangular", [NOTEBOOK_J], 128, 1),      # C5 lattice: seam classes + bulk-copy tile plan
+    ("nearest-neighbor", "triangular", [NOTEBOOK_J], 48, 1),
+    ("nearest-neighbor", "honeycomb", [NOTEBOOK_J], 24, 1),        # z = 3
+    ("nearest-neighbor", "square", [NOTEBOOK_J], 32, 1),           # z = 4 padded to 6
+    ("nearest-neighbor", "cubic", [NOTEBOOK_J], 5, 1),             # odd size, greedy colouring
+    ("tg-hbn", "triangular", [1.0, 0.3, 0.2, 0.15, 0.8], 12, 2),   # 3 labels, 12 neighbours
+])
+def test_device_tables_self_check(scmc, monkeypatch, case):
+    """scmc_verify_tables re-derives, from the DEVICE copies the kernels read, that no bond lies inside a colour class (the race-freedom condition of a
+    colour pass), that bonds are symmetric, and that the class-position tables and the bulk-copy tile plan resolve to exactly the neighbour table.
+    It finds nothing on the handles scmc_create returns and does find a planted inconsistency (self-test of the checker)."""
+    model, lattice, J, L, n = case
+    cfg = scmc.initializeCfg(model, lattice, J, L, n, n_replicas=2, precision=32, seed=1)
+    assert cfg.verify_tables() == 0
+    monkeypatch.setenv("SCMC_VERIFY_PLANT", "1")
+    assert cfg.verify_tables() >= 2
+    monkeypatch.delenv("SCMC_VERIFY_PLANT")
+    assert cfg.verify_tables() == 0                                  # the planted entry was restored
+    acc, att = cfg.sweep(1, np.array([1.0, 2.0]), np.array([0.3, 0.3]))
+    assert np.all(acc > 0)
+    cfg.close()
