@@ -41,7 +41,7 @@ def _lib(fast=False):
         lib.orc_energy.restype = C.c_double
         lib.orc_energy_difference.restype = C.c_double
         lib.orc_local_optimization.restype = C.c_double
-        for name in ("orc_sweeps_random", "orc_updates_injected", "orc_run_metropolis", "orc_run_annealing", "orc_sweeps_colour_v1", "orc_sweeps_colour"):
+        for name in ("orc_sweeps_random", "orc_updates_injected", "orc_run_metropolis", "orc_run_annealing", "orc_run_annealing_traced", "orc_sweeps_colour_v1", "orc_sweeps_colour"):
             getattr(lib, name).restype = C.c_long
         lib.orc_local_update.restype = C.c_int
         _libs[fast] = lib
@@ -219,6 +219,18 @@ class Oracle:
                                        C.c_long(min_acc_per_site), C.c_double(min_accrate), C.c_double(sigma_min), C.byref(s),
                                        C.byref(E), C.byref(b), _d(trace) if trace_cap else None, C.c_long(trace_cap))
         return dict(sweeps=n, E=E.value, beta=b.value, sigma=s.value, trace=trace[:min(n, trace_cap)])
+
+    def run_annealing_traced(self, T_i, trace_cap, T_fac=0.98, N_max=10_000_000, N_o=0, N_per_T=10000, min_acc_per_site=100, min_accrate=1e-5,
+                             sigma_min=0.05, sigma=60.0):
+        """runAnnealing! with the per-sweep series the reference keeps or prints: E/N and beta (MonteCarlo.jl:158-159) and the running
+        acceptance rate of the current temperature step (R of the checkpoint line, MonteCarlo.jl:161-167).  Entry k = sweep k + 1."""
+        s = C.c_double(sigma); E = C.c_double(); b = C.c_double()
+        tr, bt, rt = np.zeros(trace_cap), np.zeros(trace_cap), np.zeros(trace_cap)
+        n = self.lib.orc_run_annealing_traced(self.h, C.c_double(T_i), C.c_double(T_fac), C.c_long(N_max), C.c_long(N_o), C.c_long(N_per_T),
+                                              C.c_long(min_acc_per_site), C.c_double(min_accrate), C.c_double(sigma_min), C.byref(s),
+                                              C.byref(E), C.byref(b), _d(tr), _d(bt), _d(rt), C.c_long(trace_cap))
+        k = min(n - 1, trace_cap)
+        return dict(sweeps=n, E=E.value, beta=b.value, sigma=s.value, trace=tr[:k], beta_trace=bt[:k - N_o], rate_trace=rt[:k - N_o])
 
     def local_optimization(self, i):
         return self.lib.orc_local_optimization(self.h, C.c_int(i))

@@ -387,16 +387,19 @@ double orc_local_optimization(orc_t *o, int i) {
 
 /* ------------------------------------------------------------------ runAnnealing! (src/MonteCarlo.jl:112-238), no file I/O */
 /* Returns the number of annealing sweeps done; *E_out final energy; trace (optional) gets E/N per sweep (capacity trace_cap). */
-long orc_run_annealing(orc_t *o, double T_i, double T_fac, long N_max, long N_o, long N_per_T, long min_acc_per_site,
-                       double min_accrate, double sigma_min, double *sigma_io, double *E_out, double *beta_out,
-                       double *trace, long trace_cap) {
+static long run_annealing_traced(orc_t *o, double T_i, double T_fac, long N_max, long N_o, long N_per_T, long min_acc_per_site,
+                                 double min_accrate, double sigma_min, double *sigma_io, double *E_out, double *beta_out,
+                                 double *trace, double *beta_trace, double *rate_trace, long trace_cap) {
     double E = orc_energy(o), beta = 1.0 / T_i, beta_fac = 1.0 / T_fac, sigma = *sigma_io;
     long min_accepted = min_acc_per_site * o->N, sweep = 1, nt = 0;
     while (sweep < N_max) {
         long att = 0, acc = 0, sweep_at_T = 0;
         while (acc < min_accepted && sweep_at_T < N_per_T && sweep < N_max) {
             acc += orc_sweeps_random(o, 1, beta, sigma, &E); att += 2L * o->N;
-            if (trace && nt < trace_cap) trace[nt] = E / o->N; nt++;
+            if (trace && nt < trace_cap) trace[nt] = E / o->N;
+            if (beta_trace && nt < trace_cap) beta_trace[nt] = beta;                       /* push!(βs, β), MonteCarlo.jl:159 */
+            if (rate_trace && nt < trace_cap) rate_trace[nt] = (double)acc / (double)att;   /* R_cp of the checkpoint line, MonteCarlo.jl:162 */
+            nt++;
             sweep_at_T++; sweep++;
         }
         double R = (double)acc / (double)att;
@@ -415,6 +418,20 @@ long orc_run_annealing(orc_t *o, double T_i, double T_fac, long N_max, long N_o,
     }
     *sigma_io = sigma; if (E_out) *E_out = E; if (beta_out) *beta_out = beta;
     return sweep;
+}
+long orc_run_annealing(orc_t *o, double T_i, double T_fac, long N_max, long N_o, long N_per_T, long min_acc_per_site,
+                       double min_accrate, double sigma_min, double *sigma_io, double *E_out, double *beta_out,
+                       double *trace, long trace_cap) {
+    return run_annealing_traced(o, T_i, T_fac, N_max, N_o, N_per_T, min_acc_per_site, min_accrate, sigma_min, sigma_io, E_out, beta_out,
+                                trace, NULL, NULL, trace_cap);
+}
+/* the same run with the beta series (MonteCarlo.jl:159) and the running acceptance rate of the current temperature step (the R of the
+ * reference's checkpoint line, MonteCarlo.jl:161-167) per annealing sweep: what the notebook's cell 25 prints at sweeps 5000 / 10000 / 15000 */
+long orc_run_annealing_traced(orc_t *o, double T_i, double T_fac, long N_max, long N_o, long N_per_T, long min_acc_per_site,
+                              double min_accrate, double sigma_min, double *sigma_io, double *E_out, double *beta_out,
+                              double *trace, double *beta_trace, double *rate_trace, long trace_cap) {
+    return run_annealing_traced(o, T_i, T_fac, N_max, N_o, N_per_T, min_acc_per_site, min_accrate, sigma_min, sigma_io, E_out, beta_out,
+                                trace, beta_trace, rate_trace, trace_cap);
 }
 
 /* ------------------------------------------------------------------ the framework's counter-based stream, restated */

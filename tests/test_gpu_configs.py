@@ -287,6 +287,47 @@ def test_sigma_convention_reference_units(scmc, golden):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", [64, 32])
+def test_device_annealing_reproduces_the_notebook_trace(scmc, golden, precision):
+    """The reference's recorded annealing run (examples.ipynb cell 25, triangular L = 12: checkpoint lines at sweeps 5000 / 10000 / 15000, stop at
+    sweep 15010, ten optimisation sweeps) against the DEVICE's cooling controller, 48 restarts, sigma in the reference's units: the number of
+    temperature steps taken up to each checkpoint (T = T_i T_fac^k: 303 / 354 / 404 in the notebook), E/N there, the stop sweep and the energy after
+    the optimisation sweeps.  k(5000) depends on every early temperature step ending after min_acc_per_site * N acceptances (MonteCarlo.jl:152), i.e.
+    on the acceptance rate at sigma = sigma_min all the way down; the same run with sigma_min read in this framework's own units is ~29 steps behind.
+    CPU counterpart with the oracle: tests/test_oracle_physics.py::test_reference_annealing_trace_pins_the_cooling_rule."""
+    a, cps = golden["annealing"]["params"], golden["annealing"]["checkpoints"]
+    steps = lambda T: np.log(T / a["T_i"]) / np.log(a["T_fac"])
+    R, rate = 48, 100
+
+    def run(convention, seed):
+        cfg = scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], int(a["L"]), 1, n_replicas=R, precision=precision, seed=seed)
+        res = scmc.runAnnealing_(cfg, a["T_i"], T_fac=a["T_fac"], N_max=40000, N_o=int(a["N_o"]), N_per_T=int(a["N_per_T"]),
+                                 min_acc_per_site=int(a["min_acc_per_site"]), min_accrate=a["min_accrate"], σ_min=a["σ_min"], σ_convention=convention,
+                                 log_rate=rate)
+        cfg.close()
+        return res
+    res = run("reference", 31)
+    es, bs, sweeps = res["energy_series"], res["beta_series"], res["sweeps"]
+    assert np.all(sweeps < 39999) and abs(np.median(sweeps) - golden["annealing"]["stop_sweep"]) < 700, np.median(sweeps)
+    assert np.allclose(res["sigma"], a["σ_min"], rtol=1e-6)                                        # sigma sits on sigma_min, as every checkpoint line prints
+    for c in cps:
+        j = c["sweep"] // rate - 1                                                                  # log point after c["sweep"] sweeps
+        run_on = sweeps > c["sweep"]
+        if run_on.sum() < R // 2:
+            continue
+        k = steps(1 / bs[j, run_on])
+        assert abs(np.median(k) - steps(c["T"])) <= 1.01 and np.all(np.abs(k - steps(c["T"])) <= 3.01), (c["sweep"], np.median(k), k.min(), k.max())
+        assert abs(es[j, run_on].mean() - c["E"]) < 2e-3 and np.all(np.abs(es[j, run_on] - c["E"]) < 6e-3), (c["sweep"], es[j, run_on].mean(), c["E"])
+    e_opt = res["E"] / 144.0
+    exact, nb_opt = golden["annealing"]["exact_E_per_site"], golden["annealing"]["optimization_E"][-1]
+    assert np.all(e_opt > exact - (1e-9 if res["polished_fp64"] or precision == 64 else 1e-5)) and np.all(e_opt < exact + 40 * (nb_opt - exact)), (e_opt.min(), e_opt.max())
+    other = run("unit", 31)                                                                         # sigma_min = 0.05 in unit-variance normals: another history
+    j = cps[0]["sweep"] // rate - 1
+    assert np.median(steps(1 / other["beta_series"][j])) < steps(cps[0]["T"]) - 15
+    assert other["energy_series"][j].mean() > cps[0]["E"] + 8e-3
+
+
+@pytest.mark.gpu
 def test_C4_fp32_annealing_with_fp64_polish_reaches_1e8(scmc, golden):
     """C4 in the precision it ships in: 512 restarts (one GPU's share of the 4096) annealed in FP32 with the notebook's schedule, optimisation
     sweeps and energies finished in FP64 (polishFP64_): min E/N within 1e-8 of the exact -3.6 and never below it (an FP32 energy sum alone

@@ -220,3 +220,43 @@ def test_reference_sigma_trace_is_a_variance_half_convention(golden):
         assert abs(found[2 ** -0.5][s] - mid) < half + 0.06 * mid, (s, found[2 ** -0.5][s], vals)        # variance 1/2: inside the notebook's spread
         assert found[1.0][s] < lo * 0.82, (s, found[1.0][s], vals)                                          # unit variance: sqrt(2) too small
         assert abs(found[2 ** -0.5][s] / found[1.0][s] - 2 ** 0.5) < 0.12
+
+
+@pytest.mark.timeout(600)
+def test_reference_annealing_trace_pins_the_cooling_rule(golden):
+    """Second reference-held trace (examples.ipynb cell 25, L = 12): the checkpoint lines of runAnnealing! print T, E/N and the running acceptance rate R
+    at sweeps 5000 / 10000 / 15000, then the stop sweep and ten optimisation energies.  T = T_i * T_fac^k counts the temperature steps taken so far, and
+    early on a step ends as soon as min_acc_per_site * N updates were accepted (MonteCarlo.jl:152, 176-182), so k(5000) depends on the acceptance rate of
+    every step before it -- i.e. on the proposal width the fixed sigma = sigma_min = 0.05 stands for.  The oracle with proposal normals of variance 1/2 lands
+    on the notebook's k at every checkpoint (303 / 354 / 404, within a step) with its E and R; with N(0,1) normals it is 29 steps behind at sweep 5000.
+    This confirms the sigma convention found from the thermalisation trace on an independent run and pins the cooling controller quantitatively."""
+    a, cps = golden["annealing"]["params"], golden["annealing"]["checkpoints"]
+    assert [c["sweep"] for c in cps] == [5000, 10000, 15000] and all(c["sigma"] == a["σ_min"] for c in cps)
+    steps = lambda T: np.log(T / a["T_i"]) / np.log(a["T_fac"])
+    k_nb = [steps(c["T"]) for c in cps]
+    assert np.allclose(k_nb, [303, 354, 404], atol=0.02)                       # the printed temperatures lie on the geometric grid
+    pos, nbr, lab, bl = ol.triangular(int(a["L"]))
+
+    def run(scale, seed):
+        o = orc.Oracle(nbr, lab, NOTEBOOK_J, np.zeros(16), 1)
+        o.seed(seed); o.set_normal_scale(scale); o.randomize()
+        return o.run_annealing_traced(a["T_i"], 40000, T_fac=a["T_fac"], N_max=int(a["N_max"]), N_o=int(a["N_o"]), N_per_T=int(a["N_per_T"]),
+                                      min_acc_per_site=int(a["min_acc_per_site"]), min_accrate=a["min_accrate"], sigma_min=a["σ_min"])
+    for seed in (2, 5):
+        res = run(2 ** -0.5, seed)
+        bt, rt, tr = res["beta_trace"], res["rate_trace"], res["trace"]
+        n_sa = len(bt)
+        assert abs(n_sa - golden["annealing"]["stop_sweep"]) < 900, n_sa          # stops by the acceptance-rate rule within a few steps of sweep 15010
+        for c, k in zip(cps, k_nb):
+            s = c["sweep"]
+            if s > n_sa:
+                continue
+            assert abs(steps(1 / bt[s - 1]) - k) <= 2.01, (s, steps(1 / bt[s - 1]), k)
+            assert abs(tr[s - 1] - c["E"]) < 5e-3, (s, tr[s - 1], c["E"])      # 12 seeds: -3.5783 ... -3.5822 at sweep 5000 (notebook -3.579; unit variance -3.562 ... -3.565)
+            if s < 15000:                                                           # R of the running step: average a few steps around the checkpoint
+                assert abs(rt[s - 300:s + 300].mean() / c["R"] - 1) < 0.25, (s, rt[s - 300:s + 300].mean(), c["R"])
+        opt = tr[n_sa:]
+        assert len(opt) == int(a["N_o"]) and np.all(np.diff(opt) < 0) and opt[-1] > golden["annealing"]["exact_E_per_site"]
+        assert abs(opt[0] - golden["annealing"]["optimization_E"][0]) < 5e-4 and abs(opt[-1] - golden["annealing"]["optimization_E"][-1]) < 2e-5
+    res = run(1.0, 2)                                                               # unit-variance normals: a different cooling history
+    assert steps(1 / res["beta_trace"][4999]) < k_nb[0] - 15 and res["trace"][4999] > cps[0]["E"] + 8e-3
