@@ -380,11 +380,10 @@ __device__ __forceinline__ bool metropolis_hit(R* re, R* im, R* T, R* Tsq, const
 
 // psi-gather family, no on-site term: the local energy is linear in the density matrix, e(psi) = sum_n Hq[n] P_n(psi) with
 // Hq = C^T h built once per visit, so a hit needs neither T' nor a 16-term dot product (48 instead of 84 instructions).
-template <class R, int GEN>
-__device__ __forceinline__ bool metropolis_hit_psi(R* re, R* im, const R* Hq, const R* xr, const R* xi, R u, R nbeta, R sigma, R& eloc, R& dE_out) {
-    constexpr int D = GenOps<GEN>::D;
-    R nre[D], nim[D];
-    R na = R(0), nb = R(0);                  // two partial sums for the norm
+// proposal psi' = normalize(psi + sigma xi) (getRandomState!, MonteCarlo.jl:249-260): two partial sums for the norm (re and im parts)
+template <int D>
+__device__ __forceinline__ void propose_state(const double* re, const double* im, const double* xr, const double* xi, double sigma, double* nre, double* nim) {
+    double na = 0.0, nb = 0.0;
 #pragma unroll
     for (int k = 0; k < D; k++) {
         nre[k] = fma(sigma, xr[k], re[k]);
@@ -392,9 +391,54 @@ __device__ __forceinline__ bool metropolis_hit_psi(R* re, R* im, const R* Hq, co
         na = fma(nre[k], nre[k], na);
         nb = fma(nim[k], nim[k], nb);
     }
-    const R inv = inv_sqrt(na + nb);
+    const double inv = inv_sqrt(na + nb);
 #pragma unroll
     for (int k = 0; k < D; k++) { nre[k] *= inv; nim[k] *= inv; }
+}
+// FP32: the same operations in the same order on (re, im) pairs as packed fma / mul .f32x2 (SASS FFMA2 / FMUL2: one issue slot per complex
+// component instead of two; each half is the IEEE operation of the scalar form, so the result is bit for bit the scalar one)
+template <int D>
+__device__ __forceinline__ void propose_state(const float* re, const float* im, const float* xr, const float* xi, float sigma, float* nre, float* nim) {
+#ifdef SCMC_SCALAR_PROPOSAL
+    float na = 0.f, nb = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        nre[k] = fmaf(sigma, xr[k], re[k]);
+        nim[k] = fmaf(sigma, xi[k], im[k]);
+        na = fmaf(nre[k], nre[k], na);
+        nb = fmaf(nim[k], nim[k], nb);
+    }
+    const float inv = inv_sqrt(na + nb);
+#pragma unroll
+    for (int k = 0; k < D; k++) { nre[k] *= inv; nim[k] *= inv; }
+#else
+    unsigned long long n[D], acc = 0ull, ss, ii;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(sigma));
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        unsigned long long c, x;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(re[k]), "f"(im[k]));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(xr[k]), "f"(xi[k]));
+        asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(n[k]) : "l"(ss), "l"(x), "l"(c));
+        asm("fma.rn.ftz.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(n[k]));
+    }
+    float na, nb;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(na), "=f"(nb) : "l"(acc));
+    const float inv = inv_sqrt(na + nb);
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ii) : "f"(inv));
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        asm("mul.rn.ftz.f32x2 %0, %0, %1;" : "+l"(n[k]) : "l"(ii));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(nre[k]), "=f"(nim[k]) : "l"(n[k]));
+    }
+#endif
+}
+
+template <class R, int GEN>
+__device__ __forceinline__ bool metropolis_hit_psi(R* re, R* im, const R* Hq, const R* xr, const R* xi, R u, R nbeta, R sigma, R& eloc, R& dE_out) {
+    constexpr int D = GenOps<GEN>::D;
+    R nre[D], nim[D];
+    propose_state<D>(re, im, xr, xi, sigma, nre, nim);
     const R enew = GenOps<GEN>::energy_from_state(nre, nim, Hq);
     const R dE = enew - eloc;
     dE_out = dE;

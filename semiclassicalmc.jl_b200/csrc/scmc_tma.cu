@@ -270,14 +270,17 @@ struct TmaArgs {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-template <class R, int GEN, int Z, int STREAM, int HITS, bool TC>
+// CAPC > 0: the stage has CAPC slots per plane at compile time (the tile plan's cap must not exceed it), so plane and stage strides are immediates of the
+// shared-memory loads instead of two integer instructions per load; CAPC = 0: strides from T.cap at run time.
+template <class R, int GEN, int Z, int STREAM, int HITS, bool TC, int CAPC = 0>
 __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCKS) k_sweep_tma_psi(const __grid_constant__ DevModel<R, 1> M, const SweepArgs A, const TmaArgs T) {
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
     static_assert(NP == NG, "fused density basis (16 entries) only");
     using V = vec4<R>;
     constexpr uint32_t VB = sizeof(V);
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t plane_bytes = (uint32_t)T.cap * VB, stage_bytes = NPV * plane_bytes;
+    const uint32_t cap = CAPC ? (uint32_t)CAPC : (uint32_t)T.cap;
+    const uint32_t plane_bytes = cap * VB, stage_bytes = NPV * plane_bytes;
     R* sJt = reinterpret_cast<R*>(smem + TMA_STAGES * stage_bytes);                      // TC: Jq_hi, Jq_lo in core-matrix order (2 x 1 KB)
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(sJt + (TC ? 2 : 1) * NG * NG);      // full[0..S), empty[0..S), TC: one per warp
     int32_t* sRep = reinterpret_cast<int32_t*>(bars + 2 * TMA_STAGES + TMA_TILE / 32);    // replicas of this CTA that are alive
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
 
     // per-thread constants of the tile: stage slots (as byte offsets) of the own site and the neighbours, site number, permuted index
     const uint4 m0 = T.meta[((size_t)tile * TMA_TILE + tid) * 2], m1 = T.meta[((size_t)tile * TMA_TILE + tid) * 2 + 1];
-    const uint32_t zero_off = (uint32_t)(T.cap - 1) * VB;
+    const uint32_t zero_off = (cap - 1) * VB;
     uint32_t off[7];
     {
         const uint32_t w[4] = {m0.x, m0.y, m0.z, m0.w};
@@ -380,12 +383,13 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
         c_bytes = (rd.y >> 16) * VB;
     }
     const uint32_t smem0 = smem_u32(smem), bar0 = smem_u32(bars);
+    const uint32_t rep_bytes = (uint32_t)M.Ns * VB;
     auto issue = [&](int it, int s) {
         if (lane == 0) mbar_expect_tx(bar0 + 8 * s, tile_bytes);
         __syncwarp();
         if (c_bytes) {
-            bulk_g2s(smem0 + s * stage_bytes + c_dst, c_src + (size_t)sRep[it] * M.Ns * VB, c_bytes, bar0 + 8 * s);
-            if (SCMC_TMA_PREFETCH && it + SCMC_TMA_PREFETCH < n_it) bulk_prefetch_l2(c_src + (size_t)sRep[it + SCMC_TMA_PREFETCH] * M.Ns * VB, c_bytes);
+            bulk_g2s(smem0 + s * stage_bytes + c_dst, c_src + (uint32_t)sRep[it] * rep_bytes, c_bytes, bar0 + 8 * s);
+            if (SCMC_TMA_PREFETCH && it + SCMC_TMA_PREFETCH < n_it) bulk_prefetch_l2(c_src + (uint32_t)sRep[it + SCMC_TMA_PREFETCH] * rep_bytes, c_bytes);
         }
     };
     if (warp == 0) {
@@ -398,7 +402,6 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
     // it % 32; one atomic instruction per warp and 32 replicas instead of a reduce -> branch -> atomic chain per visit
     unsigned tot_mine = 0;
     char* const own = reinterpret_cast<char*>(M.psi + rb * M.Ns + p);      // own state of the chunk's first replica (plane 0)
-    const uint32_t rep_bytes = (uint32_t)M.Ns * VB;
     constexpr bool PRE = TC && HITS == 2 && STREAM == 2 && SCMC_TC_PRE;    // both hits' random numbers are generated while the tensor core works
     constexpr bool PIPE = TC && SCMC_TC_PIPE;                              // the MMAs of visit it + 1 are in flight during the hits of visit it
 
@@ -411,12 +414,30 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
 #endif
         mbar_wait(bar0 + 8 * s, parity);
         const unsigned char* st = smem + s * stage_bytes;
+        if constexpr (TC && SCMC_TC_PACKED && CAPC > 0) {
+            // compile-time strides: one add per slot (32-bit shared address of the slot in stage 0 + stage offset), the plane offset is an immediate of the load
+            const uint32_t so = smem0 + (uint32_t)s * (uint32_t)(NPV * CAPC * VB);
+            auto lds2 = [&](uint32_t a, float4& q0, float4& q1) {
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(a));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(a), "n"(CAPC * VB));
+            };
+            float4 q0, q1;
+            lds2(so + off[0], q0, q1);
+            re[0] = q0.x; im[0] = q0.y; re[1] = q0.z; im[1] = q0.w; re[2] = q1.x; im[2] = q1.y; re[3] = q1.z; im[3] = q1.w;
+            PackedDensity pd;
+            pd.clear();
 #pragma unroll
-        for (int v = 0; v < NPV; v++) {
-            const V q = *reinterpret_cast<const V*>(st + v * plane_bytes + off[0]);
-            re[2 * v] = q.x; im[2 * v] = q.y; re[2 * v + 1] = q.z; im[2 * v + 1] = q.w;
-        }
-        if constexpr (TC && SCMC_TC_PACKED) {
+            for (int k = 0; k < Z; k++) {
+                lds2(so + off[1 + k], q0, q1);
+                pd.add(q0, q1);
+            }
+            pd.finish(P);
+        } else if constexpr (TC && SCMC_TC_PACKED) {
+#pragma unroll
+            for (int v = 0; v < NPV; v++) {
+                const V q = *reinterpret_cast<const V*>(st + v * plane_bytes + off[0]);
+                re[2 * v] = q.x; im[2 * v] = q.y; re[2 * v + 1] = q.z; im[2 * v + 1] = q.w;
+            }
             PackedDensity pd;
             pd.clear();
 #pragma unroll
@@ -424,6 +445,11 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
                 pd.add(*reinterpret_cast<const float4*>(st + off[1 + k]), *reinterpret_cast<const float4*>(st + plane_bytes + off[1 + k]));
             pd.finish(P);
         } else {
+#pragma unroll
+            for (int v = 0; v < NPV; v++) {
+                const V q = *reinterpret_cast<const V*>(st + v * plane_bytes + off[0]);
+                re[2 * v] = q.x; im[2 * v] = q.y; re[2 * v + 1] = q.z; im[2 * v + 1] = q.w;
+            }
 #pragma unroll
             for (int t = 0; t < NP; t++) P[t] = R(0);
 #pragma unroll
@@ -485,6 +511,7 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
         const R sigma = sSigma[it], nbeta = neg_beta_scaled(sBeta[it]);
         R Hq[NG];
         unsigned mine = 0;
+        bool acc_hit[2] = {false, false};
         uint32_t uw[4];                                            // stream v2: acceptance-uniform words of the current group of four visits
         const int n_hits = HITS ? HITS : A.hits;                   // HITS = 2: the two hits of the reference's 2N-update sweep, unrolled
         R pxr[PRE ? 2 : 1][D], pxi[PRE ? 2 : 1][D];
@@ -531,7 +558,8 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
             if constexpr (PRE) {
 #pragma unroll
                 for (int k = 0; k < D; k++) { xr[k] = pxr[hit][k]; xi[k] = pxi[hit][k]; }
-                u = unit_uniform(pick_word(uw, ((uint32_t)A.visit0 + hit) & 3u), R(0));
+                // visit0 = 2 x sweep is even: hit 0 takes word 0 or 2, hit 1 word 1 or 3 (one select on a uniform predicate instead of pick_word's branches)
+                u = unit_uniform(((uint32_t)A.visit0 & 2u) ? uw[2 + hit] : uw[hit], R(0));
             } else if constexpr (STREAM == 2) {
                 const uint64_t visit = A.visit0 + hit;
                 stream_v2_normals<R, D>(A.seed, site, (uint32_t)(A.roff + r), visit, xr, xi);
@@ -541,13 +569,15 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
             } else {
                 stream_v1<R, D>(A.seed, site, (uint32_t)(A.roff + r), A.visit0 + hit, xr, xi, u);
             }
-            mine += metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) ? 1u : 0u;
+            const bool ok = metropolis_hit_psi<R, GEN>(re, im, Hq, xr, xi, u, nbeta, sigma, eloc, dE) && valid;
+            if (HITS == 2) acc_hit[hit & 1] = ok;
+            mine += ok ? 1u : 0u;
         }
-        if (!valid) mine = 0;
-        if (mine) store_psi<R, D>(reinterpret_cast<V*>(own + (size_t)rl * rep_bytes), ps, re, im);
+        // rl < TMA_RC and Ns * 16 B * TMA_RC < 4 GB (checked by tma_pass_available): the replica offset inside the chunk is a 32-bit product
+        if (HITS == 2 ? (acc_hit[0] || acc_hit[1]) : mine != 0) store_psi<R, D>(reinterpret_cast<V*>(own + (uint32_t)rl * rep_bytes), ps, re, im);
         if constexpr (HITS == 2) {
-            const unsigned b0 = __ballot_sync(0xffffffffu, mine & 1u), b1 = __ballot_sync(0xffffffffu, mine & 2u);
-            if (lane == (it & 31)) tot_mine = __popc(b0) + 2 * __popc(b1);
+            const unsigned b0 = __ballot_sync(0xffffffffu, acc_hit[0]), b1 = __ballot_sync(0xffffffffu, acc_hit[1]);
+            if (lane == (it & 31)) tot_mine = __popc(b0) + __popc(b1);
             if ((it & 31) == 31 || it == n_it - 1) {
                 const int j = (it & ~31) + lane;
                 if (j <= it && tot_mine) atomicAdd(A.acc + rb + sRep[j], (unsigned long long)tot_mine);
@@ -615,9 +645,12 @@ static DevModel<R, 1> make_model_t(const scmc_handle* h) {
     return M;
 }
 
-static size_t tma_smem_bytes(const scmc_handle* h, bool tc = true) {
+#ifndef SCMC_TMA_CAPC
+#define SCMC_TMA_CAPC 576        // compile-time stage capacity of the production instantiation (C5: 552 slots); 0: always the run-time form
+#endif
+static size_t tma_smem_bytes(const scmc_handle* h, bool tc = true, int capc = 0) {
     const size_t VB = 4 * h->esz();
-    return (size_t)TMA_STAGES * (h->d / 2) * h->tma.cap * VB + (tc ? 2 : 1) * 256 * h->esz() + (2 * TMA_STAGES + TMA_TILE / 32) * 8 + TMA_RC * (4 + 2 * h->esz()) + 16;
+    return (size_t)TMA_STAGES * (h->d / 2) * (capc ? capc : h->tma.cap) * VB + (tc ? 2 : 1) * 256 * h->esz() + (2 * TMA_STAGES + TMA_TILE / 32) * 8 + TMA_RC * (4 + 2 * h->esz()) + 16;
 }
 
 // Tensor-core mat-vec variant (mode 6; auto unless SCMC_TC=0): rounding of the 16x16 mat-vec differs from the FFMA order of the other psi-gather
@@ -636,11 +669,15 @@ bool tma_pass_available(const scmc_handle* h, const SweepArgs& A) {
     if (h->z != 3 && h->z != 6) return false;
     if (A.colour_last != A.colour || A.inj_xi) return false;
     if (tma_smem_bytes(h) > 200 * 1024) return false;
+    if ((uint64_t)h->Ns * 4 * h->esz() * TMA_RC >= (1ull << 32)) return false;      // 32-bit replica offsets inside a chunk
     return h->tma.cls[A.colour].ok != 0;
 }
 
-template <int GEN, int Z, int STREAM, int HITS, bool TC>
+template <int GEN, int Z, int STREAM, int HITS, bool TC, int CAPC = 0>
 static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t stream) {
+    if constexpr (CAPC > 0) {
+        if (h->tma.cap > CAPC) return launch_one<GEN, Z, STREAM, HITS, TC, 0>(h, A, stream);
+    }
     using R = float;
     auto M = make_model_t<R>(h);
     const auto& C = h->tma.cls[A.colour];
@@ -653,10 +690,10 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
     int rc = rc_env > 0 && rc_env <= TMA_RC ? rc_env : 64;      // measured on C5: 16 -> 5.18e10, 32 -> 5.38e10, 64 -> 5.40e10, 128 -> 5.39e10 (tensor-core variant)
     while (rc > 2 && (int64_t)C.n_tiles * ((A.rcount + rc - 1) / rc) < min_ctas) rc /= 2;
     T.rc = rc;
-    const size_t smem = tma_smem_bytes(h, TC);
+    const size_t smem = tma_smem_bytes(h, TC, CAPC);
     static size_t attr_set[64] = {0};      // per device: largest dynamic shared-memory size opted into so far
     if (attr_set[h->device & 63] < smem) {
-        SCMC_CK(cudaFuncSetAttribute(k_sweep_tma_psi<R, GEN, Z, STREAM, HITS, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SCMC_CK(cudaFuncSetAttribute(k_sweep_tma_psi<R, GEN, Z, STREAM, HITS, TC, CAPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[h->device & 63] = smem;
     }
     for (int64_t y0 = 0; y0 < A.rcount; y0 += (int64_t)65535 * rc) {
@@ -664,7 +701,7 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
         B.r0 = A.r0 + y0; B.rcount = std::min<int64_t>((int64_t)65535 * rc, A.rcount - y0);
         B.Jqt = h->d_Jqt; B.Jt = h->d_Jt;
         const dim3 grid((unsigned)C.n_tiles, (unsigned)((B.rcount + rc - 1) / rc));
-        k_sweep_tma_psi<R, GEN, Z, STREAM, HITS, TC><<<grid, TMA_TILE, smem, stream>>>(M, B, T);
+        k_sweep_tma_psi<R, GEN, Z, STREAM, HITS, TC, CAPC><<<grid, TMA_TILE, smem, stream>>>(M, B, T);
         h->launches++;
     }
     SCMC_CK(cudaGetLastError());
@@ -679,7 +716,7 @@ int32_t launch_colour_pass_tma(scmc_handle* h, const SweepArgs& A, cudaStream_t 
     auto go = [&](auto gen, auto zz) -> int32_t {
         constexpr int GEN = decltype(gen)::value, Z = decltype(zz)::value;
         if (tc) {
-            if (A.hits == 2 && unroll2) return A.stream == 2 ? launch_one<GEN, Z, 2, 2, true>(h, A, stream) : launch_one<GEN, Z, 1, 2, true>(h, A, stream);
+            if (A.hits == 2 && unroll2) return A.stream == 2 ? launch_one<GEN, Z, 2, 2, true, SCMC_TMA_CAPC>(h, A, stream) : launch_one<GEN, Z, 1, 2, true>(h, A, stream);
             return A.stream == 2 ? launch_one<GEN, Z, 2, 0, true>(h, A, stream) : launch_one<GEN, Z, 1, 0, true>(h, A, stream);
         }
         if (A.hits == 2 && unroll2) return A.stream == 2 ? launch_one<GEN, Z, 2, 2, false>(h, A, stream) : launch_one<GEN, Z, 1, 2, false>(h, A, stream);

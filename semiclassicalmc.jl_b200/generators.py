@@ -222,17 +222,62 @@ def _emit_density(fname_acc, fname_map, g):
                     col[idx[(j, k, "i")]] += _term(-2 * gim[a, j, k], f"h[{a}]")
     tr = [f"template <class R> __device__ __forceinline__ void {fname_map.replace('expect_from_density', 'hq_from_field')}(const R* h, R* Hq) {{"]
     tr += [f"    Hq[{n}] = R(0){c};" for n, c in enumerate(col)] + ["}"]
-    # e(psi) = sum_n Hq[n] P_n(psi) without materialising T
+    # e(psi) = sum_n Hq[n] P_n(psi) without materialising T, evaluated row by row as psi^dagger (H psi) over the upper triangle:
+    # e = sum_j re_j A_j + im_j B_j,  A_j = Hq_jj re_j + sum_{k>j} (Hq_jk^r re_k + Hq_jk^i im_k),  B_j = Hq_jj im_j + sum_{k>j} (Hq_jk^r im_k - Hq_jk^i re_k)
+    # (d = 4: 41 instead of 51 instructions; every row is its own dependent chain)
     en = [f"template <class R> __device__ __forceinline__ R {fname_map.replace('expect_from_density', 'energy_from_state')}(const R* re, const R* im, const R* Hq) {{",
-          "    R e0 = R(0), e1 = R(0), e2 = R(0), e3 = R(0);   // four partial sums: no 16-long dependent FMA chain"]
-    for (j, k, part) in terms:
-        n = idx[(j, k, part)]
-        part_sum = f"e{n % 4}"
-        if part == "r":
-            en.append(f"    {part_sum} = fma(Hq[{n}], fma(re[{j}], re[{k}], im[{j}] * im[{k}]), {part_sum});")
-        else:
-            en.append(f"    {part_sum} = fma(Hq[{n}], fma(re[{j}], im[{k}], -(im[{j}] * re[{k}])), {part_sum});")
-    en += ["    return (e0 + e1) + (e2 + e3);", "}"]
+          "    R ea = R(0), eb = R(0);"]
+    for j in range(d):
+        a_terms, b_terms = [], []
+        if (j, j, "r") in idx:
+            a_terms.append((f"Hq[{idx[(j, j, 'r')]}]", f"re[{j}]")); b_terms.append((f"Hq[{idx[(j, j, 'r')]}]", f"im[{j}]"))
+        for k in range(j + 1, d):
+            if (j, k, "r") in idx:
+                a_terms.append((f"Hq[{idx[(j, k, 'r')]}]", f"re[{k}]")); b_terms.append((f"Hq[{idx[(j, k, 'r')]}]", f"im[{k}]"))
+            if (j, k, "i") in idx:
+                a_terms.append((f"Hq[{idx[(j, k, 'i')]}]", f"im[{k}]")); b_terms.append((f"-Hq[{idx[(j, k, 'i')]}]", f"re[{k}]"))
+        if not a_terms:
+            continue
+        for name, tl in (("A", a_terms), ("B", b_terms)):
+            expr = f"{tl[0][0]} * {tl[0][1]}"
+            for (c, x) in tl[1:]:
+                expr = f"fma({c}, {x}, {expr})"
+            en.append(f"    const R {name}{j} = {expr};")
+        en.append(f"    ea = fma(re[{j}], A{j}, ea); eb = fma(im[{j}], B{j}, eb);")
+    en += ["    return ea + eb;", "}"]
+    # FP32 overload: the same operations in the same order on (re, im) / (A_j, B_j) pairs as packed fma.rn.ftz.f32x2 (SASS FFMA2: one issue slot
+    # per two FMAs; scalar coefficients and swapped halves are operand modifiers of FFMA2, not instructions).  Half 0 carries the A chain and
+    # half 1 the B chain of the template above, each half is the IEEE operation of the scalar form => bit for bit its result.
+    full = all((j, j, "r") in idx for j in range(d)) and all((j, k, q) in idx for j in range(d) for k in range(j + 1, d) for q in "ri")
+    if full:
+        fn = fname_map.replace('expect_from_density', 'energy_from_state')
+        pk = [f"__device__ __forceinline__ float {fn}(const float* re, const float* im, const float* Hq) {{",
+              "#ifdef SCMC_SCALAR_ENERGY",
+              f"    return {fn}<float>(re, im, Hq);",
+              "#else",
+              f"    unsigned long long z[{d}], zc[{d}], e = 0ull, r, c, cn;",
+              '    asm("mov.b64 %0, {%1, %2};" : "=l"(cn) : "f"(-1.0f), "f"(1.0f));',
+              "#pragma unroll",
+              f"    for (int k = 0; k < {d}; k++) {{",
+              '        asm("mov.b64 %0, {%1, %2};" : "=l"(z[k]) : "f"(re[k]), "f"(im[k]));',
+              "        if (k) {                                   // zc = (im, -re): one packed multiply by (-1, 1), halves swapped by the consumer's operand modifier",
+              "            unsigned long long w; float wr, wi;",
+              '            asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(w) : "l"(z[k]), "l"(cn));',
+              '            asm("mov.b64 {%0, %1}, %2;" : "=f"(wr), "=f"(wi) : "l"(w));',
+              '            asm("mov.b64 %0, {%1, %2};" : "=l"(zc[k]) : "f"(wi), "f"(wr));',
+              "        }",
+              "    }"]
+        for j in range(d):
+            pk.append(f'    asm("mov.b64 %0, {{%1, %1}};" : "=l"(c) : "f"(Hq[{idx[(j, j, "r")]}]));')
+            pk.append(f'    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(c), "l"(z[{j}]));')
+            for k in range(j + 1, d):
+                pk.append(f'    asm("mov.b64 %0, {{%1, %1}};" : "=l"(c) : "f"(Hq[{idx[(j, k, "r")]}]));')
+                pk.append(f'    asm("fma.rn.ftz.f32x2 %0, %1, %2, %0;" : "+l"(r) : "l"(c), "l"(z[{k}]));')
+                pk.append(f'    asm("mov.b64 %0, {{%1, %1}};" : "=l"(c) : "f"(Hq[{idx[(j, k, "i")]}]));')
+                pk.append(f'    asm("fma.rn.ftz.f32x2 %0, %1, %2, %0;" : "+l"(r) : "l"(c), "l"(zc[{k}]));')
+            pk.append(f'    asm("fma.rn.ftz.f32x2 %0, %1, %2, %0;" : "+l"(e) : "l"(z[{j}]), "l"(r));')
+        pk += ["    float ea, eb;", '    asm("mov.b64 {%0, %1}, %2;" : "=f"(ea), "=f"(eb) : "l"(e));', "    return ea + eb;", "#endif", "}"]
+        en += pk
     return acc + mp + tr + en, len(terms)
 
 
