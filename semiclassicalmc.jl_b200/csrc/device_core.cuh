@@ -222,6 +222,36 @@ __device__ __forceinline__ void stream_v2_uniform_words(uint64_t seed, uint32_t 
     philox4x32<7>(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
     w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
 }
+// The same two calls with the round keys k0 + r W0, k1 + r W1 (r = 0..6) precomputed on the host: passed in the kernel parameters they are
+// constant-bank operands of the xor instead of 12 uniform adds per site visit.  Same words as stream_v2_normals / stream_v2_uniform_words.
+struct PhiloxKeys7 { uint32_t k[14]; };
+static inline PhiloxKeys7 philox_keys7(uint64_t seed) {
+    PhiloxKeys7 K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 7; r++) { K.k[2 * r] = k0; K.k[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return K;
+}
+__device__ __forceinline__ void philox4x32_7_rk(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, const PhiloxKeys7& K) {
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo(0xD2511F53u, c0, hi0, lo0);
+        mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+        c0 = hi1 ^ c1 ^ K.k[2 * r]; c2 = hi0 ^ c3 ^ K.k[2 * r + 1];
+        c1 = lo1; c3 = lo0;
+    }
+}
+template <class R>
+__device__ __forceinline__ void stream_v2_normals_d4(const PhiloxKeys7& K, uint32_t site, uint32_t replica, uint64_t visit, R* xr, R* xi) {
+    uint32_t c0 = site, c1 = replica, c2 = (uint32_t)visit, c3 = (uint32_t)(visit >> 32) << 4;
+    philox4x32_7_rk(c0, c1, c2, c3, K);
+    box_muller16(c0, xr[0], xi[0]); box_muller16(c1, xr[1], xi[1]); box_muller16(c2, xr[2], xi[2]); box_muller16(c3, xr[3], xi[3]);
+}
+__device__ __forceinline__ void stream_v2_uniform_words(const PhiloxKeys7& K, uint32_t site, uint32_t replica, uint64_t group, uint32_t* w) {
+    uint32_t c0 = site, c1 = replica, c2 = (uint32_t)group, c3 = ((uint32_t)(group >> 32) << 4) | 8u;
+    philox4x32_7_rk(c0, c1, c2, c3, K);
+    w[0] = c0; w[1] = c1; w[2] = c2; w[3] = c3;
+}
 __device__ __forceinline__ uint32_t pick_word(const uint32_t* w, uint32_t i) { return i == 0 ? w[0] : i == 1 ? w[1] : i == 2 ? w[2] : w[3]; }
 // one update's numbers as a pure function of (seed, site, replica, visit) -- the form the kernels without a cached uniform call use
 template <class R, int D>

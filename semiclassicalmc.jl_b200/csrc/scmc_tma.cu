@@ -267,6 +267,7 @@ struct TmaArgs {
     const uint2* runs;       // [tiles][TMA_MAX_RUNS]
     const int32_t* tile;     // [tiles][4]
     int32_t first, cap, rc;  // first tile of the class, slots per plane and stage, replicas per CTA
+    PhiloxKeys7 rk;          // round keys of random stream v2 for A.seed
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -520,8 +521,8 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
             uint32_t tc_dep = 0;
             if constexpr (PRE) {
 #pragma unroll
-                for (int hit = 0; hit < 2; hit++) stream_v2_normals<R, D>(A.seed, site, (uint32_t)(A.roff + r), A.visit0 + hit, pxr[hit], pxi[hit]);
-                stream_v2_uniform_words(A.seed, site, (uint32_t)(A.roff + r), A.visit0 >> 2, uw);
+                for (int hit = 0; hit < 2; hit++) stream_v2_normals_d4<R>(T.rk, site, (uint32_t)(A.roff + r), A.visit0 + hit, pxr[hit], pxi[hit]);
+                stream_v2_uniform_words(T.rk, site, (uint32_t)(A.roff + r), A.visit0 >> 2, uw);
                 // ptxas would hoist the (possibly suspending) try_wait above this arithmetic: make the wait's parity operand depend on the
                 // last numbers computed, through a mask that is zero at run time but not at compile time (tile indices are non-negative)
                 tc_dep = uw[3];
@@ -684,6 +685,7 @@ static int32_t launch_one(scmc_handle* h, const SweepArgs& A, cudaStream_t strea
     TmaArgs T;
     T.meta = (const uint4*)h->tma.d_meta; T.runs = (const uint2*)h->tma.d_runs; T.tile = h->tma.d_tile;
     T.first = C.first; T.cap = h->tma.cap;
+    T.rk = philox_keys7(A.seed);
     // replicas per CTA: up to 64, fewer when that leaves the chip with less than about one wave of CTAs (small shards).  Measured (bench.py, sustained):
     // a threshold of 650 against 3000 CTAs per launch: 256 replicas 4.74 against 4.28e10, 1024 replicas (the 8-GPU shard) 5.21 against 4.94e10, 8192 equal
     const int rc_env = getenv("SCMC_TMA_RC") ? atoi(getenv("SCMC_TMA_RC")) : 0, min_ctas = getenv("SCMC_TMA_MINCTAS") ? atoi(getenv("SCMC_TMA_MINCTAS")) : 650;       // (read per launch: tests switch them)
