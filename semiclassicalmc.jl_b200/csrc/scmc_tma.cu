@@ -221,6 +221,16 @@ constexpr int TC_TMEM_COLS = SCMC_TC_PIPE ? 32 : 64, TC_TMEM_ALLOCS = SCMC_TC_PI
 #ifndef SCMC_TC_BLOCKS
 #define SCMC_TC_BLOCKS 5         // CTAs per SM the tensor-core variant is compiled for
 #endif
+#ifndef SCMC_TC_REFILL_LATE
+#define SCMC_TC_REFILL_LATE 1    // tensor-core variant: warp 0 waits for the stage's release and issues the refill after its tcgen05.st, not before
+#endif
+#ifndef SCMC_TC_ISSUER
+#define SCMC_TC_ISSUER 1         // warp that issues the MMAs of a tile visit (warp 0 carries the stage refills)
+#endif
+#ifndef SCMC_TC_LAST
+#define SCMC_TC_LAST 0           // 1: the warp that stores its rows LAST issues the MMAs of the tile visit (ticket from a shared-memory atomic: nobody waits on an
+#endif                           //    "A stored" barrier and no fixed warp has its own work serialised behind the rendezvous); 0: warp 1 waits for all four and issues.
+                                 //    Measured on C5 (same box): 6.00-6.03e10 burst / 5.71e10 sustained against 6.15e10 / 5.85e10 for 0 -- the atomic's round trip sits in every warp's path
 
 // Packed density sums of the tensor-core variant (d = 4; basis order of gen::density_acc_g1 / _g3): with the pairs c_m = (re_m, im_m) as they come out
 // of the 128-bit loads, c_m * c_m = (re_m^2, im_m^2), c_m * c_n = (re_m re_n, im_m im_n) and c_m * swap(c_n) = (re_m im_n, im_m re_n) are one
@@ -289,6 +299,7 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
     R* sSigma = sBeta + TMA_RC;
     __shared__ int s_nit;
     __shared__ uint32_t s_tmem[4];
+    __shared__ uint32_t s_ticket;                                  // SCMC_TC_LAST: warps that have stored their rows, over all visits of this CTA
     static_assert(!TC || (std::is_same<R, float>::value && D == 4), "tensor-core mat-vec: FP32, d = 4");
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -350,6 +361,7 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
         }
         if (lane == 0) {
             s_nit = n_alive;
+            s_ticket = 0;
 #pragma unroll
             for (int s = 0; s < TMA_STAGES; s++) { mbar_init(smem_u32(bars + s), 1); mbar_init(smem_u32(bars + TMA_STAGES + s), TMA_TILE / 32); }
             if (TC)
@@ -406,6 +418,15 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
     constexpr bool PRE = TC && HITS == 2 && STREAM == 2 && SCMC_TC_PRE;    // both hits' random numbers are generated while the tensor core works
     constexpr bool PIPE = TC && SCMC_TC_PIPE;                              // the MMAs of visit it + 1 are in flight during the hits of visit it
 
+    // ---- warp 0: once all four warps have released the stage of replica `it`, refill it with the states of replica it + STAGES.  The copies have two
+    //      visits of slack, the wait for the slowest warp does not: in the tensor-core variant it runs AFTER this warp's rows are in tensor memory
+    //      (SCMC_TC_REFILL_LATE), otherwise the other three warps' MMA waits for warp 0, which waits for them
+    auto refill = [&](int it) {
+        if (SCMC_TMA_ABLATE != 4 && warp == 0 && it + TMA_STAGES < n_it) {
+            mbar_wait(bar0 + 8 * (TMA_STAGES + it % TMA_STAGES), (uint32_t)(it / TMA_STAGES) & 1u);
+            issue(it + TMA_STAGES, it % TMA_STAGES);
+        }
+    };
     // ---- front half of a visit: wait for the stage, own state -> re / im, density sums of the neighbours -> P, release the stage, (warp 0) refill it
     auto gather = [&](int it, R* re, R* im, R* P) {
         const int s = it % TMA_STAGES;
@@ -467,13 +488,10 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
         // this warp is done with the stage: release it; warp 0 refills it with the states of replica it + STAGES once all warps have
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + 8 * (TMA_STAGES + s));
-        if (SCMC_TMA_ABLATE != 4 && warp == 0 && it + TMA_STAGES < n_it) {
-            mbar_wait(bar0 + 8 * (TMA_STAGES + s), parity);
-            issue(it + TMA_STAGES, s);
-        }
+        if constexpr (!(TC && SCMC_TC_REFILL_LATE)) refill(it);
     };
     // ---- tensor-core mat-vec, part 1: this thread's 16 sums, split into TF32 head and tail, to its lane of A buffer `buf`; arrive on "A stored"
-    auto tc_store = [&](const R* P, int buf) {
+    auto tc_store = [&](const R* P, int buf) -> bool {
         uint32_t hi[NG], lo[NG];
 #pragma unroll
         for (int t = 0; t < NG; t++) {
@@ -485,12 +503,22 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tc_bar0 + 16 + 8 * buf);
+        if constexpr (SCMC_TC_LAST && !SCMC_TC_PIPE) {
+            // every warp takes one ticket per visit (a warp cannot reach the next visit's store before this visit's result has been read, which needs all
+            // four stores): the warp holding ticket 3 (mod 4) arrived last; acq_rel orders the other warps' tensor-memory stores before its MMAs
+            uint32_t t = 0;
+            if (lane == 0) asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(t) : "r"(smem_u32(&s_ticket)) : "memory");
+            t = __shfl_sync(0xffffffffu, t, 0);
+            return (t & 3u) == 3u;
+        } else {
+            if (lane == 0) mbar_arrive(tc_bar0 + 16 + 8 * buf);
+            return false;
+        }
     };
     // ---- part 2 (warp 1; warp 0 carries the stage refills): once all four warps have stored their rows of visit `it`, one elected thread issues
     //      P_lo Jq_hi + P_hi Jq_lo + P_hi Jq_hi into D buffer `buf` and commits to "D ready"
     auto tc_issue = [&](int it, int buf) {
-        mbar_wait(tc_bar0 + 16 + 8 * buf, (uint32_t)(PIPE ? it >> 1 : it) & 1u);
+        if constexpr (!(SCMC_TC_LAST && !SCMC_TC_PIPE)) mbar_wait(tc_bar0 + 16 + 8 * buf, (uint32_t)(PIPE ? it >> 1 : it) & 1u);
         if (elect_one()) {                                      // elect.sync: ptxas then emits the MMAs straight, without a loop over the active lanes
             tc_fence_after();
             constexpr uint32_t KS = (2 * TC_LBO) >> 4;          // descriptor step of one K = 8 slice
@@ -598,6 +626,7 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
             gather(0, re, im, P);
             tc_store(P, 0);
             if (warp == 1) tc_issue(0, 0);
+            if constexpr (SCMC_TC_REFILL_LATE) refill(0);
         }
         for (int it = 0; it < n_it; it++) {
             R nre[D], nim[D];
@@ -606,6 +635,7 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
                 R P[NP];
                 gather(it + 1, nre, nim, P);
                 tc_store(P, (it + 1) & 1);
+                if constexpr (SCMC_TC_REFILL_LATE) refill(it + 1);
             }
             finish_visit(it, re, im, nullptr, more ? it + 1 : -1);
 #pragma unroll
@@ -616,8 +646,9 @@ __global__ void __launch_bounds__(TMA_TILE, TC ? SCMC_TC_BLOCKS : SCMC_TMA_BLOCK
             R re[D], im[D], P[NP];
             gather(it, re, im, P);
             if constexpr (TC) {
-                tc_store(P, 0);
-                if (warp == 1) tc_issue(it, 0);
+                const bool last = tc_store(P, 0);
+                if (SCMC_TC_LAST ? last : warp == (SCMC_TC_ISSUER < 0 ? 1 + it % 3 : SCMC_TC_ISSUER)) tc_issue(it, 0);
+                if constexpr (SCMC_TC_REFILL_LATE) refill(it);
             }
             finish_visit(it, re, im, P, -1);
         }
@@ -647,7 +678,7 @@ static DevModel<R, 1> make_model_t(const scmc_handle* h) {
 }
 
 #ifndef SCMC_TMA_CAPC
-#define SCMC_TMA_CAPC 576        // compile-time stage capacity of the production instantiation (C5: 552 slots); 0: always the run-time form
+#define SCMC_TMA_CAPC 640        // compile-time stage capacity of the production instantiation (C5: 624 slots; 5 CTAs of 45.8 KB per SM); 0: always the run-time form
 #endif
 static size_t tma_smem_bytes(const scmc_handle* h, bool tc = true, int capc = 0) {
     const size_t VB = 4 * h->esz();
