@@ -146,6 +146,11 @@ void plan_tma(scmc_handle* h, const std::vector<int32_t>& col_list, const std::v
     }
     h->bytes += (int64_t)(meta.size() + runs.size() + info.size()) * 4;
     P.ready = 1;
+    if (getenv("SCMC_TMA_DEBUG")) {
+        size_t slots = 0, nr = 0;
+        for (auto& T : tiles) { slots += T.slots; nr += T.nruns; }
+        fprintf(stderr, "scmc tile plan: %zu tiles, stage capacity %d slots, %.1f staged states and %.2f runs per tile on average, gap %d\n", nt, P.cap, (double)slots / nt, (double)nr / nt, TMA_GAP);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ mbarrier / bulk-copy primitives
