@@ -754,7 +754,10 @@ int32_t launch_colour_pass_tma(scmc_handle* h, const SweepArgs& A, cudaStream_t 
     auto go = [&](auto gen, auto zz) -> int32_t {
         constexpr int GEN = decltype(gen)::value, Z = decltype(zz)::value;
         if (tc) {
-            if (A.hits == 2 && unroll2) return A.stream == 2 ? launch_one<GEN, Z, 2, 2, true, SCMC_TMA_CAPC>(h, A, stream) : launch_one<GEN, Z, 1, 2, true>(h, A, stream);
+            // SCMC_TMA_FIXCAP=0 (read per launch: a test switches it): the run-time-capacity instantiation also where the compile-time one applies (same chain)
+            const bool fixcap = !(getenv("SCMC_TMA_FIXCAP") && atoi(getenv("SCMC_TMA_FIXCAP")) == 0);
+            if (A.hits == 2 && unroll2 && A.stream == 2 && fixcap) return launch_one<GEN, Z, 2, 2, true, SCMC_TMA_CAPC>(h, A, stream);
+            if (A.hits == 2 && unroll2) return A.stream == 2 ? launch_one<GEN, Z, 2, 2, true>(h, A, stream) : launch_one<GEN, Z, 1, 2, true>(h, A, stream);
             return A.stream == 2 ? launch_one<GEN, Z, 2, 0, true>(h, A, stream) : launch_one<GEN, Z, 1, 0, true>(h, A, stream);
         }
         if (A.hits == 2 && unroll2) return A.stream == 2 ? launch_one<GEN, Z, 2, 2, false>(h, A, stream) : launch_one<GEN, Z, 1, 2, false>(h, A, stream);

@@ -836,6 +836,24 @@ def test_tma_pipelined_kernel_is_bit_identical(scmc, case, stream):
     a.close(); b.close()
 
 
+@pytest.mark.gpu
+def test_compile_time_stage_capacity_is_the_same_chain(scmc, monkeypatch):
+    """The production instantiation of the tensor-core TMA kernel has its stage capacity at compile time (640 slots: strides are immediates of the
+    shared-memory loads); lattices whose tile plan needs more fall back to the run-time form.  Both must realise the same chain bit for bit
+    (SCMC_TMA_FIXCAP=0 forces the run-time form where the compile-time one applies)."""
+    R = 21
+    mk = lambda: scmc.initializeCfg("nearest-neighbor", "triangular", [NOTEBOOK_J], 128, 1, n_replicas=R, precision=32, seed=99, replica_offset=2, stream=2)
+    beta = np.geomspace(0.5, 50.0, R); sigma = np.geomspace(0.8, 0.03, R)
+    a = mk(); a.set_sweep_mode(6)
+    acc_a, _ = a.sweep(3, beta, sigma, hits=2)
+    monkeypatch.setenv("SCMC_TMA_FIXCAP", "0")
+    b = mk(); b.set_sweep_mode(6)
+    acc_b, _ = b.sweep(3, beta, sigma, hits=2)
+    monkeypatch.delenv("SCMC_TMA_FIXCAP")
+    assert np.array_equal(acc_a, acc_b) and np.array_equal(a.get_state(), b.get_state()) and acc_a.min() > 0
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("case", [
     ("triangular", 128, 37, 1),  # BASELINE C5 lattice, ragged replica chunks
     ("triangular", 48, 19, 1),   # L % 3 == 0
