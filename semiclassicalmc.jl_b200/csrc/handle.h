@@ -90,6 +90,8 @@ struct scmc_handle {
     int32_t lab_off[scmc::MAXL + 1] = {0};
     bool label_major = false;
     bool fused_density = false;                  // psi kernels go straight from density sums to energy coefficients (d_Jqt valid)
+    int32_t n_fwd = 0;                           // one label: number of "forward" neighbour slots (z / 2) such that every bond i-j appears exactly once as (i, slot in fwd_slot)
+    uint8_t fwd_slot[8] = {0};                   //            -- the energy measurement sums each bond once instead of twice (0: no such set, all slots with a factor 1/2)
     bool psi_labels = false;                     // several labels, d = 4, label-major slots: the psi-gather family is available through k_sweep_colour_psi_nl (d_Jqt holds one table per label)
     unsigned long long* acc = nullptr;           // [R] accepted-update counters
     uint8_t* active = nullptr;                   // [R] replica still running (annealing) -- nullptr semantics handled by callers

@@ -971,7 +971,7 @@ __global__ void __launch_bounds__(SCMC_MEASURE_THREADS, sizeof(R) == 8 ? 2 : 4) 
 // leaves NG + 1 FP64 partial sums, k_measure_finish adds them in a fixed order (deterministic) and writes the measure! row.
 // On the fused path (16 density entries, no on-site term) the partial sums are density sums; T = C . P is applied once at the end.
 template <class R, int GEN, bool ONSITE>
-__global__ void __launch_bounds__(SCMC_MEASURE_THREADS, sizeof(R) == 8 ? 3 : 5) k_measure_psi(const __grid_constant__ DevModel<R, 1> M, const void* Jt_, const void* Jqt_, double* partial) {
+__global__ void __launch_bounds__(SCMC_MEASURE_THREADS, sizeof(R) == 8 ? 3 : 5) k_measure_psi(const __grid_constant__ DevModel<R, 1> M, const void* Jt_, const void* Jqt_, double* partial, const int n_fwd, const uint64_t fwd_slots) {
     constexpr int D = GenOps<GEN>::D, NPV = D / 2, NP = GenOps<GEN>::NDENS;
     const int64_t r = blockIdx.y;
     __shared__ __align__(16) R sJt[NG * NG];
@@ -1001,11 +1001,17 @@ __global__ void __launch_bounds__(SCMC_MEASURE_THREADS, sizeof(R) == 8 ? 3 : 5) 
 #pragma unroll
         for (int t = 0; t < NP; t++) P[t] = R(0);
         const int32_t* nb = M.nbr + p;
+        // forward slots only (n_fwd > 0, fused path): every bond is summed once, from the end that holds it in a forward slot, instead of twice with a factor 1/2
+        const bool fwd = fused && n_fwd > 0;
+        const int kz = fwd ? n_fwd : M.z;
 #pragma unroll 2
-        for (int k = 0; k < M.z; k += 3) {
+        for (int k = 0; k < kz; k += 3) {
             unsigned j[3];
 #pragma unroll
-            for (int t = 0; t < 3; t++) j[t] = (unsigned)nb[(unsigned)(k + t) * stride];
+            for (int t = 0; t < 3; t++) {
+                const unsigned slot = fwd ? (unsigned)(fwd_slots >> (8 * (k + t))) & 0xFFu : (unsigned)(k + t);
+                j[t] = (fwd && k + t >= n_fwd) ? (unsigned)M.N : (unsigned)nb[slot * stride];      // beyond the set: the all-zero padding site
+            }
             vec4<R> v[3][NPV];
 #pragma unroll
             for (int t = 0; t < 3; t++)
@@ -1039,7 +1045,7 @@ __global__ void __launch_bounds__(SCMC_MEASURE_THREADS, sizeof(R) == 8 ? 3 : 5) 
             for (int t = 0; t < NG; t++) macc[t] += T[t];
         } else if constexpr (NP == NG) {
             field_from_sums_smem<1>(sJt, (const R(*)[NG])P, h);           // h = Hq
-            eacc += 0.5 * (double)GenOps<GEN>::energy_from_state(re, im, h);
+            eacc += (fwd ? 1.0 : 0.5) * (double)GenOps<GEN>::energy_from_state(re, im, h);
             R Pown[NP];
 #pragma unroll
             for (int t = 0; t < NP; t++) Pown[t] = R(0);
@@ -1584,7 +1590,10 @@ int32_t launch_measure(scmc_handle* h, double* d_rows, double* d_Etot) {
             if constexpr (NL == 1) {
                 if (psi) {
                     fused = h->fused_density && !ONS && GenOps<GEN>::NDENS == NG;
-                    k_measure_psi<R, GEN, ONS><<<grid, SCMC_MEASURE_THREADS, 0, h->stream>>>(My, h->d_Jt, fused ? h->d_Jqt : nullptr, part);
+                    uint64_t fs = 0;
+                    for (int t = 0; t < h->n_fwd && t < 8; t++) fs |= (uint64_t)h->fwd_slot[t] << (8 * t);
+                    const bool fwd_off = getenv("SCMC_MEASURE_FWD") && atoi(getenv("SCMC_MEASURE_FWD")) == 0;      // (read per call: a test switches it)
+                    k_measure_psi<R, GEN, ONS><<<grid, SCMC_MEASURE_THREADS, 0, h->stream>>>(My, h->d_Jt, fused ? h->d_Jqt : nullptr, part, fwd_off ? 0 : h->n_fwd, fs);
                     launched = true;
                 }
             }
@@ -1696,6 +1705,35 @@ int32_t scmc_create(scmc_t** out, int32_t device, int32_t precision, int64_t n_s
     h->z = (z_max + 2) / 3 * 3;           // neighbour slots padded to a multiple of 3 (chunked loads)
     for (int l = 0; l < n_labels; l++) memcpy(h->J[l], J + (size_t)l * 256, sizeof(double) * 256);
     memcpy(h->K, K, sizeof(double) * 16);
+    // One label (J = J^T by the check above): look for z / 2 "forward" slots such that every bond i-j sits in a forward slot at exactly one of its
+    // ends (Bravais lattices: three of the six directions).  The energy measurement then gathers half the neighbours (k_measure_psi).
+    if (n_labels == 1 && z_max % 2 == 0 && z_max >= 2 && z_max <= 8) {
+        std::vector<int8_t> rev((size_t)N * z_max, -1);      // slot of the reverse bond at the neighbour, -2: ambiguous (double bond)
+        bool simple = true;
+        for (int64_t i = 0; i < N && simple; i++)
+            for (int k = 0; k < z_max; k++) {
+                const int32_t j = nbr_site[i * z_max + k];
+                if (j < 0) { simple = false; break; }      // a missing bond moves the later bonds of that site to other device slots: keep all slots
+                int found = -1, cnt = 0;
+                for (int k2 = 0; k2 < z_max; k2++)
+                    if (nbr_site[(int64_t)j * z_max + k2] == i) { found = k2; cnt++; }
+                if (cnt != 1) { simple = false; break; }
+                rev[i * z_max + k] = (int8_t)found;
+            }
+        for (unsigned mask = 0; simple && mask < (1u << z_max) && h->n_fwd == 0; mask++) {
+            if (__builtin_popcount(mask) != z_max / 2) continue;
+            bool ok = true;
+            for (int64_t i = 0; i < N && ok; i++)
+                for (int k = 0; k < z_max; k++) {
+                    if (nbr_site[i * z_max + k] < 0) continue;
+                    if (((mask >> k) & 1u) == ((mask >> rev[i * z_max + k]) & 1u)) { ok = false; break; }
+                }
+            if (ok) {
+                for (int k = 0; k < z_max; k++)
+                    if ((mask >> k) & 1u) h->fwd_slot[h->n_fwd++] = (uint8_t)k;
+            }
+        }
+    }
     bool anyK = false;
     double sumK = 0.0;
     for (int a = 0; a < 16; a++) { anyK |= (K[a] != 0.0); sumK += K[a]; }

@@ -836,6 +836,28 @@ def test_tma_pipelined_kernel_is_bit_identical(scmc, case, stream):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("lattice,L,n", [("triangular", 12, 1), ("triangular", 128, 1), ("square", 16, 1), ("honeycomb", 8, 1), ("triangular", 9, 3)])
+@pytest.mark.parametrize("precision", [64, 32])
+def test_forward_bond_measurement_equals_the_full_sum(scmc, oracle_mod, monkeypatch, lattice, L, n, precision):
+    """One coupling label (J = J^T): scmc_create looks for z / 2 "forward" neighbour slots that hold every bond at exactly one of its ends (three of
+    the six directions of the triangular lattice, two of four on the square lattice; none on the honeycomb lattice, whose sublattices differ), and
+    the psi-family measurement then sums each bond once instead of twice with a factor 1/2 (getEnergy, src/Configuration.jl:236-253).  Same
+    energies and magnetisation as the full sum (SCMC_MEASURE_FWD=0), and as the oracle on a small lattice."""
+    R = 5
+    cfg = scmc.initializeCfg("nearest-neighbor", lattice, [random_symmetric_J(21)], L, n, n_replicas=R, precision=precision, seed=31)
+    tol = 1e-12 if precision == 64 else 2e-6
+    rows = cfg.measure().copy(); e = cfg.energies().copy()
+    monkeypatch.setenv("SCMC_MEASURE_FWD", "0")
+    rows0 = cfg.measure().copy(); e0 = cfg.energies().copy()
+    monkeypatch.delenv("SCMC_MEASURE_FWD")
+    assert np.allclose(e, e0, rtol=tol, atol=tol * cfg.nSites) and np.allclose(rows, rows0, rtol=tol, atol=tol)
+    assert np.array_equal(rows[:, 5:], rows0[:, 5:])                      # the magnetisation sums do not depend on the bond set
+    if cfg.nSites <= 200:
+        o = make_oracle(cfg, oracle_mod, replica=2)
+        assert abs(o.energy() - e[2]) < (1e-10 if precision == 64 else 2e-5) * cfg.nSites
+    cfg.close()
+
+
 @pytest.mark.gpu
 def test_compile_time_stage_capacity_is_the_same_chain(scmc, monkeypatch):
     """The production instantiation of the tensor-core TMA kernel has its stage capacity at compile time (640 slots: strides are immediates of the
